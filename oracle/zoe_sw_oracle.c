@@ -1,0 +1,800 @@
+/*
+ * zoe_sw_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, CPU-only, literal restatement of CDCgov/zoe's striped
+ * Smith-Waterman hot path.  It exists only so that tests/, the smoke test and
+ * bench.py's cpu_baseline leg can check the CUDA library against it.  Nothing
+ * under zoe_b200/ may call into this file.
+ *
+ * zoe itself is Rust (nightly, portable_simd) and cannot be built in this
+ * image (no rustc/cargo), so this is a restatement ("port"), pinned against
+ * every known-answer test zoe's own test-suite holds for the path
+ * (tests/test_oracle_golden.py).  BLOSUM62 / S=25 and the
+ * i32 tier have no known-answer test in zoe: for those the pin is
+ * striped == scalar agreement only.
+ *
+ * Each function cites the reference file:line it follows (paths relative to
+ * the zoe repository root).
+ *
+ * Conventions: the *profiled* sequence P (length m) is striped into the
+ * profile and indexes DP columns c; the *streamed* sequence R (length n,
+ * zoe's `reference: &[u8]` argument) indexes DP rows r.  A SIMD vector of N
+ * lanes is an int32_t[N]; element type T in {i8,i16,i32,u8,u16,u32} is
+ * emulated with explicit saturation to [MIN,MAX].
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ZO_SOME 0
+#define ZO_OVERFLOWED 1
+#define ZO_UNMAPPED 2
+
+/* ProfileError codes (src/alignment/errors.rs:6-15) */
+#define ZO_ERR_EMPTY_SEQUENCE -1
+#define ZO_ERR_GAP_OPEN_RANGE -2
+#define ZO_ERR_GAP_EXTEND_RANGE -3
+#define ZO_ERR_BAD_GAP_WEIGHTS -4
+#define ZO_ERR_BAD_ARG -5
+#define ZO_ERR_CIGAR_CAP -6
+
+/* flag bits: src/alignment/types/backtrack.rs:18-34 */
+#define F_UP 1
+#define F_UP_EXT 2
+#define F_LEFT 4
+#define F_LEFT_EXT 8
+#define F_STOP 16
+
+typedef struct {
+    const int8_t *weights; /* S*S row-major, weights[ref_idx][query_idx] (matrices/mod.rs:230-235) */
+    int S;
+    const uint8_t *map; /* 256-entry byte -> index (byte_index.rs:331-333) */
+    int gap_open;       /* as given: -127..=0 */
+    int gap_extend;
+} zo_scoring;
+
+typedef struct {
+    uint32_t score;
+    uint64_t ref_start, ref_end;     /* 0-based half-open */
+    uint64_t query_start, query_end; /* 0-based half-open */
+    uint64_t ref_len, query_len;
+    uint32_t n_ops;
+} zo_alignment;
+
+/* ---- src/alignment/profile.rs:32-44 validate_profile_args ---- */
+int zo_validate_profile_args(uint64_t seq_len, int gap_open, int gap_extend) {
+    if (seq_len == 0) return ZO_ERR_EMPTY_SEQUENCE;
+    if (gap_open < -127 || gap_open > 0) return ZO_ERR_GAP_OPEN_RANGE;
+    if (gap_extend < -127 || gap_extend > 0) return ZO_ERR_GAP_EXTEND_RANGE;
+    if (gap_extend < gap_open) return ZO_ERR_BAD_GAP_WEIGHTS;
+    return 0;
+}
+
+/* ---- element type emulation (src/math/integer.rs:17-125, data/extension/simd.rs:9-87) ---- */
+typedef struct {
+    int64_t min, max;
+    int is_signed;
+} zo_type;
+
+static int zo_make_type(int bits, int is_signed, zo_type *t) {
+    if (bits != 8 && bits != 16 && bits != 32) return ZO_ERR_BAD_ARG;
+    t->is_signed = is_signed;
+    if (is_signed) {
+        t->min = -((int64_t)1 << (bits - 1));
+        t->max = ((int64_t)1 << (bits - 1)) - 1;
+    } else {
+        t->min = 0;
+        t->max = ((int64_t)1 << bits) - 1;
+    }
+    return 0;
+}
+
+static inline int64_t sat(const zo_type *t, int64_t x) { return x < t->min ? t->min : (x > t->max ? t->max : x); }
+
+/* ---- striped profile: src/alignment/profile.rs:198-207, new_unchecked :270-306 ---- */
+typedef struct {
+    zo_type t;
+    int N, S, nv;
+    uint64_t seq_len;
+    int64_t *profile; /* [S*nv][N] */
+    int64_t gap_open, gap_extend, bias; /* positive, as T (profile.rs:300-301) */
+    const uint8_t *map;
+} zo_profile;
+
+static void zo_profile_free(zo_profile *p) {
+    free(p->profile);
+    p->profile = NULL;
+}
+
+/* to_biased_matrix (matrices/mod.rs:455-491): bias = |min(0, min weight)|, w' = w - min */
+static int zo_bias_of(const zo_scoring *sc) {
+    int mn = 0;
+    for (int i = 0; i < sc->S * sc->S; i++)
+        if (sc->weights[i] < mn) mn = sc->weights[i];
+    return -mn;
+}
+
+static int zo_profile_new(zo_profile *p, const uint8_t *seq, uint64_t m, const zo_scoring *sc, int bits, int is_signed,
+                          int lanes) {
+    int rc = zo_validate_profile_args(m, sc->gap_open, sc->gap_extend);
+    if (rc) return rc;
+    if (lanes < 1 || zo_make_type(bits, is_signed, &p->t)) return ZO_ERR_BAD_ARG;
+    p->N = lanes;
+    p->S = sc->S;
+    p->map = sc->map;
+    p->seq_len = m;
+    p->nv = (int)((m + (uint64_t)lanes - 1) / (uint64_t)lanes); /* div_ceil, profile.rs:275 */
+    int64_t bias = is_signed ? 0 : zo_bias_of(sc);
+    p->bias = bias;
+    uint64_t total_lanes = (uint64_t)lanes * (uint64_t)p->nv;
+    p->profile = (int64_t *)malloc(sizeof(int64_t) * (size_t)sc->S * p->nv * lanes);
+    if (!p->profile) return ZO_ERR_BAD_ARG;
+    for (int v = 0; v < p->nv; v++) {
+        for (int ref_index = 0; ref_index < sc->S; ref_index++) {
+            int64_t *vec = p->profile + ((size_t)ref_index * p->nv + v) * lanes;
+            int i = 0;
+            for (uint64_t q = (uint64_t)v; q < total_lanes; q += (uint64_t)p->nv, i++) { /* profile.rs:285 */
+                if (q < m) {
+                    int query_index = sc->map[seq[q]];
+                    vec[i] = (int64_t)sc->weights[ref_index * sc->S + query_index] + bias;
+                } else {
+                    vec[i] = bias; /* padding lanes hold the bias, profile.rs:279-284 */
+                }
+            }
+        }
+    }
+    p->gap_open = -sc->gap_open;
+    p->gap_extend = -sc->gap_extend;
+    return 0;
+}
+
+/* ---- src/alignment/sw/striped.rs:608-633 score_to_maybe_aligned ---- */
+static int zo_score_to_maybe_aligned(const zo_profile *p, int64_t best, uint32_t *score) {
+    const zo_type *t = &p->t;
+    if (t->is_signed) {
+        if (!(best < t->max)) return ZO_OVERFLOWED;
+        *score = (uint32_t)((uint64_t)(t->max + 1) + (uint64_t)best); /* wrapping_add_signed */
+    } else {
+        /* best.checked_add(bias + 1) */
+        if (best + p->bias + 1 > t->max) return ZO_OVERFLOWED;
+        *score = (uint32_t)best;
+    }
+    if (*score == 0) return ZO_UNMAPPED;
+    return ZO_SOME;
+}
+
+/* shift_elements_right::<1>(fill): lane i <- lane i-1, lane 0 <- fill */
+static inline void shr(int64_t *dst, const int64_t *src, int N, int64_t fill) {
+    for (int i = N - 1; i > 0; i--) dst[i] = src[i - 1];
+    dst[0] = fill;
+}
+
+/* ---- src/alignment/sw/striped.rs:65-142 sw_simd_score ---- */
+static int zo_striped_score_profile(const zo_profile *p, const uint8_t *reference, uint64_t n, uint32_t *score) {
+    const zo_type *t = &p->t;
+    const int N = p->N, nv = p->nv;
+    const int64_t min = t->min, go = p->gap_open, ge = p->gap_extend, bias = p->bias;
+    size_t vsz = (size_t)nv * N;
+    int64_t *buf = (int64_t *)malloc(sizeof(int64_t) * (3 * vsz + 4 * (size_t)N));
+    int64_t *load = buf, *store = buf + vsz, *e_scores = buf + 2 * vsz;
+    int64_t *max_scores = buf + 3 * vsz, *F = max_scores + N, *H = F + N, *tmp = H + N;
+    for (size_t i = 0; i < 3 * vsz + 4 * (size_t)N; i++) buf[i] = min;
+
+    for (uint64_t r = 0; r < n; r++) {
+        int ref_index = p->map[reference[r]];
+        for (int i = 0; i < N; i++) F[i] = min;
+        shr(H, store + (size_t)(nv - 1) * N, N, min); /* :87 */
+        int64_t *sw = load;
+        load = store;
+        store = sw; /* :89 */
+        const int64_t *scores_vec = p->profile + (size_t)ref_index * nv * N;
+        for (int j = 0; j < nv; j++) { /* :94-113 */
+            int64_t *E = e_scores + (size_t)j * N;
+            for (int i = 0; i < N; i++) {
+                int64_t h = sat(t, H[i] + scores_vec[(size_t)j * N + i]);
+                if (!t->is_signed) h = sat(t, h - bias);
+                int64_t e = E[i], f = F[i];
+                if (e > h) h = e;
+                if (f > h) h = f;
+                if (h > max_scores[i]) max_scores[i] = h;
+                store[(size_t)j * N + i] = h;
+                h = sat(t, h - go);
+                e = sat(t, e - ge);
+                if (h > e) e = h;
+                f = sat(t, f - ge);
+                if (h > f) f = h;
+                E[i] = e;
+                F[i] = f;
+                H[i] = load[(size_t)j * N + i];
+            }
+        }
+        /* lazy-F loop :115-137 */
+        int j = 0;
+        for (int i = 0; i < N; i++) H[i] = store[i];
+        shr(tmp, F, N, min);
+        memcpy(F, tmp, sizeof(int64_t) * N);
+        for (;;) {
+            int any = 0;
+            for (int i = 0; i < N; i++)
+                if (F[i] > sat(t, H[i] - go)) any = 1;
+            if (!any) break;
+            for (int i = 0; i < N; i++) {
+                if (F[i] > H[i]) H[i] = F[i];
+                store[(size_t)j * N + i] = H[i];
+                F[i] = sat(t, F[i] - ge);
+            }
+            j++;
+            if (j >= nv) {
+                j = 0;
+                shr(tmp, F, N, min);
+                memcpy(F, tmp, sizeof(int64_t) * N);
+            }
+            for (int i = 0; i < N; i++) H[i] = store[(size_t)j * N + i];
+        }
+    }
+    int64_t best = max_scores[0];
+    for (int i = 1; i < N; i++)
+        if (max_scores[i] > best) best = max_scores[i];
+    free(buf);
+    return zo_score_to_maybe_aligned(p, best, score);
+}
+
+/* ---- AlignmentStates (src/alignment/types/state.rs:142-152 add_ciglet, :232-234 soft_clip, :281-283 make_reverse) ---- */
+typedef struct {
+    uint8_t *ops;
+    uint32_t *lens;
+    uint32_t n, cap;
+    int overflow;
+} zo_states;
+
+static void st_add(zo_states *s, uint64_t inc, uint8_t op) {
+    if (inc == 0) return;
+    if (s->n > 0 && s->ops[s->n - 1] == op) {
+        s->lens[s->n - 1] += (uint32_t)inc;
+        return;
+    }
+    if (s->n >= s->cap) {
+        s->overflow = 1;
+        return;
+    }
+    s->ops[s->n] = op;
+    s->lens[s->n] = (uint32_t)inc;
+    s->n++;
+}
+
+static void st_reverse(zo_states *s) {
+    for (uint32_t i = 0, j = s->n; i + 1 < j; i++) {
+        j--;
+        uint8_t o = s->ops[i];
+        s->ops[i] = s->ops[j];
+        s->ops[j] = o;
+        uint32_t l = s->lens[i];
+        s->lens[i] = s->lens[j];
+        s->lens[j] = l;
+    }
+}
+
+/* ---- src/alignment/types/backtrack.rs:290-342 BackTrackable::to_alignment ----
+ * `cell(r,c)` abstracts move_to: row-major for the scalar matrix (:408-411),
+ * striped addressing for BacktrackMatrixStriped (:473-477). */
+typedef struct {
+    const uint8_t *data;
+    int striped;
+    int nv, N;
+    uint64_t cols;
+} zo_bt;
+
+static inline uint8_t bt_cell(const zo_bt *b, uint64_t r, uint64_t c) {
+    if (b->striped) {
+        uint64_t v = c % (uint64_t)b->nv;
+        uint64_t lane = (c - v) / (uint64_t)b->nv;
+        return b->data[((uint64_t)b->nv * r + v) * (uint64_t)b->N + lane];
+    }
+    return b->data[b->cols * r + c];
+}
+
+static void zo_to_alignment(const zo_bt *b, uint32_t score, uint64_t r_end, uint64_t c_end, uint64_t ref_len,
+                            uint64_t query_len, zo_alignment *out, zo_states *st) {
+    uint8_t op = 0;
+    uint8_t cur = bt_cell(b, r_end, c_end);
+    r_end += 1;
+    c_end += 1;
+    uint64_t r = r_end, c = c_end;
+    st_add(st, query_len - c, 'S'); /* soft clip 3' */
+    while (!(cur & F_STOP) && r > 0 && c > 0) {
+        if (op == 'D' && (cur & F_UP_EXT)) {
+            op = 'D';
+            r -= 1;
+        } else if (op == 'I' && (cur & F_LEFT_EXT)) {
+            op = 'I';
+            c -= 1;
+        } else if (cur & F_UP) {
+            op = 'D';
+            r -= 1;
+        } else if (cur & F_LEFT) {
+            op = 'I';
+            c -= 1;
+        } else {
+            op = 'M';
+            r -= 1;
+            c -= 1;
+        }
+        st_add(st, 1, op);
+        cur = bt_cell(b, r > 0 ? r - 1 : 0, c > 0 ? c - 1 : 0); /* saturating_sub(1), :326 */
+    }
+    st_add(st, c, 'S'); /* soft clip 5' */
+    st_reverse(st);
+    out->score = score;
+    out->ref_start = r;
+    out->ref_end = r_end;
+    out->query_start = c;
+    out->query_end = c_end;
+    out->ref_len = ref_len;
+    out->query_len = query_len;
+    out->n_ops = st->n;
+}
+
+/* ---- src/alignment/sw/striped.rs:449-598 sw_simd_align ---- */
+static int zo_striped_align_profile(const zo_profile *p, const uint8_t *reference, uint64_t n, zo_alignment *out,
+                                    zo_states *st) {
+    if (n == 0) return ZO_UNMAPPED; /* :455-457 */
+    const zo_type *t = &p->t;
+    const int N = p->N, nv = p->nv;
+    const int64_t min = t->min, go = p->gap_open, ge = p->gap_extend, bias = p->bias;
+    const int64_t saturating_threshold = t->is_signed ? t->max : t->max - bias; /* :469 */
+    size_t vsz = (size_t)nv * N;
+    int64_t *buf = (int64_t *)malloc(sizeof(int64_t) * (4 * vsz + 4 * (size_t)N));
+    int64_t *load = buf, *store = buf + vsz, *e_scores = buf + 2 * vsz, *max_row = buf + 3 * vsz;
+    int64_t *max_scores = buf + 4 * vsz, *F = max_scores + N, *H = F + N, *tmp = H + N;
+    for (size_t i = 0; i < 4 * vsz + 4 * (size_t)N; i++) buf[i] = min;
+    uint8_t *backtrack = (uint8_t *)malloc((size_t)n * vsz);
+
+    int64_t best = min;
+    uint64_t r_end = n - 1;
+    int status = -1;
+
+    for (uint64_t r = 0; r < n; r++) {
+        int ref_index = p->map[reference[r]];
+        for (int i = 0; i < N; i++) F[i] = min;
+        shr(H, store + (size_t)(nv - 1) * N, N, min);
+        if (r > 1 && r_end == r - 2) { /* :485-487 */
+            int64_t *sw = max_row;
+            max_row = load;
+            load = sw;
+        }
+        {
+            int64_t *sw = load;
+            load = store;
+            store = sw;
+        }
+        const int64_t *scores_vec = p->profile + (size_t)ref_index * nv * N;
+        uint8_t *backtrack_row = backtrack + (size_t)r * vsz;
+        for (int i = 0; i < N; i++) max_scores[i] = min;
+
+        for (int v = 0; v < nv; v++) { /* :495-526 */
+            int64_t *E = e_scores + (size_t)v * N;
+            for (int i = 0; i < N; i++) {
+                int64_t e = E[i], f = F[i];
+                int64_t h = sat(t, H[i] + scores_vec[(size_t)v * N + i]);
+                if (!t->is_signed) h = sat(t, h - bias);
+                if (e > h) h = e;
+                if (f > h) h = f;
+                uint8_t flags = 0;
+                if (h > max_scores[i]) max_scores[i] = h;
+                if (e == h) flags |= F_UP;
+                if (f == h) flags |= F_LEFT;
+                int stopped = (h == min);
+                store[(size_t)v * N + i] = h;
+                h = sat(t, h - go);
+                e = sat(t, e - ge);
+                if (h > e) e = h;
+                f = sat(t, f - ge);
+                if (h > f) f = h;
+                if (e > h) flags |= F_UP_EXT;
+                if (f > h) flags |= F_LEFT_EXT;
+                if (stopped) flags = F_STOP;
+                backtrack_row[(size_t)v * N + i] = flags;
+                E[i] = e;
+                F[i] = f;
+                H[i] = load[(size_t)v * N + i];
+            }
+        }
+
+        /* lazy-F :528-553 */
+        for (int pass = 0; pass < N; pass++) {
+            shr(tmp, F, N, min);
+            memcpy(F, tmp, sizeof(int64_t) * N);
+            int broke = 0;
+            for (int v = 0; v < nv; v++) {
+                int64_t *Hs = store + (size_t)v * N;
+                int any = 0;
+                for (int i = 0; i < N; i++)
+                    if (F[i] > sat(t, Hs[i] - go)) any = 1;
+                if (!any) {
+                    broke = 1;
+                    break;
+                }
+                for (int i = 0; i < N; i++) {
+                    int64_t h = Hs[i];
+                    if (F[i] > h) h = F[i];
+                    Hs[i] = h;
+                    uint8_t flags = backtrack_row[(size_t)v * N + i];
+                    int stopped = (h == min);
+                    if (F[i] == h) flags = (uint8_t)((flags & F_UP_EXT) | F_LEFT); /* backtrack.rs:218-220 */
+                    int64_t ho = sat(t, h - go);
+                    F[i] = sat(t, F[i] - ge);
+                    if (F[i] > ho) flags |= F_LEFT_EXT;
+                    if (stopped) flags = F_STOP;
+                    backtrack_row[(size_t)v * N + i] = flags;
+                }
+            }
+            if (broke) break;
+        }
+
+        int64_t row_best = max_scores[0];
+        for (int i = 1; i < N; i++)
+            if (max_scores[i] > row_best) row_best = max_scores[i];
+        if (row_best > best) { /* :555-562 */
+            if (row_best >= saturating_threshold) {
+                status = ZO_OVERFLOWED;
+                break;
+            }
+            best = row_best;
+            r_end = r;
+        }
+    }
+
+    if (status < 0) {
+        if (r_end == n - 1)
+            max_row = store;
+        else if (n >= 2 && r_end == n - 2)
+            max_row = load;
+        uint64_t c_end = p->seq_len - 1;
+        for (uint64_t ci = 0; ci < p->seq_len; ci++) { /* :573-583 */
+            uint64_t v = ci % (uint64_t)nv, lane = ci / (uint64_t)nv;
+            if (max_row[v * N + lane] == best) {
+                c_end = ci;
+                break;
+            }
+        }
+        uint32_t score = 0;
+        status = zo_score_to_maybe_aligned(p, best, &score);
+        if (status == ZO_SOME) {
+            zo_bt b = {backtrack, 1, nv, N, 0};
+            zo_to_alignment(&b, score, r_end, c_end, n, p->seq_len, out, st);
+        }
+    }
+    free(backtrack);
+    free(buf);
+    return status;
+}
+
+/* ---- src/alignment/sw/striped.rs:213-336 sw_simd_score_ends_dir::<FORWARD=true> ---- */
+static int zo_striped_score_ends_profile(const zo_profile *p, const uint8_t *reference, uint64_t n, uint32_t *score,
+                                         uint64_t *ref_end, uint64_t *query_end) {
+    if (n == 0) return ZO_UNMAPPED;
+    const zo_type *t = &p->t;
+    const int N = p->N, nv = p->nv;
+    const int64_t min = t->min, go = p->gap_open, ge = p->gap_extend, bias = p->bias;
+    const int64_t saturating_threshold = t->is_signed ? t->max : t->max - bias;
+    size_t vsz = (size_t)nv * N;
+    int64_t *buf = (int64_t *)malloc(sizeof(int64_t) * (4 * vsz + 4 * (size_t)N));
+    int64_t *load = buf, *store = buf + vsz, *e_scores = buf + 2 * vsz, *max_row = buf + 3 * vsz;
+    int64_t *max_scores = buf + 4 * vsz, *F = max_scores + N, *H = F + N, *tmp = H + N;
+    for (size_t i = 0; i < 4 * vsz + 4 * (size_t)N; i++) buf[i] = min;
+    int64_t best = min;
+    uint64_t r_end = n - 1;
+    int status = -1;
+    for (uint64_t r = 0; r < n; r++) {
+        int ref_index = p->map[reference[r]];
+        for (int i = 0; i < N; i++) F[i] = min;
+        shr(H, store + (size_t)(nv - 1) * N, N, min);
+        if (r > 1 && r_end == r - 2) {
+            int64_t *sw = max_row;
+            max_row = load;
+            load = sw;
+        }
+        {
+            int64_t *sw = load;
+            load = store;
+            store = sw;
+        }
+        const int64_t *scores_vec = p->profile + (size_t)ref_index * nv * N;
+        for (int i = 0; i < N; i++) max_scores[i] = min;
+        for (int v = 0; v < nv; v++) {
+            int64_t *E = e_scores + (size_t)v * N;
+            for (int i = 0; i < N; i++) {
+                int64_t e = E[i], f = F[i];
+                int64_t h = sat(t, H[i] + scores_vec[(size_t)v * N + i]);
+                if (!t->is_signed) h = sat(t, h - bias);
+                if (e > h) h = e;
+                if (f > h) h = f;
+                if (h > max_scores[i]) max_scores[i] = h;
+                store[(size_t)v * N + i] = h;
+                h = sat(t, h - go);
+                e = sat(t, e - ge);
+                if (h > e) e = h;
+                f = sat(t, f - ge);
+                if (h > f) f = h;
+                E[i] = e;
+                F[i] = f;
+                H[i] = load[(size_t)v * N + i];
+            }
+        }
+        for (int pass = 0; pass < N; pass++) { /* :279-294 */
+            shr(tmp, F, N, min);
+            memcpy(F, tmp, sizeof(int64_t) * N);
+            int broke = 0;
+            for (int v = 0; v < nv; v++) {
+                int64_t *Hs = store + (size_t)v * N;
+                int any = 0;
+                for (int i = 0; i < N; i++)
+                    if (F[i] > sat(t, Hs[i] - go)) any = 1;
+                if (!any) {
+                    broke = 1;
+                    break;
+                }
+                for (int i = 0; i < N; i++) {
+                    if (F[i] > Hs[i]) Hs[i] = F[i];
+                    F[i] = sat(t, F[i] - ge);
+                }
+            }
+            if (broke) break;
+        }
+        int64_t row_best = max_scores[0];
+        for (int i = 1; i < N; i++)
+            if (max_scores[i] > row_best) row_best = max_scores[i];
+        if (row_best > best) {
+            if (row_best >= saturating_threshold) {
+                status = ZO_OVERFLOWED;
+                break;
+            }
+            best = row_best;
+            r_end = r;
+        }
+    }
+    if (status < 0) {
+        if (r_end == n - 1)
+            max_row = store;
+        else if (n >= 2 && r_end == n - 2)
+            max_row = load;
+        uint64_t c_end = p->seq_len - 1;
+        for (uint64_t ci = 0; ci < p->seq_len; ci++) {
+            uint64_t v = ci % (uint64_t)nv, lane = ci / (uint64_t)nv;
+            if (max_row[v * N + lane] == best) {
+                c_end = ci;
+                break;
+            }
+        }
+        status = zo_score_to_maybe_aligned(p, best, score);
+        *ref_end = r_end + 1;
+        *query_end = c_end + 1;
+    }
+    free(buf);
+    return status;
+}
+
+/* ---- src/alignment/types/output.rs:396-425 Alignment::invert ---- */
+static void zo_invert(zo_alignment *a, zo_states *st) {
+    zo_states inv;
+    inv.cap = st->n + 2;
+    inv.ops = (uint8_t *)malloc(inv.cap);
+    inv.lens = (uint32_t *)malloc(sizeof(uint32_t) * inv.cap);
+    inv.n = 0;
+    inv.overflow = 0;
+    st_add(&inv, a->ref_start, 'S');
+    for (uint32_t i = 0; i < st->n; i++) {
+        uint8_t op = st->ops[i];
+        if (op == 'S' || op == 'H') continue;
+        if (op == 'D')
+            op = 'I';
+        else if (op == 'I')
+            op = 'D';
+        /* extend_from_ciglets: appended as-is (no merge) */
+        inv.ops[inv.n] = op;
+        inv.lens[inv.n] = st->lens[i];
+        inv.n++;
+    }
+    st_add(&inv, a->ref_len - a->ref_end, 'S');
+    if (inv.n > st->cap) {
+        st->overflow = 1;
+    } else {
+        memcpy(st->ops, inv.ops, inv.n);
+        memcpy(st->lens, inv.lens, sizeof(uint32_t) * inv.n);
+        st->n = inv.n;
+    }
+    free(inv.ops);
+    free(inv.lens);
+    uint64_t rs = a->ref_start, re = a->ref_end, rl = a->ref_len;
+    a->ref_start = a->query_start;
+    a->ref_end = a->query_end;
+    a->ref_len = a->query_len;
+    a->query_start = rs;
+    a->query_end = re;
+    a->query_len = rl;
+    a->n_ops = st->n;
+}
+
+/* =========================== exported entry points =========================== */
+
+/* StripedProfile::<T,N,S>::new(profiled).sw_score(streamed): profile.rs:239-247, 440-446 */
+int zo_striped_score(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                     int bits, int is_signed, int lanes, uint32_t *score) {
+    zo_profile p;
+    int rc = zo_profile_new(&p, profiled, m, sc, bits, is_signed, lanes);
+    if (rc) return rc;
+    *score = 0;
+    rc = zo_striped_score_profile(&p, streamed, n, score);
+    zo_profile_free(&p);
+    return rc;
+}
+
+/* StripedProfile::sw_score_ends(SeqSrc::Reference(streamed)): profile.rs:456-460 */
+int zo_striped_score_ends(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n,
+                          const zo_scoring *sc, int bits, int is_signed, int lanes, uint32_t *score, uint64_t *ref_end,
+                          uint64_t *query_end) {
+    zo_profile p;
+    int rc = zo_profile_new(&p, profiled, m, sc, bits, is_signed, lanes);
+    if (rc) return rc;
+    *score = 0;
+    rc = zo_striped_score_ends_profile(&p, streamed, n, score, ref_end, query_end);
+    zo_profile_free(&p);
+    return rc;
+}
+
+/* StripedProfile::sw_align(SeqSrc): profile.rs:515-519 + alignment/mod.rs:176-190.
+ * streamed_is_query != 0  <=>  SeqSrc::Query(streamed)  (result is invert()ed). */
+int zo_striped_align(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                     int bits, int is_signed, int lanes, int streamed_is_query, zo_alignment *out, uint8_t *ops,
+                     uint32_t *lens, uint32_t cap) {
+    zo_profile p;
+    int rc = zo_profile_new(&p, profiled, m, sc, bits, is_signed, lanes);
+    if (rc) return rc;
+    zo_states st = {ops, lens, 0, cap, 0};
+    memset(out, 0, sizeof(*out));
+    rc = zo_striped_align_profile(&p, streamed, n, out, &st);
+    zo_profile_free(&p);
+    if (rc == ZO_SOME && streamed_is_query) zo_invert(out, &st);
+    if (st.overflow) return ZO_ERR_CIGAR_CAP;
+    return rc;
+}
+
+/* ProfileSets::sw_score_from_i8 / _i16 / _i32: profile_set.rs:71-105 (signed tiers only). */
+int zo_sw_score_from(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                     int first_bits, int lanes8, int lanes16, int lanes32, uint32_t *score, int *tier) {
+    int bitsv[3] = {8, 16, 32}, lanesv[3] = {lanes8, lanes16, lanes32};
+    int rc = ZO_OVERFLOWED;
+    for (int k = 0; k < 3; k++) {
+        if (bitsv[k] < first_bits) continue;
+        *tier = bitsv[k];
+        rc = zo_striped_score(profiled, m, streamed, n, sc, bitsv[k], 1, lanesv[k], score);
+        if (rc != ZO_OVERFLOWED) return rc; /* or_else_overflowed, output.rs:81-83 */
+    }
+    return rc;
+}
+
+/* ProfileSets::sw_align_from_i8 / _i16 / _i32: profile_set.rs:136-179 */
+int zo_sw_align_from(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                     int first_bits, int lanes8, int lanes16, int lanes32, int streamed_is_query, zo_alignment *out,
+                     uint8_t *ops, uint32_t *lens, uint32_t cap, int *tier) {
+    int bitsv[3] = {8, 16, 32}, lanesv[3] = {lanes8, lanes16, lanes32};
+    int rc = ZO_OVERFLOWED;
+    for (int k = 0; k < 3; k++) {
+        if (bitsv[k] < first_bits) continue;
+        *tier = bitsv[k];
+        rc = zo_striped_align(profiled, m, streamed, n, sc, bitsv[k], 1, lanesv[k], streamed_is_query, out, ops, lens,
+                              cap);
+        if (rc != ZO_OVERFLOWED) return rc;
+    }
+    return rc;
+}
+
+/* ---- src/alignment/sw/scalar.rs:55-113 sw_scalar_score (profile = `profiled`, streamed = reference) ---- */
+int zo_scalar_score(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                    uint32_t *score) {
+    int rc = zo_validate_profile_args(m, sc->gap_open, sc->gap_extend);
+    if (rc) return rc;
+    int32_t go = sc->gap_open, ge = sc->gap_extend;
+    int32_t *h_row = (int32_t *)calloc(m, sizeof(int32_t));
+    int32_t *e_row = (int32_t *)malloc(sizeof(int32_t) * m);
+    for (uint64_t c = 0; c < m; c++) e_row[c] = go;
+    int32_t best_score = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        int ri = sc->map[streamed[r]];
+        int32_t f = go, h = 0;
+        for (uint64_t c = 0; c < m; c++) {
+            h += sc->weights[ri * sc->S + sc->map[profiled[c]]];
+            int32_t e = e_row[c];
+            if (e > h) h = e;
+            if (f > h) h = f;
+            if (h < 0) h = 0;
+            if (h > best_score) best_score = h;
+            e = e + ge > h + go ? e + ge : h + go;
+            f = f + ge > h + go ? f + ge : h + go;
+            int32_t t = h_row[c];
+            h_row[c] = h;
+            h = t;
+            e_row[c] = e;
+        }
+    }
+    free(h_row);
+    free(e_row);
+    *score = (uint32_t)best_score;
+    return best_score > 0 ? ZO_SOME : ZO_UNMAPPED;
+}
+
+/* ---- src/alignment/sw/scalar.rs:173-271 sw_scalar_align ---- */
+int zo_scalar_align(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                    int streamed_is_query, zo_alignment *out, uint8_t *ops, uint32_t *lens, uint32_t cap) {
+    int rc = zo_validate_profile_args(m, sc->gap_open, sc->gap_extend);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    if (n == 0) return ZO_UNMAPPED;
+    int32_t go = sc->gap_open, ge = sc->gap_extend;
+    int32_t best_score = 0;
+    uint64_t r_end = 0, c_end = 0;
+    int32_t *h_row = (int32_t *)calloc(m, sizeof(int32_t));
+    int32_t *e_row = (int32_t *)malloc(sizeof(int32_t) * m);
+    for (uint64_t c = 0; c < m; c++) e_row[c] = go;
+    uint8_t *bt = (uint8_t *)calloc((size_t)n * m, 1);
+    for (uint64_t r = 0; r < n; r++) {
+        int ri = sc->map[streamed[r]];
+        int32_t f = go, h = 0;
+        for (uint64_t c = 0; c < m; c++) {
+            uint8_t *cell = bt + (size_t)r * m + c;
+            h += sc->weights[ri * sc->S + sc->map[profiled[c]]];
+            int32_t e = e_row[c];
+            if (e > h) h = e;
+            if (f > h) h = f;
+            if (h < 0) h = 0;
+            if (h > best_score) {
+                best_score = h;
+                r_end = r;
+                c_end = c;
+            }
+            if (e == h) *cell |= F_UP;
+            if (f == h) *cell |= F_LEFT;
+            if (h == 0) *cell = F_STOP;
+            int32_t next_diag = h_row[c];
+            h_row[c] = h;
+            h += go;
+            e = e + ge > h ? e + ge : h;
+            f = f + ge > h ? f + ge : h;
+            if (h != go) {
+                if (e > h) *cell |= F_UP_EXT;
+                if (f > h) *cell |= F_LEFT_EXT;
+            }
+            h = next_diag;
+            e_row[c] = e;
+        }
+    }
+    int status;
+    zo_states st = {ops, lens, 0, cap, 0};
+    if (best_score == 0) {
+        status = ZO_UNMAPPED;
+    } else {
+        zo_bt b = {bt, 0, 0, 0, m};
+        zo_to_alignment(&b, (uint32_t)best_score, r_end, c_end, n, m, out, &st);
+        if (streamed_is_query) zo_invert(out, &st);
+        status = ZO_SOME;
+    }
+    free(h_row);
+    free(e_row);
+    free(bt);
+    if (st.overflow) return ZO_ERR_CIGAR_CAP;
+    return status;
+}
+
+/* Dump the striped profile (for the profile_set.rs:704-712 equality test and for debugging). */
+int zo_striped_profile_dump(const uint8_t *profiled, uint64_t m, const zo_scoring *sc, int bits, int is_signed,
+                            int lanes, int32_t *out, uint64_t out_cap, int *nv) {
+    zo_profile p;
+    int rc = zo_profile_new(&p, profiled, m, sc, bits, is_signed, lanes);
+    if (rc) return rc;
+    uint64_t tot = (uint64_t)p.S * p.nv * p.N;
+    *nv = p.nv;
+    if (tot <= out_cap)
+        for (uint64_t i = 0; i < tot; i++) out[i] = (int32_t)p.profile[i];
+    zo_profile_free(&p);
+    return tot <= out_cap ? 0 : ZO_ERR_BAD_ARG;
+}
