@@ -1,0 +1,149 @@
+/*
+ * zoe_cuda.h -- C ABI of the B200 (sm_100a) backend for zoe's striped Smith-Waterman path.
+ *
+ * zoe (CDCgov/zoe, pure Rust) has no FFI seam of its own; the drop-in boundary is its Rust
+ * API for this path.  Each entry point below names the zoe interface it stands behind
+ * (paths relative to the zoe repository root).  A Rust `-sys` crate binds exactly these symbols
+ * (see INTEGRATION.md); the C++ mirror (include/zoe_cuda.hpp) and the Python mirror
+ * (zoe_b200/) bind the same ones.
+ *
+ * Vocabulary: the *profiled* sequences P are the ones a zoe caller builds a
+ * `StripedProfile` / `SharedProfiles` from (DP columns c); the *streamed* sequences R are the ones
+ * passed to `sw_score(seq)` / `sw_align(SeqSrc)` (DP rows r).  A batch call computes every
+ * (streamed i, profiled j) pair; result index = i * n_profiled + j, independent of GPU count.
+ *
+ * Error model: every call returns 0 on success or a negative ZOE_CUDA_E_* code; the message is
+ * available from zoe_cuda_last_error().  No C++ exception crosses this boundary.  A context is
+ * NOT thread-safe (one per host thread, like zoe's `LocalProfiles`).  There is no CPU fallback:
+ * if no CUDA device is usable, zoe_cuda_create() fails.
+ */
+#ifndef ZOE_CUDA_H
+#define ZOE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zoe_cuda_ctx zoe_cuda_ctx;
+
+/* MaybeAligned<T> discriminant: src/alignment/types/output.rs:18-25 */
+#define ZOE_CUDA_SOME 0
+#define ZOE_CUDA_OVERFLOWED 1
+#define ZOE_CUDA_UNMAPPED 2
+
+/* Error codes.  -1..-4 mirror ProfileError (src/alignment/errors.rs:6-15) as raised by
+ * validate_profile_args (src/alignment/profile.rs:32-44). */
+#define ZOE_CUDA_OK 0
+#define ZOE_CUDA_E_EMPTY_SEQUENCE (-1)
+#define ZOE_CUDA_E_GAP_OPEN_RANGE (-2)
+#define ZOE_CUDA_E_GAP_EXTEND_RANGE (-3)
+#define ZOE_CUDA_E_BAD_GAP_WEIGHTS (-4)
+#define ZOE_CUDA_E_BAD_ARG (-5)
+#define ZOE_CUDA_E_CIGAR_CAP (-6)
+#define ZOE_CUDA_E_CUDA (-7)
+#define ZOE_CUDA_E_STATE (-8)
+#define ZOE_CUDA_E_UNSUPPORTED (-9)
+
+/* CIGAR encoding: BAM style (len << 4) | op with M=0, I=1, D=2, S=4 -- the only operations
+ * zoe's SW emits (src/alignment/sw/mod.rs:149-154). */
+#define ZOE_CUDA_CIGAR_M 0u
+#define ZOE_CUDA_CIGAR_I 1u
+#define ZOE_CUDA_CIGAR_D 2u
+#define ZOE_CUDA_CIGAR_S 4u
+
+/* Create a context on `n_devices` CUDA devices (device_ids == NULL: devices 0..n-1).  Batches
+ * are split over the devices by contiguous streamed-index range; there is no collective.
+ * Replaces: nothing in zoe (zoe is single-threaded; callers own parallelism,
+ * src/alignment/profile_set.rs:552-560). */
+int zoe_cuda_create(zoe_cuda_ctx **ctx, const int *device_ids, int n_devices);
+void zoe_cuda_destroy(zoe_cuda_ctx *ctx);
+const char *zoe_cuda_last_error(const zoe_cuda_ctx *ctx);
+
+/* Scoring = zoe's (WeightMatrix<i8,S>, gap_open, gap_extend) triple.
+ *   weights       S*S row-major, exactly zoe's weights[ref_idx][query_idx]
+ *                 (src/data/matrices/mod.rs:230-235)
+ *   byte_to_index zoe's ByteIndexMap table (src/data/constants/mappings/byte_index.rs:331-333)
+ *   gap_open/gap_extend  as zoe takes them: -127..=0, gap_extend >= gap_open
+ *                 (src/alignment/profile.rs:32-44); violations return the ProfileError codes.
+ *   profiled_is_query  1: the profiled sequences are queries and streamed sequences are
+ *                 references (zoe's SeqSrc::Reference(streamed), no inversion);
+ *                 0: the profiled sequences are references, streamed are queries
+ *                 (SeqSrc::Query(streamed): the Alignment is invert()ed,
+ *                 src/alignment/mod.rs:176-190, src/alignment/types/output.rs:396-425). */
+int zoe_cuda_set_scoring(zoe_cuda_ctx *ctx, const int8_t *weights, int S, const uint8_t byte_to_index[256],
+                         int8_t gap_open, int8_t gap_extend, int profiled_is_query);
+
+/* Lane counts (M, N, O) of zoe's ProfileSets: they fix the CIGAR tie-break layout of each
+ * score-width tier (src/alignment/profile_set.rs:434-483: w128 = 16/8/4, w256 = 32/16/8,
+ * w512 = 64/32/16).  Default w256, as Nucleotides::into_local_profile uses
+ * (src/data/types/nucleotides/mod.rs:262-300). */
+int zoe_cuda_set_lanes(zoe_cuda_ctx *ctx, int lanes_i8, int lanes_i16, int lanes_i32);
+
+/* The profiled sequences (raw bytes, concatenated; offsets has n+1 entries).  Replaces
+ * SharedProfiles::new / StripedProfile::new (src/alignment/profile_set.rs:382-390,
+ * src/alignment/profile.rs:239-306): validates like zoe, uploads once, replicated per device.
+ * Requires set_scoring first. */
+int zoe_cuda_set_profiled(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint32_t n);
+
+/* Batched ProfileSets::sw_score_from_i8 (src/alignment/profile_set.rs:71-78 ->
+ * sw_simd_score, src/alignment/sw/striped.rs:65-142, with the i8->i16->i32 escalation of
+ * output.rs:81-83).  Host buffers in, host buffers out; outputs have n * n_profiled entries.
+ *   score   the local alignment score (0 when not Some)
+ *   status  ZOE_CUDA_SOME / OVERFLOWED / UNMAPPED
+ *   tier    8, 16 or 32: the narrowest signed width whose run would not have overflowed
+ *           (src/alignment/sw/striped.rs:608-633). */
+int zoe_cuda_sw_score_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
+                            uint32_t *score, uint8_t *status, uint8_t *tier);
+
+/* Batched ProfileSets::sw_align_from_i8 (src/alignment/profile_set.rs:136-145 -> sw_simd_align,
+ * src/alignment/sw/striped.rs:449-598, traceback src/alignment/types/backtrack.rs:290-342).
+ * Ranges are 0-based half-open and follow zoe's Alignment after make_alignment (i.e. already
+ * inverted when profiled_is_query == 0): ref_* index the reference-side sequence, query_* the
+ * query-side one.  cigar_off has n_pairs + 1 entries into `cigar` (capacity cigar_cap words);
+ * if the CIGARs do not fit the call returns ZOE_CUDA_E_CIGAR_CAP and writes the needed
+ * capacity to cigar_off[0] (nothing else is valid).
+ *   hazard  (may be NULL) 1 where the pair went through the literal striped-emulation kernel
+ *           because its traceback met an E/F tie whose resolution depends on the lane layout. */
+int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
+                            uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
+                            uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
+                            uint64_t cigar_cap, uint8_t *hazard);
+
+/* ---- measurement hooks (not part of the zoe-facing surface) ---- */
+
+/* Device-resident variant of zoe_cuda_sw_score_batch for kernel-only timing: upload once with
+ * zoe_cuda_stage_streamed(), then run the kernels any number of times.  Results stay on the
+ * device until zoe_cuda_fetch_scores(). */
+int zoe_cuda_stage_streamed(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n);
+int zoe_cuda_run_score_staged(zoe_cuda_ctx *ctx);
+int zoe_cuda_run_align_staged(zoe_cuda_ctx *ctx);
+int zoe_cuda_fetch_scores(zoe_cuda_ctx *ctx, uint32_t *score, uint8_t *status, uint8_t *tier);
+
+/* Timing of the most recent batch/staged call, from CUDA events on the library's own streams
+ * (max over devices): total device time and the share spent in the dominant DP kernel. */
+int zoe_cuda_last_timing(const zoe_cuda_ctx *ctx, float *total_ms, float *dp_kernel_ms, uint32_t *kernel_launches);
+
+/* Counters of the most recent batch call: pairs per tier (8/16/32), overflowed, unmapped,
+ * pairs re-run at 32 bits, hazard pairs sent to the literal kernel. */
+typedef struct {
+    uint64_t pairs, cells;
+    uint64_t tier8, tier16, tier32, overflowed, unmapped;
+    uint64_t rerun_wide, hazard;
+} zoe_cuda_stats;
+int zoe_cuda_last_stats(const zoe_cuda_ctx *ctx, zoe_cuda_stats *out);
+
+/* Integer max-plus issue-rate microbenchmark (the roofline denominator):
+ * kind 0 = VIADDMNMX.S16x2 only, 1 = the score kernel's instruction mix without memory.
+ * Returns giga warp-lane-instructions per second on device 0 of the context. */
+int zoe_cuda_dpx_peak(zoe_cuda_ctx *ctx, int kind, double *giga_lane_instr_per_s, float *ms);
+
+/* Raw stream handle (cudaStream_t) of device `dev_index`, for external event timing. */
+void *zoe_cuda_stream(zoe_cuda_ctx *ctx, int dev_index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZOE_CUDA_H */

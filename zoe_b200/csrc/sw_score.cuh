@@ -1,0 +1,266 @@
+// sw_score.cuh -- score-only local alignment (affine gaps) for sm_100a.
+//
+// Replaces zoe's sw_simd_score (src/alignment/sw/striped.rs:65-142) plus the i8->i16->i32
+// escalation chain of ProfileSets::sw_score_from_i8 (src/alignment/profile_set.rs:71-78).
+// It is NOT a port of the striped algorithm: the striped layout exists to feed 128..512-bit CPU
+// vectors; on the GPU the same recurrence is evaluated as a register-resident systolic array.
+//
+// Layout ("row" = register-resident sequence, "col" = sequence streamed through):
+//   * a group of G lanes owns one task = two batch sequences (packed as the two signed 16-bit
+//     halves of every 32-bit register) or one (32-bit mode);
+//   * lane l of the group keeps rows [l*K, (l+1)*K) of H and of the along-column gap state in
+//     registers, so the K-row inner loop is fully unrolled;
+//   * columns (the profiled sequences, staged once per CTA in shared memory) are swept with a
+//     one-column skew per lane; the row-boundary H and the along-row gap state hop to the next
+//     lane with two __shfl_up_sync per step;
+//   * the substitution scores come from a per-task table in shared memory,
+//     tab[col_symbol][row/4][lane] = uint4 of four packed row scores, read with one conflict-free
+//     128-bit load per four cells.
+//
+// Arithmetic (true, un-offset values; zoe's MIN-offset saturating arithmetic computes the same
+// H, SURVEY.md 8(a) "Equivalent closed form"):
+//     x  = max(E^, F^, go) - go            (E^ = E + go, F^ = F + go: the shifted gap states)
+//     H  = max(Hdiag + W, x)               VIADDMNMX.S16x2
+//     E^ = max(E^ - ge, H)                 VIADDMNMX.S16x2
+//     F^ = max(F^ - ge, H)                 VIADDMNMX.S16x2
+//     best = max(best, H, H')              VIMNMX3.S16x2 (two rows per instruction)
+// i.e. 4.5 DPX/ALU instructions + 1 plain add per packed cell pair.  The subtraction is exact as a
+// plain 32-bit add because max(..., go) - go >= 0 in both halves (no borrow crosses the halves).
+//
+// Overflow / escalation: the packed kernel is exact while every H < OVF_THRESH (= 32767 - max
+// weight); a task whose best reaches the threshold is reported as "needs wide" and re-run by the
+// 32-bit instantiation of the same kernel -- the GPU analogue of or_else_overflowed
+// (src/alignment/types/output.rs:81-83).  The zoe tier label (8/16/32) is derived from the exact
+// score (striped.rs:608-633: i8 holds 1..=254, i16 1..=65534).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zoe_cuda {
+
+constexpr int kPadWeight = -16384;  // score of a padding row (never wins a max, never wraps)
+
+struct ScoreParams {
+    const uint8_t *rseq;       // batch sequences, raw bytes (device)
+    const uint64_t *roff;      // n_rseq + 1 offsets into rseq
+    const uint32_t *task_ids;  // optional list of batch-sequence indices (wide re-run); else nullptr
+    uint32_t n_tasks;          // packed: ceil(n_rseq / 2) (or list length / 2); 32-bit: count
+    uint32_t n_rseq;
+    const uint8_t *ccodes;     // column sequences as dense symbol codes (device)
+    const uint32_t *coff;      // n_cseq + 1 offsets into ccodes
+    uint32_t n_cseq;
+    uint32_t ccodes_bytes;     // total bytes of ccodes (staged in smem when it fits)
+    int cols_in_smem;
+    const int8_t *wk;          // [n_csym][S] weight of (column dense code, row symbol index)
+    int n_csym;                // dense column-symbol count
+    int S;
+    const uint8_t *lut;        // 256: byte -> row symbol index
+    int go, ge;                // positive penalties
+    int ovf_thresh;            // packed mode only
+    int32_t *best;             // [n_rseq * n_cseq] exact score, or -1 = needs the wide kernel
+};
+
+template <bool PACKED>
+struct Ops;
+
+template <>
+struct Ops<true> {
+    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
+        return __viaddmax_s16x2(a, b, c);
+    }
+    static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) {
+        return __vimax3_s16x2(a, b, c);
+    }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ uint32_t splat(int v) {
+        return (uint32_t)(v & 0xffff) | ((uint32_t)(v & 0xffff) << 16);
+    }
+};
+
+template <>
+struct Ops<false> {
+    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
+        return (uint32_t)__viaddmax_s32((int)a, (int)b, (int)c);
+    }
+    static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) {
+        return (uint32_t)__vimax3_s32((int)a, (int)b, (int)c);
+    }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return (uint32_t)max((int)a, (int)b); }
+    static __device__ __forceinline__ uint32_t splat(int v) { return (uint32_t)v; }
+};
+
+// Shared-memory footprint helpers (host + device).
+__host__ __device__ inline int score_tab_bytes(int n_csym, int G, int K) { return n_csym * ((K + 3) / 4) * G * 16; }
+
+template <int G, int K, bool PACKED>
+__global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
+    using O = Ops<PACKED>;
+    constexpr int K4 = (K + 3) / 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    const int tid = threadIdx.x;
+    const int lig = tid % G;                  // lane in group
+    const int group_in_block = tid / G;
+    const int groups_per_block = blockDim.x / G;
+
+    // ---- shared memory carve-up: [tables][lut 256][wk][ccodes] ----
+    const int tab_bytes = p.n_csym * K4 * G * 16;
+    uint4 *tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * tab_bytes);
+    uint8_t *s_lut = smem + (size_t)groups_per_block * tab_bytes;
+    int8_t *s_wk = reinterpret_cast<int8_t *>(s_lut + 256);
+    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
+
+    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
+    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
+    if (p.cols_in_smem)
+        for (uint32_t i = tid; i < p.ccodes_bytes; i += blockDim.x) s_cc[i] = p.ccodes[i];
+    __syncthreads();
+    const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
+
+    const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+
+    // Static round-robin task assignment: every group of a warp makes the same number of trips,
+    // so the warp never diverges on the task loop (invalid trips run on empty sequences).
+    const uint32_t total_groups = gridDim.x * groups_per_block;
+    const uint32_t trips = (p.n_tasks + total_groups - 1) / total_groups;
+    const uint32_t first = blockIdx.x * groups_per_block + group_in_block;
+
+    for (uint32_t trip = 0; trip < trips; ++trip) {
+        const uint32_t task = first + trip * total_groups;
+        const bool valid = task < p.n_tasks;
+
+        // ---- which batch sequences does this task hold? ----
+        uint32_t id_lo = 0xffffffffu, id_hi = 0xffffffffu;
+        if (valid) {
+            if (PACKED) {
+                uint32_t a = 2 * task, b = 2 * task + 1;
+                if (p.task_ids) {
+                    id_lo = p.task_ids[a];
+                    id_hi = (b < p.n_rseq) ? p.task_ids[b] : 0xffffffffu;
+                } else {
+                    id_lo = a;
+                    id_hi = (b < p.n_rseq) ? b : 0xffffffffu;
+                }
+            } else {
+                id_lo = p.task_ids ? p.task_ids[task] : task;
+            }
+        }
+        uint64_t off_lo = 0, off_hi = 0;
+        int len_lo = 0, len_hi = 0;
+        if (id_lo != 0xffffffffu) {
+            off_lo = p.roff[id_lo];
+            len_lo = (int)(p.roff[id_lo + 1] - off_lo);
+        }
+        if (PACKED && id_hi != 0xffffffffu) {
+            off_hi = p.roff[id_hi];
+            len_hi = (int)(p.roff[id_hi + 1] - off_hi);
+        }
+
+        // ---- build this task's score table: lane l fills its own K rows for every column symbol ----
+        __syncwarp();
+        {
+            int sym_lo[K], sym_hi[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                int r = lig * K + i;
+                sym_lo[i] = (r < len_lo) ? (int)s_lut[p.rseq[off_lo + r]] : -1;
+                sym_hi[i] = (PACKED && r < len_hi) ? (int)s_lut[p.rseq[off_hi + r]] : -1;
+            }
+            for (int s = 0; s < p.n_csym; ++s) {
+                const int8_t *wrow = s_wk + s * p.S;
+#pragma unroll
+                for (int i4 = 0; i4 < K4; ++i4) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int i = i4 * 4 + q;
+                        int wl = kPadWeight, wh = kPadWeight;
+                        if (i < K) {
+                            if (sym_lo[i] >= 0) wl = wrow[sym_lo[i]];
+                            if (sym_hi[i] >= 0) wh = wrow[sym_hi[i]];
+                        }
+                        w[q] = PACKED ? ((uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16)) : (uint32_t)wl;
+                    }
+                    tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- sweep every column sequence ----
+        for (uint32_t cj = 0; cj < p.n_cseq; ++cj) {
+            const uint32_t c0 = p.coff[cj];
+            const int L = (int)(p.coff[cj + 1] - c0);
+            const uint8_t *cs = cc + c0;
+
+            uint32_t Hrow[K], Frow[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                Hrow[i] = 0;
+                Frow[i] = 0;
+            }
+            uint32_t best = 0, h_last = 0, e_out = 0, h_up_prev = 0;
+            const int nsteps = L + G - 1;
+
+            for (int step = 0; step < nsteps; ++step) {
+                uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G);
+                uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G);
+                if (lig == 0) {
+                    h_in = 0;
+                    e_in = 0;
+                }
+                const int j = step - lig;
+                if (j >= 0 && j < L) {
+                    const int s = cs[j];
+                    const uint4 *tp = tab + (size_t)s * (K4 * G) + lig;
+                    uint32_t diag = h_up_prev;
+                    uint32_t E = e_in;
+                    uint32_t hprev = 0;
+#pragma unroll
+                    for (int i4 = 0; i4 < K4; ++i4) {
+                        const uint4 w4 = tp[i4 * G];
+                        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = i4 * 4 + q;
+                            if (i < K) {
+                                uint32_t x = O::max3(E, Frow[i], go_s) - go_s;
+                                uint32_t H = O::addmax(diag, w[q], x);
+                                diag = Hrow[i];
+                                E = O::addmax(E, neg_ge, H);
+                                Frow[i] = O::addmax(Frow[i], neg_ge, H);
+                                Hrow[i] = H;
+                                if (i & 1)
+                                    best = O::max3(best, H, hprev);
+                                else
+                                    hprev = H;
+                            }
+                        }
+                    }
+                    if (K & 1) best = O::max2(best, hprev);
+                    h_last = Hrow[K - 1];
+                    e_out = E;
+                }
+                h_up_prev = h_in;
+            }
+
+            // ---- reduce the group's best and write the exact scores ----
+#pragma unroll
+            for (int d = G / 2; d >= 1; d >>= 1) best = O::max2(best, __shfl_xor_sync(FULL, best, d, G));
+            if (lig == 0 && valid) {
+                if (PACKED) {
+                    int b_lo = (int)(int16_t)(best & 0xffff), b_hi = (int)(int16_t)(best >> 16);
+                    if (id_lo != 0xffffffffu)
+                        p.best[(size_t)id_lo * p.n_cseq + cj] = (b_lo >= p.ovf_thresh) ? -1 : b_lo;
+                    if (id_hi != 0xffffffffu)
+                        p.best[(size_t)id_hi * p.n_cseq + cj] = (b_hi >= p.ovf_thresh) ? -1 : b_hi;
+                } else {
+                    p.best[(size_t)id_lo * p.n_cseq + cj] = (int)best;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace zoe_cuda

@@ -1,0 +1,774 @@
+// zoe_cuda.cu -- the C-ABI shared library (include/zoe_cuda.h): context, scoring, profiled
+// sequences, batch drivers, sharding over devices.  Kernels live in sw_score.cuh / sw_align.cuh.
+//
+// No CPU fallback exists in this file by design: every result returned through this ABI was
+// computed by a CUDA kernel below.
+#include "../../include/zoe_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sw_score.cuh"
+
+using namespace zoe_cuda;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct Device {
+    int id = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    // scoring + profiled (replicated on every device)
+    DevBuf ccodes, coff, wk, lut;
+    // batch state
+    DevBuf rseq, roff, best, score, status, tier, wide_ids, counters;
+    uint64_t n_first = 0, n_count = 0;  // shard of the streamed batch owned by this device
+    uint64_t rseq_bytes = 0;
+    bool timed_kernel = false;
+};
+
+struct KernelEntry {
+    int G, K;
+    void (*packed)(const ScoreParams);
+    void (*wide)(const ScoreParams);
+};
+
+#define ZK(G, K) \
+    KernelEntry { G, K, sw_score_kernel<G, K, true>, sw_score_kernel<G, K, false> }
+
+// Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
+// sequence of a batch.  G = 8 serves short reads (150 nt -> 8 x 19), G = 32 the longest rows
+// a single pass can hold (1024).
+const KernelEntry kScoreKernels[] = {
+    ZK(8, 4),  ZK(8, 8),   ZK(8, 13),  ZK(8, 16),  ZK(8, 19),  ZK(8, 24),  ZK(8, 32),
+    ZK(16, 19), ZK(16, 24), ZK(16, 32), ZK(32, 10), ZK(32, 20), ZK(32, 24), ZK(32, 32),
+};
+constexpr int kNumScoreKernels = sizeof(kScoreKernels) / sizeof(kScoreKernels[0]);
+constexpr int kMaxRowsSinglePass = 32 * 32;
+
+}  // namespace
+
+struct zoe_cuda_ctx {
+    std::vector<Device> devs;
+    std::string err;
+    // scoring
+    bool have_scoring = false;
+    int S = 0;
+    std::vector<int8_t> weights;  // S*S, zoe's weights[ref_idx][query_idx]
+    uint8_t lut[256];
+    int go = 0, ge = 0;  // positive penalties
+    int profiled_is_query = 0;
+    int max_weight = 0;
+    int lanes[3] = {32, 16, 8};
+    // profiled
+    bool have_profiled = false;
+    uint32_t n_prof = 0;
+    std::vector<uint8_t> prof_bytes;
+    std::vector<uint64_t> prof_off;
+    std::vector<uint8_t> ccodes;
+    std::vector<uint32_t> coff;
+    std::vector<int8_t> wk;
+    int n_csym = 0;
+    uint32_t max_prof_len = 0;
+    // staged batch (host view)
+    uint64_t staged_n = 0;
+    uint32_t staged_max_len = 0;
+    uint64_t staged_cells = 0;
+    bool staged = false;
+    // measurements
+    float last_total_ms = 0.f, last_dp_ms = 0.f;
+    uint32_t last_launches = 0;
+    zoe_cuda_stats stats{};
+};
+
+namespace {
+
+int fail(zoe_cuda_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, ZOE_CUDA_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+// zoe: validate_profile_args, src/alignment/profile.rs:32-44
+int validate_profile_args(uint64_t len, int gap_open, int gap_extend) {
+    if (len == 0) return ZOE_CUDA_E_EMPTY_SEQUENCE;
+    if (gap_open < -127 || gap_open > 0) return ZOE_CUDA_E_GAP_OPEN_RANGE;
+    if (gap_extend < -127 || gap_extend > 0) return ZOE_CUDA_E_GAP_EXTEND_RANGE;
+    if (gap_extend < gap_open) return ZOE_CUDA_E_BAD_GAP_WEIGHTS;
+    return 0;
+}
+
+// score/status/tier from the exact best score: src/alignment/sw/striped.rs:608-633 applied along
+// the escalation chain of src/alignment/profile_set.rs:71-78.
+__global__ void finalize_scores_kernel(const int32_t *best, uint64_t n, uint32_t *score, uint8_t *status,
+                                       uint8_t *tier, unsigned long long *counters) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c8 = 0, c16 = 0, c32 = 0, cun = 0;
+    if (i < n) {
+        int32_t b = best[i];
+        uint32_t s = (uint32_t)b;
+        uint8_t st = ZOE_CUDA_SOME, t = 8;
+        if (b <= 0) {
+            s = 0;
+            st = ZOE_CUDA_UNMAPPED;  // Unmapped does not escalate: it is decided in the i8 tier
+            cun = 1;
+        } else if (b <= 254) {
+            t = 8;
+            c8 = 1;
+        } else if (b <= 65534) {
+            t = 16;
+            c16 = 1;
+        } else {
+            t = 32;
+            c32 = 1;
+        }
+        score[i] = s;
+        status[i] = st;
+        tier[i] = t;
+    }
+    // warp-aggregate the counters
+    for (int d = 16; d >= 1; d >>= 1) {
+        c8 += __shfl_xor_sync(0xffffffffu, c8, d);
+        c16 += __shfl_xor_sync(0xffffffffu, c16, d);
+        c32 += __shfl_xor_sync(0xffffffffu, c32, d);
+        cun += __shfl_xor_sync(0xffffffffu, cun, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c8) atomicAdd(&counters[0], c8);
+        if (c16) atomicAdd(&counters[1], c16);
+        if (c32) atomicAdd(&counters[2], c32);
+        if (cun) atomicAdd(&counters[3], cun);
+    }
+}
+
+// Collect the batch sequences that have at least one pair flagged "needs wide" (-1).
+__global__ void collect_wide_kernel(const int32_t *best, uint32_t n_rseq, uint32_t n_cseq, uint32_t *ids,
+                                    unsigned long long *counters) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rseq) return;
+    bool any = false;
+    for (uint32_t j = 0; j < n_cseq; ++j) any |= (best[(size_t)i * n_cseq + j] == -1);
+    if (any) {
+        unsigned long long slot = atomicAdd(&counters[4], 1ULL);
+        ids[slot] = i;
+    }
+}
+
+// Integer max-plus issue-rate microbenchmarks (roofline denominator).
+template <int KIND>
+__global__ void __launch_bounds__(256) dpx_peak_kernel(uint32_t *out, int iters, uint32_t seed) {
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = seed * (threadIdx.x + 1) + i;
+        b[i] = seed + i * 7u;
+    }
+    const uint32_t c = seed ^ 0x00030003u, g = 0x000a000au;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (KIND == 0) {
+                a[i] = __viaddmax_s16x2(a[i], c, b[i]);
+                b[i] = __viaddmax_s16x2(b[i], c, a[i]);
+            } else {
+                // the score kernel's per-cell-pair mix: 1 max3 + 1 add + 3 addmax + 0.5 max3
+                uint32_t x = __vimax3_s16x2(a[i], b[i], g) - g;
+                uint32_t h = __viaddmax_s16x2(a[(i + 1) & 7], c, x);
+                a[i] = __viaddmax_s16x2(a[i], c, h);
+                b[i] = __viaddmax_s16x2(b[i], c, h);
+                if (i & 1) a[(i + 3) & 7] = __vimax3_s16x2(a[(i + 3) & 7], h, x);
+            }
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= a[i] ^ b[i];
+    if (r == 0x12345678u) out[threadIdx.x] = r;
+}
+
+const KernelEntry *pick_score_kernel(uint32_t max_len, int n_csym) {
+    const KernelEntry *bestk = nullptr;
+    for (int i = 0; i < kNumScoreKernels; ++i) {
+        const KernelEntry &k = kScoreKernels[i];
+        if ((uint32_t)(k.G * k.K) < max_len) continue;
+        if (!bestk) {
+            bestk = &k;
+            continue;
+        }
+        int rows = k.G * k.K, brow = bestk->G * bestk->K;
+        // tightest row capacity wins; on ties a large alphabet (big per-task table) prefers the
+        // wider group (more threads per table), a small one the narrower group (less skew).
+        if (rows < brow || (rows == brow && ((n_csym > 8) ? (k.G > bestk->G) : (k.G < bestk->G)))) bestk = &k;
+    }
+    return bestk;
+}
+
+struct LaunchPlan {
+    int threads = 0, blocks_per_sm = 0;
+    size_t smem = 0;
+    int cols_in_smem = 0;
+};
+
+size_t score_smem_bytes(const zoe_cuda_ctx *ctx, const KernelEntry &k, int threads, int cols_in_smem) {
+    size_t tab = (size_t)score_tab_bytes(ctx->n_csym, k.G, k.K) * (threads / k.G);
+    size_t s = tab + 256 + (((size_t)ctx->n_csym * ctx->S + 15) & ~(size_t)15);
+    if (cols_in_smem) s += (ctx->ccodes.size() + 15) & ~(size_t)15;
+    return s;
+}
+
+int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, void (*fn)(const ScoreParams), LaunchPlan *plan) {
+    int best_warps = 0;
+    LaunchPlan bp;
+    for (int cols_in_smem = 1; cols_in_smem >= 0; --cols_in_smem) {
+        if (cols_in_smem && ctx->ccodes.size() > 96 * 1024) continue;
+        for (int threads : {512, 256, 128, 64, 32}) {
+            if (threads < k.G) continue;
+            size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem);
+            if (smem > 227 * 1024) continue;
+            int nb = 0;
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            int warps = nb * threads / 32;
+            if (warps > best_warps) {
+                best_warps = warps;
+                bp.threads = threads;
+                bp.blocks_per_sm = nb;
+                bp.smem = smem;
+                bp.cols_in_smem = cols_in_smem;
+            }
+        }
+        if (best_warps > 0) break;  // prefer staging the columns in shared memory when possible
+    }
+    if (best_warps == 0)
+        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no launch configuration fits shared memory (alphabet %d, G=%d K=%d)",
+                    ctx->n_csym, k.G, k.K);
+    *plan = bp;
+    return 0;
+}
+
+int upload_scoring_and_profiled(zoe_cuda_ctx *ctx) {
+    for (Device &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, d.ccodes.reserve(ctx->ccodes.size()));
+        CU(ctx, d.coff.reserve(ctx->coff.size() * sizeof(uint32_t)));
+        CU(ctx, d.wk.reserve(ctx->wk.size()));
+        CU(ctx, d.lut.reserve(256));
+        CU(ctx, cudaMemcpyAsync(d.ccodes.p, ctx->ccodes.data(), ctx->ccodes.size(), cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaMemcpyAsync(d.coff.p, ctx->coff.data(), ctx->coff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                d.stream));
+        CU(ctx, cudaMemcpyAsync(d.wk.p, ctx->wk.data(), ctx->wk.size(), cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaMemcpyAsync(d.lut.p, ctx->lut, 256, cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+    }
+    return 0;
+}
+
+// Split [0, n) over the devices by contiguous index range; no collective.
+void shard(zoe_cuda_ctx *ctx, uint64_t n) {
+    size_t nd = ctx->devs.size();
+    for (size_t k = 0; k < nd; ++k) {
+        uint64_t a = n * k / nd, b = n * (k + 1) / nd;
+        ctx->devs[k].n_first = a;
+        ctx->devs[k].n_count = b - a;
+    }
+}
+
+int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n) {
+    if (!ctx->have_profiled) return fail(ctx, ZOE_CUDA_E_STATE, "set_profiled must be called before a batch");
+    if (n > 0 && (!concat || !offsets)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null batch pointers");
+    if (n >= 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "batch too large");
+    uint32_t max_len = 0;
+    uint64_t tot = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "offsets must be non-decreasing");
+        uint64_t len = offsets[i + 1] - offsets[i];
+        if (len > 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "sequence too long");
+        max_len = std::max<uint32_t>(max_len, (uint32_t)len);
+        tot += len;
+    }
+    uint64_t prof_total = ctx->prof_off[ctx->n_prof];
+    ctx->staged_n = n;
+    ctx->staged_max_len = max_len;
+    ctx->staged_cells = tot * prof_total;
+    shard(ctx, n);
+    for (Device &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+        if (d.n_count == 0) continue;
+        uint64_t b0 = offsets[d.n_first], b1 = offsets[d.n_first + d.n_count];
+        d.rseq_bytes = b1 - b0;
+        CU(ctx, d.rseq.reserve(d.rseq_bytes + 16));
+        CU(ctx, d.roff.reserve((d.n_count + 1) * sizeof(uint64_t)));
+        if (d.rseq_bytes)
+            CU(ctx, cudaMemcpyAsync(d.rseq.p, concat + b0, d.rseq_bytes, cudaMemcpyHostToDevice, d.stream));
+        // offsets are rebased on the device by the kernel reading (off - base): keep them absolute
+        // on the host and subtract here in a small staging vector (pageable -> the copy is staged).
+        std::vector<uint64_t> rel(d.n_count + 1);
+        for (uint64_t i = 0; i <= d.n_count; ++i) rel[i] = offsets[d.n_first + i] - b0;
+        CU(ctx, cudaMemcpyAsync(d.roff.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));  // `rel` dies at scope end
+        size_t pairs = (size_t)d.n_count * ctx->n_prof;
+        CU(ctx, d.best.reserve(pairs * sizeof(int32_t)));
+        CU(ctx, d.score.reserve(pairs * sizeof(uint32_t)));
+        CU(ctx, d.status.reserve(pairs));
+        CU(ctx, d.tier.reserve(pairs));
+        CU(ctx, d.wide_ids.reserve((d.n_count + 1) * sizeof(uint32_t)));
+        CU(ctx, d.counters.reserve(16 * sizeof(unsigned long long)));
+    }
+    ctx->staged = true;
+    return 0;
+}
+
+int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed, const uint32_t *task_ids,
+                 uint32_t n_ids) {
+    void (*fn)(const ScoreParams) = packed ? k.packed : k.wide;
+    LaunchPlan plan;
+    int rc = plan_launch(ctx, k, fn, &plan);
+    if (rc) return rc;
+    ScoreParams p{};
+    p.rseq = d.rseq.as<uint8_t>();
+    p.roff = d.roff.as<uint64_t>();
+    p.task_ids = task_ids;
+    uint32_t n_seq = task_ids ? n_ids : (uint32_t)d.n_count;
+    p.n_rseq = n_seq;
+    p.n_tasks = packed ? (n_seq + 1) / 2 : n_seq;
+    p.ccodes = d.ccodes.as<uint8_t>();
+    p.coff = d.coff.as<uint32_t>();
+    p.n_cseq = ctx->n_prof;
+    p.ccodes_bytes = (uint32_t)ctx->ccodes.size();
+    p.cols_in_smem = plan.cols_in_smem;
+    p.wk = d.wk.as<int8_t>();
+    p.n_csym = ctx->n_csym;
+    p.S = ctx->S;
+    p.lut = d.lut.as<uint8_t>();
+    p.go = ctx->go;
+    p.ge = ctx->ge;
+    p.ovf_thresh = 32767 - std::max(ctx->max_weight, 0) - 1;
+    p.best = d.best.as<int32_t>();
+    if (p.n_tasks == 0) return 0;
+    CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    uint32_t groups_per_block = plan.threads / k.G;
+    uint32_t max_blocks = (uint32_t)(d.sm_count * plan.blocks_per_sm);
+    uint32_t need_blocks = (p.n_tasks + groups_per_block - 1) / groups_per_block;
+    uint32_t blocks = std::min(max_blocks, need_blocks);
+    fn<<<blocks, plan.threads, plan.smem, d.stream>>>(p);
+    CU(ctx, cudaGetLastError());
+    ctx->last_launches++;
+    return 0;
+}
+
+// The score pipeline on one device, all asynchronous on d.stream.
+int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
+    if (d.n_count == 0) return 0;
+    CU(ctx, cudaSetDevice(d.id));
+    if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass)
+        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "streamed sequences longer than %d are not supported yet",
+                    kMaxRowsSinglePass);
+    const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
+    if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
+    size_t pairs = (size_t)d.n_count * ctx->n_prof;
+    CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
+    // Static bound: can any packed 16-bit lane reach the overflow threshold?
+    uint64_t bound = (uint64_t)std::min<uint32_t>(ctx->staged_max_len, ctx->max_prof_len) *
+                     (uint64_t)std::max(ctx->max_weight, 0);
+    bool packed_ok = bound < 60000;  // above this nearly everything would be re-run: go wide directly
+    CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+    int rc;
+    if (packed_ok) {
+        rc = launch_score(ctx, d, *k, true, nullptr, 0);
+        if (rc) return rc;
+        if (bound >= (uint64_t)(32767 - ctx->max_weight - 1)) {
+            // escalation: re-run the flagged sequences at 32 bits (or_else_overflowed, output.rs:81-83)
+            uint32_t threads = 256, blocks = (uint32_t)((d.n_count + threads - 1) / threads);
+            collect_wide_kernel<<<blocks, threads, 0, d.stream>>>(d.best.as<int32_t>(), (uint32_t)d.n_count,
+                                                                  ctx->n_prof, d.wide_ids.as<uint32_t>(),
+                                                                  d.counters.as<unsigned long long>());
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+            unsigned long long n_wide = 0;
+            CU(ctx, cudaMemcpyAsync(&n_wide, d.counters.as<unsigned long long>() + 4, sizeof(n_wide),
+                                    cudaMemcpyDeviceToHost, d.stream));
+            CU(ctx, cudaStreamSynchronize(d.stream));
+            if (n_wide) {
+                rc = launch_score(ctx, d, *k, false, d.wide_ids.as<uint32_t>(), (uint32_t)n_wide);
+                if (rc) return rc;
+                ctx->stats.rerun_wide += n_wide * ctx->n_prof;
+            }
+        }
+    } else {
+        rc = launch_score(ctx, d, *k, false, nullptr, 0);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+    d.timed_kernel = true;
+    {
+        uint32_t threads = 256;
+        uint32_t blocks = (uint32_t)((pairs + threads - 1) / threads);
+        finalize_scores_kernel<<<blocks, threads, 0, d.stream>>>(d.best.as<int32_t>(), pairs, d.score.as<uint32_t>(),
+                                                                 d.status.as<uint8_t>(), d.tier.as<uint8_t>(),
+                                                                 d.counters.as<unsigned long long>());
+        CU(ctx, cudaGetLastError());
+        ctx->last_launches++;
+    }
+    return 0;
+}
+
+int sync_and_time(zoe_cuda_ctx *ctx) {
+    float total = 0.f, dp = 0.f;
+    for (Device &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaEventRecord(d.ev_end, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        float t = 0.f;
+        CU(ctx, cudaEventElapsedTime(&t, d.ev_begin, d.ev_end));
+        total = std::max(total, t);
+        if (d.timed_kernel) {
+            CU(ctx, cudaEventElapsedTime(&t, d.ev_k0, d.ev_k1));
+            dp = std::max(dp, t);
+        }
+    }
+    ctx->last_total_ms = total;
+    ctx->last_dp_ms = dp;
+    return 0;
+}
+
+int gather_stats(zoe_cuda_ctx *ctx) {
+    for (Device &d : ctx->devs) {
+        if (d.n_count == 0) continue;
+        CU(ctx, cudaSetDevice(d.id));
+        unsigned long long c[16];
+        CU(ctx, cudaMemcpy(c, d.counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+        ctx->stats.tier8 += c[0];
+        ctx->stats.tier16 += c[1];
+        ctx->stats.tier32 += c[2];
+        ctx->stats.unmapped += c[3];
+        ctx->stats.hazard += c[5];
+    }
+    ctx->stats.pairs = ctx->staged_n * ctx->n_prof;
+    ctx->stats.cells = ctx->staged_cells;
+    return 0;
+}
+
+void begin_call(zoe_cuda_ctx *ctx) {
+    ctx->last_launches = 0;
+    ctx->stats = zoe_cuda_stats{};
+    for (Device &d : ctx->devs) d.timed_kernel = false;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int zoe_cuda_create(zoe_cuda_ctx **out, const int *device_ids, int n_devices) {
+    if (!out) return ZOE_CUDA_E_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return ZOE_CUDA_E_CUDA;  // no CPU fallback: fail loudly
+    if (n_devices <= 0) n_devices = 1;
+    if (n_devices > count) return ZOE_CUDA_E_BAD_ARG;
+    zoe_cuda_ctx *ctx = new zoe_cuda_ctx();
+    for (int i = 0; i < 256; ++i) ctx->lut[i] = 0;
+    for (int k = 0; k < n_devices; ++k) {
+        Device d;
+        d.id = device_ids ? device_ids[k] : k;
+        if (d.id < 0 || d.id >= count || cudaSetDevice(d.id) != cudaSuccess ||
+            cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.id) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&d.ev_begin) != cudaSuccess || cudaEventCreate(&d.ev_end) != cudaSuccess ||
+            cudaEventCreate(&d.ev_k0) != cudaSuccess || cudaEventCreate(&d.ev_k1) != cudaSuccess) {
+            delete ctx;
+            return ZOE_CUDA_E_CUDA;
+        }
+        ctx->devs.push_back(d);
+    }
+    *out = ctx;
+    return 0;
+}
+
+void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
+    if (!ctx) return;
+    for (Device &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
+                          &d.wide_ids, &d.counters})
+            b->release();
+        if (d.ev_begin) cudaEventDestroy(d.ev_begin);
+        if (d.ev_end) cudaEventDestroy(d.ev_end);
+        if (d.ev_k0) cudaEventDestroy(d.ev_k0);
+        if (d.ev_k1) cudaEventDestroy(d.ev_k1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+const char *zoe_cuda_last_error(const zoe_cuda_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int zoe_cuda_set_scoring(zoe_cuda_ctx *ctx, const int8_t *weights, int S, const uint8_t byte_to_index[256],
+                         int8_t gap_open, int8_t gap_extend, int profiled_is_query) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (!weights || !byte_to_index || S < 1 || S > 64) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "bad scoring arguments");
+    int rc = validate_profile_args(1, gap_open, gap_extend);
+    if (rc) return fail(ctx, rc, "invalid gap penalties (open %d, extend %d)", gap_open, gap_extend);
+    for (int i = 0; i < 256; ++i)
+        if (byte_to_index[i] >= S) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "byte_to_index[%d] out of range", i);
+    ctx->S = S;
+    ctx->weights.assign(weights, weights + (size_t)S * S);
+    memcpy(ctx->lut, byte_to_index, 256);
+    ctx->go = -(int)gap_open;
+    ctx->ge = -(int)gap_extend;
+    ctx->profiled_is_query = profiled_is_query ? 1 : 0;
+    ctx->max_weight = *std::max_element(ctx->weights.begin(), ctx->weights.end());
+    ctx->have_scoring = true;
+    ctx->have_profiled = false;
+    ctx->staged = false;
+    return 0;
+}
+
+int zoe_cuda_set_lanes(zoe_cuda_ctx *ctx, int lanes_i8, int lanes_i16, int lanes_i32) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    for (int l : {lanes_i8, lanes_i16, lanes_i32})
+        if (l < 1 || l > 64 || (l & (l - 1))) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "lane counts must be powers of two <= 64");
+    ctx->lanes[0] = lanes_i8;
+    ctx->lanes[1] = lanes_i16;
+    ctx->lanes[2] = lanes_i32;
+    return 0;
+}
+
+int zoe_cuda_set_profiled(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint32_t n) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (!ctx->have_scoring) return fail(ctx, ZOE_CUDA_E_STATE, "set_scoring must be called before set_profiled");
+    if (n == 0 || !concat || !offsets) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "no profiled sequences");
+    uint64_t total = offsets[n] - offsets[0];
+    if (total > 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "profiled sequences too long");
+    uint32_t max_len = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+        if (offsets[j + 1] < offsets[j]) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "offsets must be non-decreasing");
+        uint64_t len = offsets[j + 1] - offsets[j];
+        // StripedProfile::new -> validate_profile_args: an empty profiled sequence is an error
+        if (len == 0) return fail(ctx, ZOE_CUDA_E_EMPTY_SEQUENCE, "profiled sequence %u is empty", j);
+        max_len = std::max<uint32_t>(max_len, (uint32_t)len);
+    }
+    ctx->n_prof = n;
+    ctx->max_prof_len = max_len;
+    ctx->prof_bytes.assign(concat + offsets[0], concat + offsets[n]);
+    ctx->prof_off.resize(n + 1);
+    ctx->coff.resize(n + 1);
+    for (uint32_t j = 0; j <= n; ++j) {
+        ctx->prof_off[j] = offsets[j] - offsets[0];
+        ctx->coff[j] = (uint32_t)ctx->prof_off[j];
+    }
+    // dense column-symbol codes: only the symbols that occur in the profiled set get a table row
+    int dense[64];
+    for (int i = 0; i < 64; ++i) dense[i] = -1;
+    std::vector<int> sym_of_dense;
+    ctx->ccodes.resize(total);
+    for (uint64_t i = 0; i < total; ++i) {
+        int s = ctx->lut[ctx->prof_bytes[i]];
+        if (dense[s] < 0) {
+            dense[s] = (int)sym_of_dense.size();
+            sym_of_dense.push_back(s);
+        }
+        ctx->ccodes[i] = (uint8_t)dense[s];
+    }
+    ctx->n_csym = (int)sym_of_dense.size();
+    // wk[c][r] = weights[streamed symbol r][profiled symbol c]  (profile.rs:290-291: the profile row is
+    // indexed by the streamed symbol, the lane by the profiled residue)
+    ctx->wk.assign((size_t)ctx->n_csym * ctx->S, 0);
+    for (int c = 0; c < ctx->n_csym; ++c)
+        for (int r = 0; r < ctx->S; ++r) ctx->wk[(size_t)c * ctx->S + r] = ctx->weights[(size_t)r * ctx->S + sym_of_dense[c]];
+    int rc = upload_scoring_and_profiled(ctx);
+    if (rc) return rc;
+    ctx->have_profiled = true;
+    ctx->staged = false;
+    return 0;
+}
+
+int zoe_cuda_stage_streamed(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    begin_call(ctx);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    if (rc) return rc;
+    return sync_and_time(ctx);
+}
+
+int zoe_cuda_run_score_staged(zoe_cuda_ctx *ctx) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (!ctx->staged) return fail(ctx, ZOE_CUDA_E_STATE, "nothing staged");
+    begin_call(ctx);
+    for (Device &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+    }
+    for (Device &d : ctx->devs) {
+        int rc = run_score_on_device(ctx, d);
+        if (rc) return rc;
+    }
+    int rc = sync_and_time(ctx);
+    if (rc) return rc;
+    return gather_stats(ctx);
+}
+
+int zoe_cuda_run_align_staged(zoe_cuda_ctx *ctx) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "align path not built yet");
+}
+
+int zoe_cuda_fetch_scores(zoe_cuda_ctx *ctx, uint32_t *score, uint8_t *status, uint8_t *tier) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (!ctx->staged) return fail(ctx, ZOE_CUDA_E_STATE, "nothing staged");
+    for (Device &d : ctx->devs) {
+        if (d.n_count == 0) continue;
+        CU(ctx, cudaSetDevice(d.id));
+        size_t first = (size_t)d.n_first * ctx->n_prof, pairs = (size_t)d.n_count * ctx->n_prof;
+        if (score)
+            CU(ctx, cudaMemcpyAsync(score + first, d.score.p, pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
+        if (status) CU(ctx, cudaMemcpyAsync(status + first, d.status.p, pairs, cudaMemcpyDeviceToHost, d.stream));
+        if (tier) CU(ctx, cudaMemcpyAsync(tier + first, d.tier.p, pairs, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (Device &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+    }
+    return 0;
+}
+
+int zoe_cuda_sw_score_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
+                            uint32_t *score, uint8_t *status, uint8_t *tier) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    begin_call(ctx);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    if (rc) return rc;
+    for (Device &d : ctx->devs) {
+        rc = run_score_on_device(ctx, d);
+        if (rc) return rc;
+    }
+    // D2H is queued behind the kernels on each device's stream; devices overlap with each other.
+    for (Device &d : ctx->devs) {
+        if (d.n_count == 0) continue;
+        CU(ctx, cudaSetDevice(d.id));
+        size_t first = (size_t)d.n_first * ctx->n_prof, pairs = (size_t)d.n_count * ctx->n_prof;
+        if (score)
+            CU(ctx, cudaMemcpyAsync(score + first, d.score.p, pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
+        if (status) CU(ctx, cudaMemcpyAsync(status + first, d.status.p, pairs, cudaMemcpyDeviceToHost, d.stream));
+        if (tier) CU(ctx, cudaMemcpyAsync(tier + first, d.tier.p, pairs, cudaMemcpyDeviceToHost, d.stream));
+    }
+    rc = sync_and_time(ctx);
+    if (rc) return rc;
+    return gather_stats(ctx);
+}
+
+int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *, const uint64_t *, uint64_t, uint32_t *, uint8_t *,
+                            uint8_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, uint64_t *, uint64_t,
+                            uint8_t *) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "align path not built yet");
+}
+
+int zoe_cuda_last_timing(const zoe_cuda_ctx *ctx, float *total_ms, float *dp_kernel_ms, uint32_t *kernel_launches) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (total_ms) *total_ms = ctx->last_total_ms;
+    if (dp_kernel_ms) *dp_kernel_ms = ctx->last_dp_ms;
+    if (kernel_launches) *kernel_launches = ctx->last_launches;
+    return 0;
+}
+
+int zoe_cuda_last_stats(const zoe_cuda_ctx *ctx, zoe_cuda_stats *out) {
+    if (!ctx || !out) return ZOE_CUDA_E_BAD_ARG;
+    *out = ctx->stats;
+    return 0;
+}
+
+int zoe_cuda_dpx_peak(zoe_cuda_ctx *ctx, int kind, double *giga_lane_instr_per_s, float *ms_out) {
+    if (!ctx || !giga_lane_instr_per_s) return ZOE_CUDA_E_BAD_ARG;
+    Device &d = ctx->devs[0];
+    CU(ctx, cudaSetDevice(d.id));
+    const int iters = 4096, threads = 256, blocks = d.sm_count * 8;
+    DevBuf out;
+    CU(ctx, out.reserve(threads * sizeof(uint32_t)));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+        if (kind == 0)
+            dpx_peak_kernel<0><<<blocks, threads, 0, d.stream>>>(out.as<uint32_t>(), iters, 12345u + rep);
+        else
+            dpx_peak_kernel<1><<<blocks, threads, 0, d.stream>>>(out.as<uint32_t>(), iters, 12345u + rep);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        float ms = 0.f;
+        CU(ctx, cudaEventElapsedTime(&ms, d.ev_k0, d.ev_k1));
+        if (rep > 0) best_ms = std::min(best_ms, ms);
+    }
+    out.release();
+    // kind 0: 16 DPX instructions per inner iteration; kind 1: 8 cell pairs x 5.5 instructions
+    double instr_per_thread = (kind == 0) ? 16.0 * iters : 8.0 * 5.5 * iters;
+    double lanes = (double)blocks * threads;
+    *giga_lane_instr_per_s = instr_per_thread * lanes / (best_ms * 1e-3) / 1e9;
+    if (ms_out) *ms_out = best_ms;
+    return 0;
+}
+
+void *zoe_cuda_stream(zoe_cuda_ctx *ctx, int dev_index) {
+    if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return nullptr;
+    return (void *)ctx->devs[dev_index].stream;
+}
+
+}  // extern "C"
