@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- SW GCUPS of the B200 path on BASELINE.json's configurations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input.  The default workload is
+BASELINE.json configs[1]: 1M x 150-nt reads vs 8 influenza-A-length segments, score only
+(2.04e12 cells per GPU per step).  Multi-GPU: one process per GPU (torchrun), each rank scores
+its own 1M-read shard, no collective on the data path ("weak": per-GPU work is fixed).
+
+`value`  = GCUPS with the batch already resident in HBM (CUDA events on the library's stream).
+`e2e`    = GCUPS through the host-buffer C-ABI call (pinned host -> device copies and the
+           device -> host result copies inside the timed region).
+`--impl reference` times the CPU restatement of zoe's striped path (oracle/zoe_sw_cpu.cpp) on all
+host threads; zoe itself (Rust nightly) cannot be built in this image.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sw_gcups"
+UNIT = "GCUPS"
+DPX_INSTR_PER_CELL = 2.25  # 4.5 DPX/ALU instructions per packed cell pair (DESIGN.md "score kernel")
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def make_workload(config: int, n_override: int | None, rank: int):
+    """Returns (name, matrix, gap_open, gap_extend, targets, (buf, offs), mode)."""
+    from zoe_b200 import BLOSUM_62, WeightMatrix, synth
+
+    dna = WeightMatrix.new_dna_matrix(2, -5, b"N")
+    if config == 1:
+        n = n_override or 10_000
+        t, r = synth.config1(ROOT, n_reads=n, seed=1 + 1000 * rank)
+        return (f"cfg1: {n} x 150nt reads vs 1704nt HA, score", dna, -10, -1, t, synth.fixed_len_batch(r), "score")
+    if config == 2:
+        n = n_override or 1_000_000
+        t, r = synth.config2(n_reads=n, seed_reads=3 + 1000 * rank)
+        return (f"cfg2: {n} x 150nt reads vs 8 flu-A-length segments (13588nt), score-only", dna, -10, -1, t,
+                synth.fixed_len_batch(r), "score")
+    if config == 3:
+        n = n_override or 1_000_000
+        t, r = synth.config3(ROOT, n_reads=n, seed=4 + 1000 * rank)
+        return (f"cfg3: {n} x 150nt reads vs 1704nt HA, align with traceback", dna, -10, -1, t,
+                synth.fixed_len_batch(r), "align")
+    if config == 5:
+        n = n_override or 1_000_000
+        t, q = synth.config5(n_queries=n, seed_queries=8 + 1000 * rank)
+        return (f"cfg5: {n} x 300aa queries vs 566aa target, BLOSUM62, score-only", BLOSUM_62, -10, -1, t,
+                synth.fixed_len_batch(q), "score")
+    raise SystemExit(f"config {config} is not a bench workload yet")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads, width_bits=256):
+    from oracle import cpu_baseline as CB
+    from zoe_b200 import synth
+
+    pbuf, poff = synth.pack([np.asarray(t, dtype=np.uint8) for t in targets])
+    o = offs[: n_sample + 1]
+    t0 = time.perf_counter()
+    res = CB.score_batch(pbuf, poff, buf[: int(o[-1])], o, matrix.weights, matrix.mapping.index_map, go, ge,
+                         width_bits=width_bits, n_threads=threads)
+    dt = time.perf_counter() - t0
+    cells = int(o[-1]) * int(poff[-1])
+    return cells / dt / 1e9, dt, res
+
+
+def run_reference(args):
+    """`--impl reference`: the CPU restatement on all host threads, rank 0 only."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as CB
+
+    name, matrix, go, ge, targets, (buf, offs), mode = make_workload(args.config, args.n, 0)
+    threads = CB.hardware_threads()
+    n_total = len(offs) - 1
+    # calibrate a bounded sample: ~4 s of CPU work per step
+    probe = min(n_total, 2000)
+    g0, dt0, _ = cpu_port_run(matrix, go, ge, targets, buf, offs, probe, threads)
+    n_sample = int(min(n_total, max(probe, probe * 4.0 / max(dt0, 1e-3))))
+    for _ in range(args.warmup):
+        cpu_port_run(matrix, go, ge, targets, buf, offs, min(n_sample, probe), threads)
+    times = []
+    for _ in range(args.steps):
+        g, dt, _ = cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads)
+        times.append(dt)
+    prof_total = sum(len(t) for t in targets)
+    cells = int(offs[n_sample]) * prof_total
+    value = cells * len(times) / sum(times) / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "i8/i16/i32 (zoe tiers, w256 lanes)", "data": "synthetic",
+        "config": {"workload": name, "sample": f"first {n_sample} sequences of the workload per step",
+                   "orientation": "profile = reference side, reads streamed"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} sequences x {prof_total} profiled residues per step, {CB.isa()}, "
+                                   "C++ restatement of zoe's striped sw_simd_score + i8->i16->i32 escalation "
+                                   "(zoe itself needs nightly Rust: not buildable here)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--n", type=int, default=None, help="override the number of streamed sequences per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    distributed = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: zoe_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    in_process_devices = args.gpus if (not distributed and args.gpus > 1) else 1
+
+    from zoe_b200 import CudaProfiles
+
+    name, matrix, go, ge, targets, (buf, offs), mode = make_workload(args.config, args.n, rank)
+    if in_process_devices > 1:
+        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, n_devices=in_process_devices)
+    else:
+        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, devices=[local_rank])
+    n = len(offs) - 1
+    n_prof = len(targets)
+    prof_total = sum(len(t) for t in targets)
+    cells_per_step = int(offs[-1]) * prof_total  # per process
+
+    # pinned host buffers for the end-to-end leg
+    t_buf = torch.from_numpy(buf).pin_memory()
+    t_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
+    h_buf, h_offs = t_buf.numpy(), t_offs.numpy().view(np.uint64)
+    t_score = torch.empty(n * n_prof, dtype=torch.int32).pin_memory()
+    t_status = torch.empty(n * n_prof, dtype=torch.uint8).pin_memory()
+    t_tier = torch.empty(n * n_prof, dtype=torch.uint8).pin_memory()
+    h_score, h_status, h_tier = t_score.numpy().view(np.uint32), t_status.numpy(), t_tier.numpy()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    stream = torch.cuda.ExternalStream(prof.stream_handle(0), device=torch.device("cuda", local_rank))
+    run_staged = prof.run_score_staged if mode == "score" else prof.run_align_staged
+
+    # ---------------- device-resident leg (`value`) ----------------
+    prof.stage(h_buf, h_offs)
+    for _ in range(args.warmup):
+        run_staged()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dp_ms, launches = [], 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        run_staged()
+        tm = prof.last_timing()
+        dp_ms.append(tm["dp_kernel_ms"])
+        launches += tm["kernel_launches"]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    stats = prof.last_stats()
+    total_cells = sum_over_ranks(float(cells_per_step))
+    value = total_cells * args.steps / (dev_ms * 1e-3) / 1e9
+
+    # ---------------- end-to-end leg (`e2e`): host buffers in, host results out ----------------
+    e2e = None
+    if mode == "score":
+        for _ in range(min(args.warmup, 2)):
+            prof.sw_score_into(h_buf, h_offs, h_score, h_status, h_tier)
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev2.record(stream)
+        for _ in range(args.steps):
+            prof.sw_score_into(h_buf, h_offs, h_score, h_status, h_tier)
+            launches += prof.last_timing()["kernel_launches"]
+        ev3.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), wall_ms))
+        e2e = {"value": total_cells * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_buf.nbytes + h_offs.nbytes),
+               "d2h_bytes_per_step": int(h_score.nbytes + h_status.nbytes + h_tier.nbytes),
+               "ms_per_step": e2e_ms / args.steps, "result_checksum": int(h_score.sum(dtype=np.uint64))}
+
+    # ---------------- roofline of the dominant kernel ----------------
+    dpx_g, _ = prof.dpx_peak(0)  # G lane-instr/s, measured live on this GPU
+    peak_gcups = dpx_g / DPX_INSTR_PER_CELL
+    kernel_gcups = cells_per_step / (float(np.mean(dp_ms)) * 1e-3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    in_bytes = float(h_buf.nbytes + h_offs.nbytes + n * n_prof * 4)
+    roofline = {
+        "bound": "alu", "achieved": kernel_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
+        "traffic": None,
+        "note": ("integer max-plus (DPX on the ALU pipe) bound, not hbm/tensor: peak = live-measured "
+                 "VIADDMNMX.S16x2 issue rate (%.0f G lane-instr/s) / %.2f instr per cell; kernel = sw_score_kernel, "
+                 "avg of %d launches, CUDA events on the library stream" % (dpx_g, DPX_INSTR_PER_CELL, len(dp_ms))),
+        "hbm": {"algorithmic_bytes_per_launch": in_bytes, "achieved_gbs": in_bytes / (float(np.mean(dp_ms)) * 1e-3) / 1e9,
+                "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "frac": in_bytes / (float(np.mean(dp_ms)) * 1e-3) / 1e9 / hbm_peak},
+    }
+
+    # ---------------- CPU baseline + parity on a bounded sample (rank 0, N=1 only) ----------------
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "score":
+        from oracle import cpu_baseline as CB
+        threads = CB.hardware_threads()
+        probe = min(n, 2000)
+        g0, dt0, _ = cpu_port_run(matrix, go, ge, targets, buf, offs, probe, threads)
+        n_sample = int(min(n, max(probe, probe * 12.0 / max(dt0, 1e-3))))
+        g, dt, (c_score, c_status, c_tier) = cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads)
+        cpu = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {n_sample} sequences x all {n_prof} profiled ({dt:.1f} s, {CB.isa()}, w256 lanes)"}
+        g_score = h_score.reshape(n, n_prof)[:n_sample]
+        g_status = h_status.reshape(n, n_prof)[:n_sample]
+        g_tier = h_tier.reshape(n, n_prof)[:n_sample]
+        some = c_status == 0
+        mism = int((g_status != c_status).sum() + (g_score[some] != c_score[some]).sum()
+                   + (g_tier[some] != c_tier[some]).sum())
+        parity = {"checked_pairs": int(n_sample * n_prof), "mismatches": mism, "against": "cpu port (oracle/zoe_sw_cpu.cpp)"}
+
+    if rank == 0:
+        n_gpus = world if distributed else in_process_devices
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "s16x2 packed (s32 on overflow)", "data": "synthetic",
+            "config": {"workload": name, "sequences_per_gpu": n, "profiled": n_prof, "mode": mode,
+                       "cells_per_gpu_per_step": cells_per_step, "l2": "inputs_exceed_l2" if h_buf.nbytes > 126e6 else
+                       "inputs_smaller_than_l2 (compute-bound kernel; sequence bytes are read once)",
+                       "orientation": "profile = reference side, reads streamed (SeqSrc::Query)", "lanes": "w256"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "parity": parity, "tiers": stats,
+        }
+        print(json.dumps(line), flush=True)
+    prof.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,7 +73,7 @@ def test_golden_known_answers(seqs):
 def test_config1_sample_vs_oracle():
     targets, reads = synth.config1(ROOT, n_reads=600)
     score, status, tier = check(targets, list(reads), W25)
-    assert (tier == 16).sum() > 300  # true-origin reads escalate i8 -> i16
+    assert (tier == 16).sum() > 200  # forward-strand true-origin reads escalate i8 -> i16 (half the reads are reverse strand)
     assert (tier == 8).sum() > 10
 
 
@@ -124,7 +124,7 @@ def test_various_scorings_random():
         for _ in range(40):
             L = int(rng.integers(5, 160))
             s = synth.random_dna(rng, L)
-            if L > 30:
+            if L > 40:
                 st = int(rng.integers(0, 120 - 30))
                 s[5:35] = target[st:st + 30]
             seqs.append(s)

@@ -223,6 +223,14 @@ class CudaProfiles:
         shape = (n, self.n_profiled)
         return score[:pairs].reshape(shape), status[:pairs].reshape(shape), tier[:pairs].reshape(shape)
 
+    def sw_score_into(self, buf: np.ndarray, offs: np.ndarray, score: np.ndarray, status: np.ndarray, tier: np.ndarray):
+        """Like :meth:`sw_score_arrays` but writes into caller-owned (ideally pinned) output arrays."""
+        self._check(self._lib.zoe_cuda_sw_score_batch(self._h, _p(buf, C.c_uint8), _p(offs, C.c_uint64), len(offs) - 1,
+                                                      _p(score, C.c_uint32), _p(status, C.c_uint8), _p(tier, C.c_uint8)))
+
+    def stream_handle(self, dev_index: int = 0) -> int:
+        return int(self._lib.zoe_cuda_stream(self._h, dev_index) or 0)
+
     def stage(self, buf: np.ndarray, offs: np.ndarray):
         self._check(self._lib.zoe_cuda_stage_streamed(self._h, _p(buf, C.c_uint8), _p(offs, C.c_uint64), len(offs) - 1))
         self._staged_n = len(offs) - 1
