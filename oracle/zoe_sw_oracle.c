@@ -798,3 +798,106 @@ int zo_striped_profile_dump(const uint8_t *profiled, uint64_t m, const zo_scorin
     zo_profile_free(&p);
     return tot <= out_cap ? 0 : ZO_ERR_BAD_ARG;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Hazard study support (tests/test_hazard_rule.py, DESIGN.md "tie hazards").
+ * Same as zo_scalar_align, but also reports whether the traceback consulted a cell whose
+ * canonical flags have both UP and LEFT set (E == H == F, H > 0): the only situation in which the
+ * striped layout (lane count) can change which of two equal-score gap orders the CIGAR shows.
+ * hazard bit 0: consulted cell with UP && LEFT.
+ * --------------------------------------------------------------------------------------------- */
+int zo_scalar_align_hazard(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n,
+                           const zo_scoring *sc, int streamed_is_query, zo_alignment *out, uint8_t *ops,
+                           uint32_t *lens, uint32_t cap, int *hazard) {
+    int rc = zo_validate_profile_args(m, sc->gap_open, sc->gap_extend);
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    *hazard = 0;
+    if (n == 0) return ZO_UNMAPPED;
+    int32_t go = sc->gap_open, ge = sc->gap_extend;
+    int32_t best_score = 0;
+    uint64_t r_end = 0, c_end = 0;
+    int32_t *h_row = (int32_t *)calloc(m, sizeof(int32_t));
+    int32_t *e_row = (int32_t *)malloc(sizeof(int32_t) * m);
+    for (uint64_t c = 0; c < m; c++) e_row[c] = go;
+    uint8_t *bt = (uint8_t *)calloc((size_t)n * m, 1);
+    uint8_t *tie = (uint8_t *)calloc((size_t)n * m, 1);
+    for (uint64_t r = 0; r < n; r++) {
+        int ri = sc->map[streamed[r]];
+        int32_t f = go, h = 0;
+        for (uint64_t c = 0; c < m; c++) {
+            uint8_t *cell = bt + (size_t)r * m + c;
+            h += sc->weights[ri * sc->S + sc->map[profiled[c]]];
+            int32_t e = e_row[c];
+            if (e > h) h = e;
+            if (f > h) h = f;
+            if (h < 0) h = 0;
+            if (h > best_score) {
+                best_score = h;
+                r_end = r;
+                c_end = c;
+            }
+            if (e == h) *cell |= F_UP;
+            if (f == h) *cell |= F_LEFT;
+            if (e == h && f == h && h != 0) tie[(size_t)r * m + c] = 1;
+            if (h == 0) *cell = F_STOP;
+            int32_t next_diag = h_row[c];
+            h_row[c] = h;
+            h += go;
+            e = e + ge > h ? e + ge : h;
+            f = f + ge > h ? f + ge : h;
+            if (h != go) {
+                if (e > h) *cell |= F_UP_EXT;
+                if (f > h) *cell |= F_LEFT_EXT;
+            }
+            h = next_diag;
+            e_row[c] = e;
+        }
+    }
+    int status;
+    zo_states st = {ops, lens, 0, cap, 0};
+    if (best_score == 0) {
+        status = ZO_UNMAPPED;
+    } else {
+        /* replay of zo_to_alignment's walk, only to collect the hazard bit */
+        {
+            uint64_t r = r_end + 1, c = c_end + 1;
+            uint8_t op = 0;
+            uint64_t cr = r_end, cc = c_end;
+            uint8_t cur = bt[(size_t)cr * m + cc];
+            while (!(cur & F_STOP) && r > 0 && c > 0) {
+                if (tie[(size_t)cr * m + cc]) *hazard |= 1;
+                if (op == 'D' && (cur & F_UP_EXT)) {
+                    op = 'D';
+                    r -= 1;
+                } else if (op == 'I' && (cur & F_LEFT_EXT)) {
+                    op = 'I';
+                    c -= 1;
+                } else if (cur & F_UP) {
+                    op = 'D';
+                    r -= 1;
+                } else if (cur & F_LEFT) {
+                    op = 'I';
+                    c -= 1;
+                } else {
+                    op = 'M';
+                    r -= 1;
+                    c -= 1;
+                }
+                cr = r > 0 ? r - 1 : 0;
+                cc = c > 0 ? c - 1 : 0;
+                cur = bt[(size_t)cr * m + cc];
+            }
+        }
+        zo_bt b = {bt, 0, 0, 0, m};
+        zo_to_alignment(&b, (uint32_t)best_score, r_end, c_end, n, m, out, &st);
+        if (streamed_is_query) zo_invert(out, &st);
+        status = ZO_SOME;
+    }
+    free(h_row);
+    free(e_row);
+    free(bt);
+    free(tie);
+    if (st.overflow) return ZO_ERR_CIGAR_CAP;
+    return status;
+}
