@@ -72,6 +72,7 @@ struct Ops<true> {
         return __vimax3_s16x2(a, b, c);
     }
     static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
     static __device__ __forceinline__ uint32_t splat(int v) {
         return (uint32_t)(v & 0xffff) | ((uint32_t)(v & 0xffff) << 16);
     }
@@ -86,6 +87,7 @@ struct Ops<false> {
         return (uint32_t)__vimax3_s32((int)a, (int)b, (int)c);
     }
     static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return (uint32_t)max((int)a, (int)b); }
+    static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return (uint32_t)min((int)a, (int)b); }
     static __device__ __forceinline__ uint32_t splat(int v) { return (uint32_t)v; }
 };
 

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "sw_align.cuh"
 #include "sw_score.cuh"
 
 using namespace zoe_cuda;
@@ -56,6 +57,10 @@ struct Device {
     DevBuf ccodes, coff, wk, lut;
     // batch state
     DevBuf rseq, roff, best, score, status, tier, wide_ids, counters;
+    // align state
+    DevBuf pbytes, ends, flags, flag_base, ref_start, ref_end, query_start, query_end, hazard, hazard_list;
+    DevBuf cig_scratch, cig_count, cig_off, cig_out, ex_hbuf, ex_fbuf, ex_cig, weights;
+    uint64_t cig_total = 0;
     uint64_t n_first = 0, n_count = 0;  // shard of the streamed batch owned by this device
     uint64_t rseq_bytes = 0;
     bool timed_kernel = false;
@@ -65,10 +70,11 @@ struct KernelEntry {
     int G, K;
     void (*packed)(const ScoreParams);
     void (*wide)(const ScoreParams);
+    void (*fill)(const AlignParams);
 };
 
 #define ZK(G, K) \
-    KernelEntry { G, K, sw_score_kernel<G, K, true>, sw_score_kernel<G, K, false> }
+    KernelEntry { G, K, sw_score_kernel<G, K, true>, sw_score_kernel<G, K, false>, sw_align_fill_kernel<G, K, true> }
 
 // Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
 // sequence of a batch.  G = 8 serves short reads (150 nt -> 8 x 19), G = 32 the longest rows
@@ -109,6 +115,7 @@ struct zoe_cuda_ctx {
     uint32_t staged_max_len = 0;
     uint64_t staged_cells = 0;
     bool staged = false;
+    uint64_t flag_budget_bytes = 0;  // 0 = auto (a fraction of free device memory)
     // measurements
     float last_total_ms = 0.f, last_dp_ms = 0.f;
     uint32_t last_launches = 0;
@@ -262,7 +269,8 @@ size_t score_smem_bytes(const zoe_cuda_ctx *ctx, const KernelEntry &k, int threa
     return s;
 }
 
-int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, void (*fn)(const ScoreParams), LaunchPlan *plan) {
+template <class Fn>
+int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan) {
     int best_warps = 0;
     LaunchPlan bp;
     for (int cols_in_smem = 1; cols_in_smem >= 0; --cols_in_smem) {
@@ -312,6 +320,12 @@ int upload_scoring_and_profiled(zoe_cuda_ctx *ctx) {
                                 d.stream));
         CU(ctx, cudaMemcpyAsync(d.wk.p, ctx->wk.data(), ctx->wk.size(), cudaMemcpyHostToDevice, d.stream));
         CU(ctx, cudaMemcpyAsync(d.lut.p, ctx->lut, 256, cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, d.pbytes.reserve(ctx->prof_bytes.size()));
+        CU(ctx, d.weights.reserve(ctx->weights.size()));
+        CU(ctx, cudaMemcpyAsync(d.pbytes.p, ctx->prof_bytes.data(), ctx->prof_bytes.size(), cudaMemcpyHostToDevice,
+                                d.stream));
+        CU(ctx, cudaMemcpyAsync(d.weights.p, ctx->weights.data(), ctx->weights.size(), cudaMemcpyHostToDevice,
+                                d.stream));
         CU(ctx, cudaStreamSynchronize(d.stream));
     }
     return 0;
@@ -467,6 +481,297 @@ int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// align pipeline (one device): chunks of batch sequences -> fill -> traceback -> exact -> compaction
+// ---------------------------------------------------------------------------------------------
+__global__ void apply_wide_scores_kernel(const uint32_t *list, uint32_t n, const int32_t *best, uint32_t *score,
+                                         uint8_t *status, uint8_t *tier) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t gid = list[i];
+    if (status[gid] != 0xFF) return;
+    int32_t b = best[gid];
+    score[gid] = b > 0 ? (uint32_t)b : 0u;
+    status[gid] = b > 0 ? ZOE_CUDA_SOME : ZOE_CUDA_UNMAPPED;
+    tier[gid] = b <= 254 ? 8 : (b <= 65534 ? 16 : 32);
+}
+
+__global__ void collect_wide_range_kernel(const int32_t *best, uint32_t first, uint32_t count, uint32_t n_cseq,
+                                          uint32_t *ids, unsigned long long *counters) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t seq = first + i;
+    bool any = false;
+    for (uint32_t j = 0; j < n_cseq; ++j) any |= (best[(size_t)seq * n_cseq + j] == -1);
+    if (any) {
+        unsigned long long slot = atomicAdd(&counters[4], 1ULL);
+        ids[slot] = seq;
+    }
+}
+
+__global__ void count_status_kernel(const uint32_t *score, const uint8_t *status, uint64_t n,
+                                    unsigned long long *counters) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c8 = 0, c16 = 0, c32 = 0, cun = 0;
+    if (i < n) {
+        if (status[i] == ZOE_CUDA_SOME) {
+            uint32_t s = score[i];
+            if (s <= 254) c8 = 1; else if (s <= 65534) c16 = 1; else c32 = 1;
+        } else {
+            cun = 1;
+        }
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        c8 += __shfl_xor_sync(0xffffffffu, c8, d);
+        c16 += __shfl_xor_sync(0xffffffffu, c16, d);
+        c32 += __shfl_xor_sync(0xffffffffu, c32, d);
+        cun += __shfl_xor_sync(0xffffffffu, cun, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c8) atomicAdd(&counters[0], c8);
+        if (c16) atomicAdd(&counters[1], c16);
+        if (c32) atomicAdd(&counters[2], c32);
+        if (cun) atomicAdd(&counters[3], cun);
+    }
+}
+
+int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) {
+    d.cig_total = 0;
+    if (d.n_count == 0) return 0;
+    CU(ctx, cudaSetDevice(d.id));
+    if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass)
+        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "streamed sequences longer than %d are not supported by the align path yet",
+                    kMaxRowsSinglePass);
+    const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
+    if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
+    const int NW = align_words_per_lane(k->K);
+    const uint32_t n_prof = ctx->n_prof;
+    const size_t pairs = (size_t)d.n_count * n_prof;
+
+    // flag layout of one task: every profiled sequence back to back
+    std::vector<uint64_t> flag_base(n_prof);
+    uint64_t task_stride = 0;
+    for (uint32_t j = 0; j < n_prof; ++j) {
+        flag_base[j] = task_stride;
+        task_stride += (uint64_t)(ctx->coff[j + 1] - ctx->coff[j]) * k->G * NW;
+    }
+    // chunk size from the flag-memory budget
+    size_t free_b = 0, total_b = 0;
+    CU(ctx, cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = ctx->flag_budget_bytes ? ctx->flag_budget_bytes : (uint64_t)(free_b * 0.55);
+    budget = std::min<uint64_t>(budget, (uint64_t)48 << 30);
+    uint64_t tasks_cap = std::max<uint64_t>(1, budget / (task_stride * 4));
+    uint64_t chunk_seqs = std::min<uint64_t>(d.n_count, tasks_cap * 2);
+    if (chunk_seqs > 1) chunk_seqs &= ~1ULL;
+    const uint32_t cig_cap = 2 * std::min<uint32_t>(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->max_prof_len) + 4;
+
+    CU(ctx, d.flag_base.reserve(n_prof * sizeof(uint64_t)));
+    CU(ctx, cudaMemcpyAsync(d.flag_base.p, flag_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    CU(ctx, d.ends.reserve(pairs * sizeof(AlignEnd)));
+    CU(ctx, d.flags.reserve(((chunk_seqs + 1) / 2) * task_stride * 4));
+    for (DevBuf *b : {&d.ref_start, &d.ref_end, &d.query_start, &d.query_end, &d.cig_count, &d.best, &d.score})
+        CU(ctx, b->reserve(pairs * sizeof(uint32_t)));
+    CU(ctx, d.status.reserve(pairs));
+    CU(ctx, d.tier.reserve(pairs));
+    CU(ctx, d.hazard.reserve(pairs));
+    CU(ctx, d.hazard_list.reserve((size_t)chunk_seqs * n_prof * sizeof(uint32_t)));
+    CU(ctx, d.cig_scratch.reserve((size_t)chunk_seqs * n_prof * cig_cap * sizeof(uint32_t)));
+    CU(ctx, d.cig_off.reserve((pairs + 1) * sizeof(uint64_t)));
+    CU(ctx, d.cig_out.reserve(std::max<uint64_t>(cigar_cap_words, 1) * sizeof(uint32_t)));
+    CU(ctx, d.wide_ids.reserve((d.n_count + 1) * sizeof(uint32_t)));
+    CU(ctx, d.counters.reserve(16 * sizeof(unsigned long long)));
+    CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
+    unsigned long long *ctr = d.counters.as<unsigned long long>();
+
+    LaunchPlan plan;
+    int rc = plan_launch(ctx, *k, k->fill, &plan);
+    if (rc) return rc;
+    CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    const bool all_exact = (ctx->go == 0);
+    const int invert = ctx->profiled_is_query ? 0 : 1;
+    float dp_ms_total = 0.f;
+
+    for (uint64_t c0 = 0; c0 < d.n_count; c0 += chunk_seqs) {
+        const uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_seqs, d.n_count - c0);
+        // ---- fill ----
+        AlignParams ap{};
+        ScoreParams &p = ap.s;
+        p.rseq = d.rseq.as<uint8_t>();
+        p.roff = d.roff.as<uint64_t>();
+        p.task_ids = nullptr;
+        p.n_rseq = cn;
+        p.n_tasks = (cn + 1) / 2;
+        p.ccodes = d.ccodes.as<uint8_t>();
+        p.coff = d.coff.as<uint32_t>();
+        p.n_cseq = n_prof;
+        p.ccodes_bytes = (uint32_t)ctx->ccodes.size();
+        p.cols_in_smem = plan.cols_in_smem;
+        p.wk = d.wk.as<int8_t>();
+        p.n_csym = ctx->n_csym;
+        p.S = ctx->S;
+        p.lut = d.lut.as<uint8_t>();
+        p.go = ctx->go;
+        p.ge = ctx->ge;
+        p.ovf_thresh = 32767 - std::max(ctx->max_weight, 0) - 1 - ctx->go;
+        p.best = nullptr;
+        ap.ends = d.ends.as<AlignEnd>();
+        ap.flags = d.flags.as<uint32_t>();
+        ap.flag_base = d.flag_base.as<uint64_t>();
+        ap.task_stride = task_stride;
+        ap.chunk_first = (uint32_t)c0;
+        uint32_t groups_per_block = plan.threads / k->G;
+        uint32_t blocks = std::min<uint32_t>((uint32_t)(d.sm_count * plan.blocks_per_sm),
+                                             (p.n_tasks + groups_per_block - 1) / groups_per_block);
+        CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+        k->fill<<<blocks, plan.threads, plan.smem, d.stream>>>(ap);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+        ctx->last_launches++;
+
+        // ---- traceback ----
+        CU(ctx, cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(unsigned long long), d.stream));  // [4] wide seqs, [5] exact list
+        TraceParams t{};
+        t.ends = ap.ends;
+        t.flags = ap.flags;
+        t.flag_base = ap.flag_base;
+        t.task_stride = task_stride;
+        t.roff = p.roff;
+        t.coff = p.coff;
+        t.n_cseq = n_prof;
+        t.chunk_first = (uint32_t)c0;
+        t.seq_ids = nullptr;
+        t.n_slots = cn;
+        t.best_arr = d.best.as<int32_t>();
+        t.G = k->G;
+        t.K = k->K;
+        t.NW = NW;
+        t.packed = 1;
+        t.invert = invert;
+        t.score = d.score.as<uint32_t>();
+        t.status = d.status.as<uint8_t>();
+        t.tier = d.tier.as<uint8_t>();
+        t.hazard = d.hazard.as<uint8_t>();
+        t.ref_start = d.ref_start.as<uint32_t>();
+        t.ref_end = d.ref_end.as<uint32_t>();
+        t.query_start = d.query_start.as<uint32_t>();
+        t.query_end = d.query_end.as<uint32_t>();
+        t.cig_scratch = d.cig_scratch.as<uint32_t>();
+        t.cig_count = d.cig_count.as<uint32_t>();
+        t.cig_cap = cig_cap;
+        t.counters = ctr;
+        t.hazard_list = d.hazard_list.as<uint32_t>();
+        t.all_exact = all_exact ? 1 : 0;
+        const uint32_t cpairs = cn * n_prof;
+        sw_traceback_kernel<<<(cpairs + 127) / 128, 128, 0, d.stream>>>(t);
+        CU(ctx, cudaGetLastError());
+        ctx->last_launches++;
+
+        unsigned long long hc[5] = {0, 0, 0, 0, 0};  // ctr[4..8]
+        CU(ctx, cudaMemcpyAsync(hc, ctr + 4, sizeof(hc), cudaMemcpyDeviceToHost, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        {
+            float ms = 0.f;
+            CU(ctx, cudaEventElapsedTime(&ms, d.ev_k0, d.ev_k1));
+            dp_ms_total += ms;
+        }
+        const uint32_t n_exact = (uint32_t)hc[1];
+        if (hc[4] > 0) {
+            // packed overflow: exact scores from the 32-bit score kernel (or_else_overflowed, output.rs:81-83)
+            collect_wide_range_kernel<<<(cn + 255) / 256, 256, 0, d.stream>>>(d.best.as<int32_t>(), (uint32_t)c0, cn, n_prof,
+                                                                              d.wide_ids.as<uint32_t>(), ctr);
+            CU(ctx, cudaGetLastError());
+            unsigned long long n_wide = 0;
+            CU(ctx, cudaMemcpyAsync(&n_wide, ctr + 4, sizeof(n_wide), cudaMemcpyDeviceToHost, d.stream));
+            CU(ctx, cudaStreamSynchronize(d.stream));
+            rc = launch_score(ctx, d, *k, false, d.wide_ids.as<uint32_t>(), (uint32_t)n_wide);
+            if (rc) return rc;
+            apply_wide_scores_kernel<<<(n_exact + 255) / 256, 256, 0, d.stream>>>(
+                d.hazard_list.as<uint32_t>(), n_exact, d.best.as<int32_t>(), t.score, t.status, t.tier);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches += 2;
+            ctx->stats.rerun_wide += hc[4];
+        }
+        if (n_exact > 0) {
+            // ---- literal striped emulation for hazard / overflow / gap_open == 0 pairs ----
+            const uint32_t slots = std::min<uint32_t>(n_exact, (uint32_t)d.sm_count * 16);
+            const uint64_t vcap = (uint64_t)ctx->max_prof_len + 64;
+            const uint64_t fcap = (uint64_t)std::max<uint32_t>(ctx->staged_max_len, 1) * vcap;
+            CU(ctx, d.ex_hbuf.reserve((size_t)slots * 4 * vcap * sizeof(int32_t)));
+            CU(ctx, d.ex_fbuf.reserve((size_t)slots * fcap));
+            CU(ctx, d.ex_cig.reserve((size_t)n_exact * cig_cap * sizeof(uint32_t)));
+            ExactParams x{};
+            x.pair_ids = d.hazard_list.as<uint32_t>();
+            x.n_pairs = n_exact;
+            x.rseq = p.rseq;
+            x.roff = p.roff;
+            x.pbytes = d.pbytes.as<uint8_t>();
+            x.coff = p.coff;
+            x.n_cseq = n_prof;
+            x.weights = d.weights.as<int8_t>();
+            x.S = ctx->S;
+            x.lut = p.lut;
+            x.go = ctx->go;
+            x.ge = ctx->ge;
+            x.lanes8 = ctx->lanes[0];
+            x.lanes16 = ctx->lanes[1];
+            x.lanes32 = ctx->lanes[2];
+            x.invert = invert;
+            x.hbuf = d.ex_hbuf.as<int32_t>();
+            x.fbuf = d.ex_fbuf.as<uint8_t>();
+            x.vcap = vcap;
+            x.fcap = fcap;
+            x.score_in = t.score;
+            x.ref_start = t.ref_start;
+            x.ref_end = t.ref_end;
+            x.query_start = t.query_start;
+            x.query_end = t.query_end;
+            x.cig_scratch = d.ex_cig.as<uint32_t>();
+            x.cig_count = t.cig_count;
+            x.cig_cap = cig_cap;
+            x.counters = ctr;
+            sw_align_exact_kernel<<<(slots + 3) / 4, 128, 0, d.stream>>>(x);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+            ctx->stats.hazard += n_exact - hc[4];
+        }
+        // ---- CIGAR compaction, chained through the device-side running base ctr[9] ----
+        cigar_scan_kernel<<<1, 1024, 0, d.stream>>>(t.cig_count, (uint64_t)c0 * n_prof, cpairs, d.cig_off.as<uint64_t>(),
+                                                    ctr + 9);
+        CU(ctx, cudaGetLastError());
+        cigar_gather_kernel<<<cpairs, 32, 0, d.stream>>>(t.cig_scratch, cig_cap, nullptr, cpairs, (uint32_t)(c0 * n_prof),
+                                                         t.cig_count, d.cig_off.as<uint64_t>(), d.cig_out.as<uint32_t>(),
+                                                         cigar_cap_words, t.hazard);
+        CU(ctx, cudaGetLastError());
+        ctx->last_launches += 2;
+        if (n_exact > 0) {
+            cigar_gather_kernel<<<n_exact, 32, 0, d.stream>>>(d.ex_cig.as<uint32_t>(), cig_cap, d.hazard_list.as<uint32_t>(),
+                                                              n_exact, 0, t.cig_count, d.cig_off.as<uint64_t>(),
+                                                              d.cig_out.as<uint32_t>(), cigar_cap_words, nullptr);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+        }
+    }
+    // tier histogram + totals
+    CU(ctx, cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), d.stream));
+    count_status_kernel<<<(uint32_t)((pairs + 255) / 256), 256, 0, d.stream>>>(d.score.as<uint32_t>(), d.status.as<uint8_t>(),
+                                                                              pairs, ctr);
+    CU(ctx, cudaGetLastError());
+    ctx->last_launches++;
+    unsigned long long tail[3] = {0, 0, 0};  // ctr[7] score mismatch, [8] overflow, [9] cigar total
+    CU(ctx, cudaMemcpyAsync(tail, ctr + 7, sizeof(tail), cudaMemcpyDeviceToHost, d.stream));
+    unsigned long long cig_ovf = 0;
+    CU(ctx, cudaMemcpyAsync(&cig_ovf, ctr + 6, sizeof(cig_ovf), cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    d.cig_total = tail[2];
+    d.timed_kernel = false;  // several fill launches: report their sum instead of one event pair
+    ctx->last_dp_ms = std::max(ctx->last_dp_ms, dp_ms_total);
+    if (tail[0]) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: literal kernel disagreed with the fill score on %llu pairs", tail[0]);
+    if (cig_ovf) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: CIGAR scratch overflow on %llu pairs", cig_ovf);
+    return 0;
+}
+
 int sync_and_time(zoe_cuda_ctx *ctx) {
     float total = 0.f, dp = 0.f;
     for (Device &d : ctx->devs) {
@@ -482,7 +787,7 @@ int sync_and_time(zoe_cuda_ctx *ctx) {
         }
     }
     ctx->last_total_ms = total;
-    ctx->last_dp_ms = dp;
+    ctx->last_dp_ms = std::max(dp, ctx->last_dp_ms);
     return 0;
 }
 
@@ -496,7 +801,6 @@ int gather_stats(zoe_cuda_ctx *ctx) {
         ctx->stats.tier16 += c[1];
         ctx->stats.tier32 += c[2];
         ctx->stats.unmapped += c[3];
-        ctx->stats.hazard += c[5];
     }
     ctx->stats.pairs = ctx->staged_n * ctx->n_prof;
     ctx->stats.cells = ctx->staged_cells;
@@ -505,6 +809,7 @@ int gather_stats(zoe_cuda_ctx *ctx) {
 
 void begin_call(zoe_cuda_ctx *ctx) {
     ctx->last_launches = 0;
+    ctx->last_dp_ms = 0.f;
     ctx->stats = zoe_cuda_stats{};
     for (Device &d : ctx->devs) d.timed_kernel = false;
 }
@@ -548,7 +853,9 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
         for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
-                          &d.wide_ids, &d.counters})
+                          &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
+                          &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
+                          &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
@@ -668,7 +975,20 @@ int zoe_cuda_run_score_staged(zoe_cuda_ctx *ctx) {
 
 int zoe_cuda_run_align_staged(zoe_cuda_ctx *ctx) {
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
-    return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "align path not built yet");
+    if (!ctx->staged) return fail(ctx, ZOE_CUDA_E_STATE, "nothing staged");
+    begin_call(ctx);
+    for (Device &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+    }
+    // generous device-side CIGAR capacity: 8 words per pair (typical CIGARs have <= 5 entries)
+    for (Device &d : ctx->devs) {
+        int rc = run_align_on_device(ctx, d, (uint64_t)d.n_count * ctx->n_prof * 8 + 1024);
+        if (rc) return rc;
+    }
+    int rc = sync_and_time(ctx);
+    if (rc) return rc;
+    return gather_stats(ctx);
 }
 
 int zoe_cuda_fetch_scores(zoe_cuda_ctx *ctx, uint32_t *score, uint8_t *status, uint8_t *tier) {
@@ -715,11 +1035,59 @@ int zoe_cuda_sw_score_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
     return gather_stats(ctx);
 }
 
-int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *, const uint64_t *, uint64_t, uint32_t *, uint8_t *,
-                            uint8_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, uint64_t *, uint64_t,
-                            uint8_t *) {
+int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
+                            uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
+                            uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
+                            uint64_t cigar_cap, uint8_t *hazard) {
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
-    return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "align path not built yet");
+    if (!cigar_off || (!cigar && cigar_cap)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null CIGAR outputs");
+    begin_call(ctx);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    if (rc) return rc;
+    for (Device &d : ctx->devs) {
+        rc = run_align_on_device(ctx, d, cigar_cap);
+        if (rc) return rc;
+    }
+    // CIGAR offsets: device-local running sums -> global offsets (devices own contiguous index ranges)
+    uint64_t total = 0;
+    for (Device &d : ctx->devs) total += d.cig_total;
+    if (total > cigar_cap) {
+        cigar_off[0] = total;
+        sync_and_time(ctx);
+        return fail(ctx, ZOE_CUDA_E_CIGAR_CAP, "CIGAR buffer too small: need %llu words, have %llu",
+                    (unsigned long long)total, (unsigned long long)cigar_cap);
+    }
+    uint64_t base = 0;
+    for (Device &d : ctx->devs) {
+        if (d.n_count == 0) continue;
+        CU(ctx, cudaSetDevice(d.id));
+        size_t first = (size_t)d.n_first * ctx->n_prof, pairs = (size_t)d.n_count * ctx->n_prof;
+        auto d2h = [&](void *dst, const DevBuf &src, size_t elem) -> cudaError_t {
+            if (!dst) return cudaSuccess;
+            return cudaMemcpyAsync((uint8_t *)dst + first * elem, src.p, pairs * elem, cudaMemcpyDeviceToHost, d.stream);
+        };
+        CU(ctx, d2h(score, d.score, 4));
+        CU(ctx, d2h(status, d.status, 1));
+        CU(ctx, d2h(tier, d.tier, 1));
+        CU(ctx, d2h(ref_start, d.ref_start, 4));
+        CU(ctx, d2h(ref_end, d.ref_end, 4));
+        CU(ctx, d2h(query_start, d.query_start, 4));
+        CU(ctx, d2h(query_end, d.query_end, 4));
+        CU(ctx, d2h(hazard, d.hazard, 1));
+        CU(ctx, cudaMemcpyAsync(cigar_off + first, d.cig_off.p, (pairs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                d.stream));
+        if (d.cig_total)
+            CU(ctx, cudaMemcpyAsync(cigar + base, d.cig_out.p, d.cig_total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                    d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        if (base)
+            for (size_t i = 0; i <= pairs; ++i) cigar_off[first + i] += base;
+        base += d.cig_total;
+    }
+    if (n == 0) cigar_off[0] = 0;
+    rc = sync_and_time(ctx);
+    if (rc) return rc;
+    return gather_stats(ctx);
 }
 
 int zoe_cuda_last_timing(const zoe_cuda_ctx *ctx, float *total_ms, float *dp_kernel_ms, uint32_t *kernel_launches) {
