@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -632,6 +633,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
 
         // ---- traceback ----
         CU(ctx, cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(unsigned long long), d.stream));  // [4] wide seqs, [5] exact list
+        CU(ctx, cudaMemsetAsync(ctr + 8, 0, sizeof(unsigned long long), d.stream));      // [8] packed overflows (per chunk)
         TraceParams t{};
         t.ends = ap.ends;
         t.flags = ap.flags;
@@ -677,7 +679,10 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             dp_ms_total += ms;
         }
         const uint32_t n_exact = (uint32_t)hc[1];
-        if (hc[4] > 0) {
+        if (getenv("ZOE_CUDA_DEBUG"))
+            fprintf(stderr, "[zoe_cuda] chunk %llu: wide_seqs %llu exact %llu cig_ovf %llu mismatch %llu overflow %llu\n",
+                    (unsigned long long)c0, hc[0], hc[1], hc[2], hc[3], hc[4]);
+        if (hc[4] > 0 && n_exact > 0) {
             // packed overflow: exact scores from the 32-bit score kernel (or_else_overflowed, output.rs:81-83)
             collect_wide_range_kernel<<<(cn + 255) / 256, 256, 0, d.stream>>>(d.best.as<int32_t>(), (uint32_t)c0, cn, n_prof,
                                                                               d.wide_ids.as<uint32_t>(), ctr);
