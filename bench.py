@@ -280,6 +280,37 @@ def main():
                "d2h_bytes_per_step": int(h_score.nbytes + h_status.nbytes + h_tier.nbytes),
                "ms_per_step": e2e_ms / args.steps, "result_checksum": int(h_score.sum(dtype=np.uint64))}
 
+    if mode == "align":
+        cap = n * n_prof * 8 + 1024
+        t_out = {k: torch.empty(n * n_prof, dtype=torch.int32).pin_memory() for k in
+                 ("score", "ref_start", "ref_end", "query_start", "query_end")}
+        t_b = {k: torch.empty(n * n_prof, dtype=torch.uint8).pin_memory() for k in ("status", "tier", "hazard")}
+        t_off = torch.empty(n * n_prof + 1, dtype=torch.int64).pin_memory()
+        t_cig = torch.empty(cap, dtype=torch.int32).pin_memory()
+        outs = {k: v.numpy().view(np.uint32) for k, v in t_out.items()}
+        outs.update({k: v.numpy() for k, v in t_b.items()})
+        outs["cigar_off"] = t_off.numpy().view(np.uint64)
+        outs["cigar"] = t_cig.numpy().view(np.uint32)
+        for _ in range(min(args.warmup, 2)):
+            prof.align_into(h_buf, h_offs, outs)
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev2.record(stream)
+        for _ in range(args.steps):
+            prof.align_into(h_buf, h_offs, outs)
+            launches += prof.last_timing()["kernel_launches"]
+        ev3.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), wall_ms))
+        n_words = int(outs["cigar_off"][n * n_prof])
+        e2e = {"value": total_cells * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_buf.nbytes + h_offs.nbytes),
+               "d2h_bytes_per_step": int(n * n_prof * (5 * 4 + 3 + 8) + 8 + n_words * 4),
+               "ms_per_step": e2e_ms / args.steps,
+               "result_checksum": int(outs["score"].sum(dtype=np.uint64)) ^ int(outs["cigar"][:n_words].sum(dtype=np.uint64))}
+
     # ---------------- roofline of the dominant kernel ----------------
     dpx_g, _ = prof.dpx_peak(0)  # G lane-instr/s, measured live on this GPU
     peak_gcups = dpx_g / DPX_INSTR_PER_CELL
@@ -291,12 +322,16 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     in_bytes = float(h_buf.nbytes + h_offs.nbytes + n * n_prof * 4)
+    if mode == "align":  # one flag byte-ish per cell: 32 B per lane per column for 3x19 rows x 2 sequences
+        in_bytes += float(prof.align_flag_bytes(n, 150))
     roofline = {
         "bound": "alu", "achieved": kernel_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
         "traffic": None,
         "note": ("integer max-plus (DPX on the ALU pipe) bound, not hbm/tensor: peak = live-measured "
-                 "VIADDMNMX.S16x2 issue rate (%.0f G lane-instr/s) / %.2f instr per cell; kernel = sw_score_kernel, "
-                 "avg of %d launches, CUDA events on the library stream" % (dpx_g, DPX_INSTR_PER_CELL, len(dp_ms))),
+                 "VIADDMNMX.S16x2 issue rate (%.0f G lane-instr/s) / %.2f instr per cell (the score recurrence; the "
+                 "align fill kernel needs 4.75 more ALU instr per cell for its 5 direction bits); kernel = %s, "
+                 "avg of %d steps, CUDA events on the library stream"
+                 % (dpx_g, DPX_INSTR_PER_CELL, "sw_score_kernel" if mode == "score" else "sw_align_fill_kernel", len(dp_ms))),
         "hbm": {"algorithmic_bytes_per_launch": in_bytes, "achieved_gbs": in_bytes / (float(np.mean(dp_ms)) * 1e-3) / 1e9,
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "frac": in_bytes / (float(np.mean(dp_ms)) * 1e-3) / 1e9 / hbm_peak},
@@ -321,6 +356,31 @@ def main():
         mism = int((g_status != c_status).sum() + (g_score[some] != c_score[some]).sum()
                    + (g_tier[some] != c_tier[some]).sum())
         parity = {"checked_pairs": int(n_sample * n_prof), "mismatches": mism, "against": "cpu port (oracle/zoe_sw_cpu.cpp)"}
+
+    if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "align":
+        from oracle import oracle as O
+        sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
+        n_sample = min(n, 600)
+        t0 = time.perf_counter()
+        mism = 0
+        for i in range(n_sample):
+            s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
+            for j, tg in enumerate(targets):
+                rc, want, _ = O.sw_align_from(bytes(tg), s_i, sc, streamed_is_query=True)
+                k = i * n_prof + j
+                ok = int(outs["status"][k]) == rc
+                if ok and rc == 0:
+                    lo, hi = int(outs["cigar_off"][k]), int(outs["cigar_off"][k + 1])
+                    cig = "".join(f"{int(w) >> 4}{'MID?S'[int(w) & 15]}" for w in outs["cigar"][lo:hi])
+                    ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
+                          int(outs["query_start"][k]), int(outs["query_end"][k]), cig) == \
+                         (want.score, want.ref_range[0], want.ref_range[1], want.query_range[0], want.query_range[1], want.cigar)
+                mism += 0 if ok else 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of sw_simd_align + escalation ({dt:.1f} s); "
+                         "not vectorised -- a checker, not a tuned baseline"}
+        parity = {"checked_pairs": n_sample * n_prof, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c (score, ranges, CIGAR)"}
 
     if rank == 0:
         n_gpus = world if distributed else in_process_devices

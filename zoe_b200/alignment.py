@@ -295,6 +295,21 @@ class CudaProfiles:
         out["cigar"] = cigar
         return out
 
+    def align_into(self, buf: np.ndarray, offs: np.ndarray, out: dict):
+        """Like :meth:`align_arrays` but into caller-owned (ideally pinned) arrays; ``out['cigar']`` is the capacity."""
+        n = len(offs) - 1
+        self._check(self._lib.zoe_cuda_sw_align_batch(
+            self._h, _p(buf, C.c_uint8), _p(offs, C.c_uint64), n, _p(out["score"], C.c_uint32),
+            _p(out["status"], C.c_uint8), _p(out["tier"], C.c_uint8), _p(out["ref_start"], C.c_uint32),
+            _p(out["ref_end"], C.c_uint32), _p(out["query_start"], C.c_uint32), _p(out["query_end"], C.c_uint32),
+            _p(out["cigar"], C.c_uint32), _p(out["cigar_off"], C.c_uint64), len(out["cigar"]), _p(out["hazard"], C.c_uint8)))
+
+    def align_flag_bytes(self, n_seqs: int, seq_len: int) -> int:
+        """Bytes of direction flags one align pass writes (8 lanes x 32 B per column per sequence pair for <= 152 rows)."""
+        cols = sum(len(t) for t in self.targets)
+        lanes_words = {True: 8 * 8}  # G=8, NW=8 (K=19) -- the short-read layout
+        return int((n_seqs + 1) // 2 * cols * lanes_words[True] * 4) if seq_len <= 152 else 0
+
     # ---- zoe-shaped API ----
     def sw_score_batch(self, seqs: Sequence[bytes]):
         """``[[MaybeAligned[int]]]``: ``out[i][j] == profiles[j].sw_score_from_i8(seqs[i])``."""

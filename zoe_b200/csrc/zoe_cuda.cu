@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,17 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // small utilities
 // ---------------------------------------------------------------------------------------------
+struct DebugTimer {  // host-side phase timing, printed when ZOE_CUDA_DEBUG is set
+    bool on = getenv("ZOE_CUDA_DEBUG") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[zoe_cuda] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -585,11 +597,14 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     CU(ctx, d.counters.reserve(16 * sizeof(unsigned long long)));
     CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
     unsigned long long *ctr = d.counters.as<unsigned long long>();
+    { DebugTimer t; if (t.on) fprintf(stderr, "[zoe_cuda] align: chunk_seqs %llu task_stride %llu words, cig_cap %u\n", (unsigned long long)chunk_seqs, (unsigned long long)task_stride, cig_cap); }
 
+    DebugTimer dbg;
     LaunchPlan plan;
     int rc = plan_launch(ctx, *k, k->fill, &plan);
     if (rc) return rc;
     CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    dbg.lap("align: plan");
     const bool all_exact = (ctx->go == 0);
     const int invert = ctx->profiled_is_query ? 0 : 1;
     float dp_ms_total = 0.f;
@@ -679,6 +694,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             dp_ms_total += ms;
         }
         const uint32_t n_exact = (uint32_t)hc[1];
+        dbg.lap("align: fill+traceback");
         if (getenv("ZOE_CUDA_DEBUG"))
             fprintf(stderr, "[zoe_cuda] chunk %llu: wide_seqs %llu exact %llu cig_ovf %llu mismatch %llu overflow %llu\n",
                     (unsigned long long)c0, hc[0], hc[1], hc[2], hc[3], hc[4]);
@@ -769,6 +785,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     unsigned long long cig_ovf = 0;
     CU(ctx, cudaMemcpyAsync(&cig_ovf, ctr + 6, sizeof(cig_ovf), cudaMemcpyDeviceToHost, d.stream));
     CU(ctx, cudaStreamSynchronize(d.stream));
+    dbg.lap("align: compaction+tail");
     d.cig_total = tail[2];
     d.timed_kernel = false;  // several fill launches: report their sum instead of one event pair
     ctx->last_dp_ms = std::max(ctx->last_dp_ms, dp_ms_total);
@@ -1047,12 +1064,15 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     if (!cigar_off || (!cigar && cigar_cap)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null CIGAR outputs");
     begin_call(ctx);
+    DebugTimer dbg;
     int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
     if (rc) return rc;
+    dbg.lap("align: stage");
     for (Device &d : ctx->devs) {
         rc = run_align_on_device(ctx, d, cigar_cap);
         if (rc) return rc;
     }
+    dbg.lap("align: run_align_on_device");
     // CIGAR offsets: device-local running sums -> global offsets (devices own contiguous index ranges)
     uint64_t total = 0;
     for (Device &d : ctx->devs) total += d.cig_total;
@@ -1090,6 +1110,7 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
         base += d.cig_total;
     }
     if (n == 0) cigar_off[0] = 0;
+    dbg.lap("align: d2h");
     rc = sync_and_time(ctx);
     if (rc) return rc;
     return gather_stats(ctx);
