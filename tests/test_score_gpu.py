@@ -129,3 +129,36 @@ def test_various_scorings_random():
                 s[5:35] = target[st:st + 30]
             seqs.append(s)
         check([target], seqs, wm, go, ge)
+
+
+def test_long_rows_golden_self_score(seqs):
+    # sw/test.rs:272-280, 303-311: CY137594 (1686 nt) vs itself = 3372, i8 -> i16 escalation; 1686 rows take the
+    # chunked long-row kernel
+    cy = seqs["CY137594"]
+    prof = CudaProfiles.new_with_w128([cy, seqs["H5_HA"]], W25, -10, -1)
+    buf, offs = synth.pack([np.frombuffer(cy, dtype=np.uint8), np.frombuffer(seqs["H1_HA"], dtype=np.uint8)])
+    score, status, tier = prof.sw_score_arrays(buf, offs)
+    assert int(score[0, 0]) == 3372 and int(tier[0, 0]) == 16
+    assert int(score[1, 1]) == 37 and int(tier[1, 1]) == 8
+    prof.close()
+
+
+def test_long_rows_vs_cpu_port_and_oracle():
+    from oracle import cpu_baseline as CB
+    targets, reads = synth.config4(n_reads=24, min_len=900, max_len=4200)
+    genome = targets[0][:9000]
+    reads = reads + [reads[0][:1024], reads[1][:1025], reads[2][:767], reads[3][:769], reads[4][:1]]
+    prof = CudaProfiles.new_with_w256([bytes(genome), bytes(genome[:700])], W25, -10, -1)
+    buf, offs = synth.pack(reads)
+    score, status, tier = prof.sw_score_arrays(buf, offs)
+    pbuf, poff = synth.pack([genome, genome[:700]])
+    c_score, c_status, c_tier = CB.score_batch(pbuf, poff, buf, offs, W25.weights, W25.mapping.index_map, -10, -1)
+    assert np.array_equal(status, c_status)
+    assert np.array_equal(score[c_status == 0], c_score[c_status == 0])
+    assert np.array_equal(tier[c_status == 0], c_tier[c_status == 0])
+    assert (tier == 16).any()
+    sc = osc(W25)
+    for i in (0, 5, len(reads) - 2):  # spot-check the plain-C oracle as well
+        rc, s_, t_ = O.sw_score_from(bytes(genome), bytes(reads[i]), sc)
+        assert (int(status[i, 0]), int(score[i, 0]), int(tier[i, 0])) == (rc, s_, t_)
+    prof.close()

@@ -18,6 +18,7 @@
 
 #include "sw_align.cuh"
 #include "sw_score.cuh"
+#include "sw_score_long.cuh"
 
 using namespace zoe_cuda;
 
@@ -74,6 +75,8 @@ struct Device {
     DevBuf pbytes, ends, flags, flag_base, ref_start, ref_end, query_start, query_end, hazard, hazard_list;
     DevBuf cig_scratch, cig_count, cig_off, cig_out, ex_hbuf, ex_fbuf, ex_cig, weights;
     uint64_t cig_total = 0;
+    // long-row score path
+    DevBuf long_ids, long_bnd, long_queue;
     uint64_t n_first = 0, n_count = 0;  // shard of the streamed batch owned by this device
     uint64_t rseq_bytes = 0;
     bool timed_kernel = false;
@@ -128,6 +131,7 @@ struct zoe_cuda_ctx {
     uint32_t staged_max_len = 0;
     uint64_t staged_cells = 0;
     bool staged = false;
+    std::vector<uint32_t> staged_len;  // per streamed sequence (only kept when the long-row path is needed)
     uint64_t flag_budget_bytes = 0;  // 0 = auto (a fraction of free device memory)
     // measurements
     float last_total_ms = 0.f, last_dp_ms = 0.f;
@@ -370,6 +374,11 @@ int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *o
     uint64_t prof_total = ctx->prof_off[ctx->n_prof];
     ctx->staged_n = n;
     ctx->staged_max_len = max_len;
+    ctx->staged_len.clear();
+    if (max_len > (uint32_t)kMaxRowsSinglePass) {
+        ctx->staged_len.resize(n);
+        for (uint64_t i = 0; i < n; ++i) ctx->staged_len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+    }
     ctx->staged_cells = tot * prof_total;
     shard(ctx, n);
     for (Device &d : ctx->devs) {
@@ -438,17 +447,140 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// long-row score path (rows > kMaxRowsSinglePass): chunked sweeps with a boundary row per warp
+// ---------------------------------------------------------------------------------------------
+constexpr int kLongK = 24;  // rows per lane per chunk: 32 x 24 = 768 rows, 16 warps per SM at DNA alphabet size
+
+template <bool PACKED>
+int launch_score_long(zoe_cuda_ctx *ctx, Device &d, const uint32_t *d_ids, uint32_t n_ids) {
+    auto fn = sw_score_long_kernel<kLongK, PACKED>;
+    const size_t tab_per_warp = (size_t)ctx->n_csym * (kLongK / 4) * 32 * 16;
+    const size_t fixed = 256 + (((size_t)ctx->n_csym * ctx->S + 15) & ~(size_t)15);
+    int best_warps = 0, best_threads = 0, best_blocks = 0, best_cols = 0;
+    size_t best_smem = 0;
+    for (int cols_in_smem = 1; cols_in_smem >= 0 && best_warps == 0; --cols_in_smem) {
+        if (cols_in_smem && ctx->ccodes.size() > 96 * 1024) continue;
+        for (int threads : {512, 384, 256, 128, 64, 32}) {
+            size_t smem = tab_per_warp * (threads / 32) + fixed + (cols_in_smem ? ((ctx->ccodes.size() + 15) & ~(size_t)15) : 0);
+            if (smem > 227 * 1024) continue;
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            if (nb * threads / 32 > best_warps) {
+                best_warps = nb * threads / 32;
+                best_threads = threads;
+                best_blocks = nb;
+                best_smem = smem;
+                best_cols = cols_in_smem;
+            }
+        }
+    }
+    if (!best_warps) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "long-row kernel does not fit shared memory (alphabet %d)", ctx->n_csym);
+    LongParams lp{};
+    ScoreParams &p = lp.s;
+    p.rseq = d.rseq.as<uint8_t>();
+    p.roff = d.roff.as<uint64_t>();
+    p.task_ids = d_ids;
+    p.n_rseq = n_ids;
+    p.n_tasks = PACKED ? (n_ids + 1) / 2 : n_ids;
+    p.ccodes = d.ccodes.as<uint8_t>();
+    p.coff = d.coff.as<uint32_t>();
+    p.n_cseq = ctx->n_prof;
+    p.ccodes_bytes = (uint32_t)ctx->ccodes.size();
+    p.cols_in_smem = best_cols;
+    p.wk = d.wk.as<int8_t>();
+    p.n_csym = ctx->n_csym;
+    p.S = ctx->S;
+    p.lut = d.lut.as<uint8_t>();
+    p.go = ctx->go;
+    p.ge = ctx->ge;
+    p.ovf_thresh = 32767 - std::max(ctx->max_weight, 0) - 1;
+    p.best = d.best.as<int32_t>();
+    if (p.n_tasks == 0) return 0;
+    const uint32_t warps_per_block = best_threads / 32;
+    uint32_t blocks = std::min<uint32_t>((uint32_t)(d.sm_count * best_blocks), (p.n_tasks + warps_per_block - 1) / warps_per_block);
+    CU(ctx, d.long_bnd.reserve((size_t)blocks * warps_per_block * ctx->max_prof_len * sizeof(uint2)));
+    CU(ctx, d.long_queue.reserve(sizeof(unsigned int)));
+    CU(ctx, cudaMemsetAsync(d.long_queue.p, 0, sizeof(unsigned int), d.stream));
+    lp.boundary = d.long_bnd.as<uint2>();
+    lp.max_L = ctx->max_prof_len;
+    lp.queue = d.long_queue.as<unsigned int>();
+    CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem));
+    fn<<<blocks, best_threads, best_smem, d.stream>>>(lp);
+    CU(ctx, cudaGetLastError());
+    ctx->last_launches++;
+    return 0;
+}
+
+int run_score_long_on_device(zoe_cuda_ctx *ctx, Device &d) {
+    // longest-first order, so that (a) the two halves of a packed task have similar lengths and (b) the
+    // atomic queue hands out the big tasks first
+    std::vector<uint32_t> order(d.n_count);
+    for (uint64_t i = 0; i < d.n_count; ++i) order[i] = (uint32_t)i;
+    const uint32_t *len = ctx->staged_len.data() + d.n_first;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len[a] > len[b]; });
+    CU(ctx, d.long_ids.reserve(order.size() * sizeof(uint32_t)));
+    CU(ctx, cudaMemcpyAsync(d.long_ids.p, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    uint64_t bound = (uint64_t)std::min<uint32_t>(ctx->staged_max_len, ctx->max_prof_len) * (uint64_t)std::max(ctx->max_weight, 0);
+    const bool packed_ok = bound < 60000;
+    CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+    int rc;
+    if (packed_ok) {
+        rc = launch_score_long<true>(ctx, d, d.long_ids.as<uint32_t>(), (uint32_t)d.n_count);
+        if (rc) return rc;
+        if (bound >= (uint64_t)(32767 - ctx->max_weight - 1)) {
+            uint32_t threads = 256, blocks = (uint32_t)((d.n_count + threads - 1) / threads);
+            collect_wide_kernel<<<blocks, threads, 0, d.stream>>>(d.best.as<int32_t>(), (uint32_t)d.n_count, ctx->n_prof,
+                                                                  d.wide_ids.as<uint32_t>(), d.counters.as<unsigned long long>());
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+            unsigned long long n_wide = 0;
+            CU(ctx, cudaMemcpyAsync(&n_wide, d.counters.as<unsigned long long>() + 4, sizeof(n_wide), cudaMemcpyDeviceToHost, d.stream));
+            CU(ctx, cudaStreamSynchronize(d.stream));
+            if (n_wide) {
+                rc = launch_score_long<false>(ctx, d, d.wide_ids.as<uint32_t>(), (uint32_t)n_wide);
+                if (rc) return rc;
+                ctx->stats.rerun_wide += n_wide * ctx->n_prof;
+            }
+        }
+    } else {
+        rc = launch_score_long<false>(ctx, d, d.long_ids.as<uint32_t>(), (uint32_t)d.n_count);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+    d.timed_kernel = true;
+    return 0;
+}
+
 // The score pipeline on one device, all asynchronous on d.stream.
 int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
     if (d.n_count == 0) return 0;
     CU(ctx, cudaSetDevice(d.id));
-    if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass)
-        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "streamed sequences longer than %d are not supported yet",
-                    kMaxRowsSinglePass);
-    const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
-    if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
     size_t pairs = (size_t)d.n_count * ctx->n_prof;
     CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
+    if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass) {
+        int rc = run_score_long_on_device(ctx, d);
+        if (rc) return rc;
+        uint32_t threads = 256;
+        uint32_t blocks = (uint32_t)((pairs + threads - 1) / threads);
+        finalize_scores_kernel<<<blocks, threads, 0, d.stream>>>(d.best.as<int32_t>(), pairs, d.score.as<uint32_t>(),
+                                                                 d.status.as<uint8_t>(), d.tier.as<uint8_t>(),
+                                                                 d.counters.as<unsigned long long>());
+        CU(ctx, cudaGetLastError());
+        ctx->last_launches++;
+        return 0;
+    }
+    const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
+    if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
     // Static bound: can any packed 16-bit lane reach the overflow threshold?
     uint64_t bound = (uint64_t)std::min<uint32_t>(ctx->staged_max_len, ctx->max_prof_len) *
                      (uint64_t)std::max(ctx->max_weight, 0);
@@ -877,7 +1009,8 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
         for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
-                          &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights})
+                          &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.long_ids, &d.long_bnd,
+                          &d.long_queue})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
