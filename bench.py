@@ -61,6 +61,11 @@ def make_workload(config: int, n_override: int | None, rank: int):
         t, r = synth.config3(ROOT, n_reads=n, seed=4 + 1000 * rank)
         return (f"cfg3: {n} x 150nt reads vs 1704nt HA, align with traceback", dna, -10, -1, t,
                 synth.fixed_len_batch(r), "align")
+    if config == 4:
+        n = n_override or 100_000
+        t, r = synth.config4(n_reads=n, seed_reads=6 + 1000 * rank)
+        return (f"cfg4: {n} x 1-5kb ONT-like reads vs 29903nt genome, score-only (long-row path)", dna, -10, -1, t,
+                synth.pack(r), "score")
     if config == 5:
         n = n_override or 1_000_000
         t, q = synth.config5(n_queries=n, seed_queries=8 + 1000 * rank)

@@ -31,23 +31,27 @@ def pack(seqs):
 
 
 def _mutate(rng, frag, sub, ins, dele, alphabet):
-    """Apply substitutions / insertions / deletions (geometric indel length, p = 0.5)."""
-    out = []
-    i = 0
+    """Apply substitutions / insertions / deletions (geometric insertion length, p = 0.5); vectorised."""
     n = len(frag)
+    if n == 0:
+        return np.zeros(0, dtype=np.uint8)
     r = rng.random(n)
-    for i in range(n):
-        x = r[i]
-        if x < dele:
-            continue
-        if x < dele + ins:
-            k = int(rng.geometric(0.5))
-            out.extend(alphabet[rng.integers(0, len(alphabet), k)].tolist())
-        if x < dele + ins + sub:
-            out.append(int(alphabet[rng.integers(0, len(alphabet))]))
-        else:
-            out.append(int(frag[i]))
-    return np.array(out, dtype=np.uint8)
+    deleted = r < dele
+    inserted = (~deleted) & (r < dele + ins)
+    substituted = (~deleted) & (r < dele + ins + sub)
+    ins_len = np.where(inserted, rng.geometric(0.5, n), 0)
+    out_len = ins_len + (~deleted)
+    total = int(out_len.sum())
+    if total == 0:
+        return np.zeros(0, dtype=np.uint8)
+    idx = np.repeat(np.arange(n), out_len)
+    first = np.cumsum(out_len) - out_len
+    within = np.arange(total) - np.repeat(first, out_len)
+    is_ins = within < np.repeat(ins_len, out_len)
+    out = np.asarray(frag, dtype=np.uint8)[idx]
+    rnd = is_ins | substituted[idx]
+    out[rnd] = alphabet[rng.integers(0, len(alphabet), int(rnd.sum()))]
+    return out
 
 
 def illumina_reads(rng: np.random.Generator, targets, n_reads: int, read_len: int = 150, sub: float = 0.01,
