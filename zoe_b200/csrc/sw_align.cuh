@@ -477,6 +477,7 @@ struct ExactParams {
     int32_t *hbuf;              // [slots][4][vcap]   load, store, e, max_row
     uint8_t *fbuf;              // [slots][fcap]      flag bytes n * nv * N
     uint64_t vcap, fcap;
+    int rows_in_smem;
     // outputs (same arrays as TraceParams)
     const uint32_t *score_in;   // exact score from the fill pass (decides the tier)
     uint32_t *ref_start, *ref_end, *query_start, *query_end;
@@ -507,8 +508,12 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
         const int nv = (m + N - 1) / N;
         // lane t owns SIMD lanes t and t+32 (N <= 64)
         const int NL = (N + 31) / 32;
-        int32_t *load = x.hbuf + (size_t)slot * 4 * x.vcap, *store = load + x.vcap, *es = store + x.vcap,
-                *max_row = es + x.vcap;
+        // H / E rows: shared memory when the profiled sequence is short enough (latency 30 vs ~600 cycles),
+        // else the per-slot global scratch
+        extern __shared__ __align__(16) int32_t ex_smem[];
+        int32_t *load = x.rows_in_smem ? ex_smem + (size_t)(threadIdx.x / 32) * 4 * x.vcap
+                                       : x.hbuf + (size_t)slot * 4 * x.vcap;
+        int32_t *store = load + x.vcap, *es = store + x.vcap, *max_row = es + x.vcap;
         uint8_t *bt = x.fbuf + (size_t)slot * x.fcap;
         for (int i = lane; i < nv * N; i += 32) {
             load[i] = 0;

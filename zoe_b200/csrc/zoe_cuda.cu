@@ -848,7 +848,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         }
         if (n_exact > 0) {
             // ---- literal striped emulation for hazard / overflow / gap_open == 0 pairs ----
-            const uint32_t slots = std::min<uint32_t>(n_exact, (uint32_t)d.sm_count * 16);
+            const uint32_t slots = (std::min<uint32_t>(n_exact, (uint32_t)d.sm_count * 16) + 3u) & ~3u;  // whole blocks
             const uint64_t vcap = (uint64_t)ctx->max_prof_len + 64;
             const uint64_t fcap = (uint64_t)std::max<uint32_t>(ctx->staged_max_len, 1) * vcap;
             CU(ctx, d.ex_hbuf.reserve((size_t)slots * 4 * vcap * sizeof(int32_t)));
@@ -884,7 +884,13 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             x.cig_count = t.cig_count;
             x.cig_cap = cig_cap;
             x.counters = ctr;
-            sw_align_exact_kernel<<<(slots + 3) / 4, 128, 0, d.stream>>>(x);
+            // four warps per block when their H/E rows fit in shared memory, else global scratch
+            const size_t rows_bytes = (size_t)4 * vcap * sizeof(int32_t);
+            x.rows_in_smem = rows_bytes * 4 <= 200 * 1024 ? 1 : 0;
+            const size_t ex_smem = x.rows_in_smem ? rows_bytes * 4 : 0;
+            if (ex_smem > 48 * 1024)
+                CU(ctx, cudaFuncSetAttribute(sw_align_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+            sw_align_exact_kernel<<<slots / 4, 128, ex_smem, d.stream>>>(x);
             CU(ctx, cudaGetLastError());
             ctx->last_launches++;
             ctx->stats.hazard += n_exact - hc[4];
