@@ -48,6 +48,7 @@ struct ScoreParams {
     uint32_t n_rseq;
     const uint8_t *ccodes;     // column sequences as dense symbol codes (device)
     const uint32_t *coff;      // n_cseq + 1 offsets into ccodes
+    const uint32_t *corder;    // optional visiting order of the column sequences (longest first)
     uint32_t n_cseq;
     uint32_t ccodes_bytes;     // total bytes of ccodes (staged in smem when it fits)
     int cols_in_smem;
@@ -94,7 +95,28 @@ struct Ops<false> {
 // Shared-memory footprint helpers (host + device).
 __host__ __device__ inline int score_tab_bytes(int n_csym, int G, int K) { return n_csym * ((K + 3) / 4) * G * 16; }
 
-template <int G, int K, bool PACKED>
+// One column step of one systolic stream: K rows, fully unrolled.  `tp` points at this lane's uint4 of the
+// column symbol's table row; (diag, E) enter from the lane above.
+#define ZOE_SCORE_ROW(ST, W)                                     \
+    {                                                            \
+        uint32_t x = O::max3(ST##E, ST##F[i], go_s) - go_s;      \
+        uint32_t H = O::addmax(ST##diag, W, x);                  \
+        ST##diag = ST##H[i];                                     \
+        ST##E = O::addmax(ST##E, neg_ge, H);                     \
+        ST##F[i] = O::addmax(ST##F[i], neg_ge, H);               \
+        ST##H[i] = H;                                            \
+        if (i & 1)                                               \
+            ST##best = O::max3(ST##best, H, ST##hp);             \
+        else                                                     \
+            ST##hp = H;                                          \
+    }
+
+// NS = number of column sequences swept concurrently by one group (1 or 2).  With NS = 2 every thread
+// carries two independent H/E/F recurrences that share the task's score table, which doubles the
+// instruction-level parallelism available to hide the 4-deep dependent chain per row (the ALU pipe, not the
+// issue slots or the latency, then bounds the kernel).  Column sequences are visited in `corder`
+// (longest first) so the two streams of a pair have similar lengths.
+template <int G, int K, bool PACKED, int NS>
 __global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
     using O = Ops<PACKED>;
     constexpr int K4 = (K + 3) / 4;
@@ -121,6 +143,7 @@ __global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
     const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
 
     const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+    const uint4 *tab_lane = tab + lig;
 
     // Static round-robin task assignment: every group of a warp makes the same number of trips,
     // so the warp never diverges on the task loop (invalid trips run on empty sequences).
@@ -161,104 +184,162 @@ __global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
 
         // ---- build this task's score table: lane l fills its own K rows for every column symbol ----
         __syncwarp();
-        {
-            int sym_lo[K], sym_hi[K];
+        for (int i4 = 0; i4 < K4; ++i4) {
+            int sym_lo[4], sym_hi[4];
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-                int r = lig * K + i;
-                sym_lo[i] = (r < len_lo) ? (int)s_lut[p.rseq[off_lo + r]] : -1;
-                sym_hi[i] = (PACKED && r < len_hi) ? (int)s_lut[p.rseq[off_hi + r]] : -1;
+            for (int q = 0; q < 4; ++q) {
+                const int i = i4 * 4 + q, r = lig * K + i;
+                sym_lo[q] = (i < K && r < len_lo) ? (int)s_lut[p.rseq[off_lo + r]] : -1;
+                sym_hi[q] = (PACKED && i < K && r < len_hi) ? (int)s_lut[p.rseq[off_hi + r]] : -1;
             }
             for (int s = 0; s < p.n_csym; ++s) {
                 const int8_t *wrow = s_wk + s * p.S;
+                uint32_t w[4];
 #pragma unroll
-                for (int i4 = 0; i4 < K4; ++i4) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        int i = i4 * 4 + q;
-                        int wl = kPadWeight, wh = kPadWeight;
-                        if (i < K) {
-                            if (sym_lo[i] >= 0) wl = wrow[sym_lo[i]];
-                            if (sym_hi[i] >= 0) wh = wrow[sym_hi[i]];
-                        }
-                        w[q] = PACKED ? ((uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16)) : (uint32_t)wl;
-                    }
-                    tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int q = 0; q < 4; ++q) {
+                    const int wl = sym_lo[q] >= 0 ? (int)wrow[sym_lo[q]] : kPadWeight;
+                    const int wh = sym_hi[q] >= 0 ? (int)wrow[sym_hi[q]] : kPadWeight;
+                    w[q] = PACKED ? ((uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16)) : (uint32_t)wl;
                 }
+                tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
         __syncwarp();
 
-        // ---- sweep every column sequence ----
-        for (uint32_t cj = 0; cj < p.n_cseq; ++cj) {
-            const uint32_t c0 = p.coff[cj];
-            const int L = (int)(p.coff[cj + 1] - c0);
-            const uint8_t *cs = cc + c0;
+        // ---- sweep the column sequences, NS at a time ----
+        for (uint32_t ci = 0; ci < p.n_cseq; ci += NS) {
+            const uint32_t cjA = p.corder ? p.corder[ci] : ci;
+            const uint32_t cA0 = p.coff[cjA];
+            const int LA = (int)(p.coff[cjA + 1] - cA0);
+            const uint8_t *csA = cc + cA0;
+            uint32_t cjB = 0;
+            int LB = 0;
+            const uint8_t *csB = cc;
+            if (NS == 2 && ci + 1 < p.n_cseq) {
+                cjB = p.corder ? p.corder[ci + 1] : ci + 1;
+                const uint32_t cB0 = p.coff[cjB];
+                LB = (int)(p.coff[cjB + 1] - cB0);
+                csB = cc + cB0;
+            }
 
-            uint32_t Hrow[K], Frow[K];
+            uint32_t aH[K], aF[K], bH[NS == 2 ? K : 1], bF[NS == 2 ? K : 1];
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-                Hrow[i] = 0;
-                Frow[i] = 0;
+                aH[i] = 0;
+                aF[i] = 0;
+                if (NS == 2) {
+                    bH[i] = 0;
+                    bF[i] = 0;
+                }
             }
-            uint32_t best = 0, h_last = 0, e_out = 0, h_up_prev = 0;
-            const int nsteps = L + G - 1;
+            uint32_t abest = 0, ah_last = 0, ae_out = 0, ah_up_prev = 0;
+            uint32_t bbest = 0, bh_last = 0, be_out = 0, bh_up_prev = 0;
+            const int nsteps = max(LA, LB) + G - 1;
 
             for (int step = 0; step < nsteps; ++step) {
-                uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G);
-                uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G);
+                uint32_t ah_in = __shfl_up_sync(FULL, ah_last, 1, G);
+                uint32_t ae_in = __shfl_up_sync(FULL, ae_out, 1, G);
+                uint32_t bh_in = 0, be_in = 0;
+                if (NS == 2) {
+                    bh_in = __shfl_up_sync(FULL, bh_last, 1, G);
+                    be_in = __shfl_up_sync(FULL, be_out, 1, G);
+                }
                 if (lig == 0) {
-                    h_in = 0;
-                    e_in = 0;
+                    ah_in = 0;
+                    ae_in = 0;
+                    bh_in = 0;
+                    be_in = 0;
                 }
                 const int j = step - lig;
-                if (j >= 0 && j < L) {
-                    const int s = cs[j];
-                    const uint4 *tp = tab + (size_t)s * (K4 * G) + lig;
-                    uint32_t diag = h_up_prev;
-                    uint32_t E = e_in;
-                    uint32_t hprev = 0;
+                const bool actA = j >= 0 && j < LA;
+                const bool actB = NS == 2 && j >= 0 && j < LB;
+                if (actA && actB) {
+                    const uint4 *tpA = tab_lane + (size_t)csA[j] * (K4 * G);
+                    const uint4 *tpB = tab_lane + (size_t)csB[j] * (K4 * G);
+                    uint32_t adiag = ah_up_prev, aE = ae_in, ahp = 0;
+                    uint32_t bdiag = bh_up_prev, bE = be_in, bhp = 0;
 #pragma unroll
                     for (int i4 = 0; i4 < K4; ++i4) {
-                        const uint4 w4 = tp[i4 * G];
-                        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+                        const uint4 wa4 = tpA[i4 * G], wb4 = tpB[i4 * G];
+                        const uint32_t wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w};
+                        const uint32_t wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int i = i4 * 4 + q;
                             if (i < K) {
-                                uint32_t x = O::max3(E, Frow[i], go_s) - go_s;
-                                uint32_t H = O::addmax(diag, w[q], x);
-                                diag = Hrow[i];
-                                E = O::addmax(E, neg_ge, H);
-                                Frow[i] = O::addmax(Frow[i], neg_ge, H);
-                                Hrow[i] = H;
-                                if (i & 1)
-                                    best = O::max3(best, H, hprev);
-                                else
-                                    hprev = H;
+                                ZOE_SCORE_ROW(a, wa[q])
+                                if (NS == 2) ZOE_SCORE_ROW(b, wb[q])
                             }
                         }
                     }
-                    if (K & 1) best = O::max2(best, hprev);
-                    h_last = Hrow[K - 1];
-                    e_out = E;
+                    if (K & 1) {
+                        abest = O::max2(abest, ahp);
+                        bbest = O::max2(bbest, bhp);
+                    }
+                    ah_last = aH[K - 1];
+                    ae_out = aE;
+                    if (NS == 2) {
+                        bh_last = bH[K - 1];
+                        be_out = bE;
+                    }
+                } else if (actA) {
+                    const uint4 *tpA = tab_lane + (size_t)csA[j] * (K4 * G);
+                    uint32_t adiag = ah_up_prev, aE = ae_in, ahp = 0;
+#pragma unroll
+                    for (int i4 = 0; i4 < K4; ++i4) {
+                        const uint4 wa4 = tpA[i4 * G];
+                        const uint32_t wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = i4 * 4 + q;
+                            if (i < K) ZOE_SCORE_ROW(a, wa[q])
+                        }
+                    }
+                    if (K & 1) abest = O::max2(abest, ahp);
+                    ah_last = aH[K - 1];
+                    ae_out = aE;
+                } else if (actB) {
+                    const uint4 *tpB = tab_lane + (size_t)csB[j] * (K4 * G);
+                    uint32_t bdiag = bh_up_prev, bE = be_in, bhp = 0;
+#pragma unroll
+                    for (int i4 = 0; i4 < K4; ++i4) {
+                        const uint4 wb4 = tpB[i4 * G];
+                        const uint32_t wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = i4 * 4 + q;
+                            if (i < K) ZOE_SCORE_ROW(b, wb[q])
+                        }
+                    }
+                    if (K & 1) bbest = O::max2(bbest, bhp);
+                    bh_last = bH[K - 1];
+                    be_out = bE;
                 }
-                h_up_prev = h_in;
+                ah_up_prev = ah_in;
+                bh_up_prev = bh_in;
             }
 
             // ---- reduce the group's best and write the exact scores ----
 #pragma unroll
-            for (int d = G / 2; d >= 1; d >>= 1) best = O::max2(best, __shfl_xor_sync(FULL, best, d, G));
+            for (int d = G / 2; d >= 1; d >>= 1) {
+                abest = O::max2(abest, __shfl_xor_sync(FULL, abest, d, G));
+                if (NS == 2) bbest = O::max2(bbest, __shfl_xor_sync(FULL, bbest, d, G));
+            }
             if (lig == 0 && valid) {
-                if (PACKED) {
-                    int b_lo = (int)(int16_t)(best & 0xffff), b_hi = (int)(int16_t)(best >> 16);
-                    if (id_lo != 0xffffffffu)
-                        p.best[(size_t)id_lo * p.n_cseq + cj] = (b_lo >= p.ovf_thresh) ? -1 : b_lo;
-                    if (id_hi != 0xffffffffu)
-                        p.best[(size_t)id_hi * p.n_cseq + cj] = (b_hi >= p.ovf_thresh) ? -1 : b_hi;
-                } else {
-                    p.best[(size_t)id_lo * p.n_cseq + cj] = (int)best;
+#pragma unroll
+                for (int st = 0; st < NS; ++st) {
+                    if (st == 1 && !(ci + 1 < p.n_cseq)) break;
+                    const uint32_t best = st == 0 ? abest : bbest;
+                    const uint32_t cj = st == 0 ? cjA : cjB;
+                    if (PACKED) {
+                        int b_lo = (int)(int16_t)(best & 0xffff), b_hi = (int)(int16_t)(best >> 16);
+                        if (id_lo != 0xffffffffu)
+                            p.best[(size_t)id_lo * p.n_cseq + cj] = (b_lo >= p.ovf_thresh) ? -1 : b_lo;
+                        if (id_hi != 0xffffffffu)
+                            p.best[(size_t)id_hi * p.n_cseq + cj] = (b_hi >= p.ovf_thresh) ? -1 : b_hi;
+                    } else {
+                        p.best[(size_t)id_lo * p.n_cseq + cj] = (int)best;
+                    }
                 }
             }
         }

@@ -68,7 +68,7 @@ struct Device {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     // scoring + profiled (replicated on every device)
-    DevBuf ccodes, coff, wk, lut;
+    DevBuf ccodes, coff, wk, lut, corder;
     // batch state
     DevBuf rseq, roff, best, score, status, tier, wide_ids, counters;
     // align state
@@ -87,10 +87,14 @@ struct KernelEntry {
     void (*packed)(const ScoreParams);
     void (*wide)(const ScoreParams);
     void (*fill)(const AlignParams);
+    void (*packed2)(const ScoreParams);  // two column sequences per sweep
 };
 
 #define ZK(G, K) \
-    KernelEntry { G, K, sw_score_kernel<G, K, true>, sw_score_kernel<G, K, false>, sw_align_fill_kernel<G, K, true> }
+    KernelEntry {                                                                                          \
+        G, K, sw_score_kernel<G, K, true, 1>, sw_score_kernel<G, K, false, 1>, sw_align_fill_kernel<G, K, true>, \
+            sw_score_kernel<G, K, true, 2>                                                                 \
+    }
 
 // Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
 // sequence of a batch.  G = 8 serves short reads (150 nt -> 8 x 19), G = 32 the longest rows
@@ -122,7 +126,7 @@ struct zoe_cuda_ctx {
     std::vector<uint8_t> prof_bytes;
     std::vector<uint64_t> prof_off;
     std::vector<uint8_t> ccodes;
-    std::vector<uint32_t> coff;
+    std::vector<uint32_t> coff, corder;
     std::vector<int8_t> wk;
     int n_csym = 0;
     uint32_t max_prof_len = 0;
@@ -337,6 +341,9 @@ int upload_scoring_and_profiled(zoe_cuda_ctx *ctx) {
                                 d.stream));
         CU(ctx, cudaMemcpyAsync(d.wk.p, ctx->wk.data(), ctx->wk.size(), cudaMemcpyHostToDevice, d.stream));
         CU(ctx, cudaMemcpyAsync(d.lut.p, ctx->lut, 256, cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, d.corder.reserve(ctx->corder.size() * sizeof(uint32_t)));
+        CU(ctx, cudaMemcpyAsync(d.corder.p, ctx->corder.data(), ctx->corder.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                d.stream));
         CU(ctx, d.pbytes.reserve(ctx->prof_bytes.size()));
         CU(ctx, d.weights.reserve(ctx->weights.size()));
         CU(ctx, cudaMemcpyAsync(d.pbytes.p, ctx->prof_bytes.data(), ctx->prof_bytes.size(), cudaMemcpyHostToDevice,
@@ -411,7 +418,8 @@ int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *o
 
 int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed, const uint32_t *task_ids,
                  uint32_t n_ids) {
-    void (*fn)(const ScoreParams) = packed ? k.packed : k.wide;
+    const bool two_streams = packed && ctx->n_prof >= 2 && !getenv("ZOE_CUDA_ONE_STREAM");
+    void (*fn)(const ScoreParams) = packed ? (two_streams ? k.packed2 : k.packed) : k.wide;
     LaunchPlan plan;
     int rc = plan_launch(ctx, k, fn, &plan);
     if (rc) return rc;
@@ -424,6 +432,7 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
     p.n_tasks = packed ? (n_seq + 1) / 2 : n_seq;
     p.ccodes = d.ccodes.as<uint8_t>();
     p.coff = d.coff.as<uint32_t>();
+    p.corder = two_streams ? d.corder.as<uint32_t>() : nullptr;
     p.n_cseq = ctx->n_prof;
     p.ccodes_bytes = (uint32_t)ctx->ccodes.size();
     p.cols_in_smem = plan.cols_in_smem;
@@ -1012,7 +1021,7 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
     if (!ctx) return;
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
-        for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
+        for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.corder, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.long_ids, &d.long_bnd,
@@ -1083,6 +1092,12 @@ int zoe_cuda_set_profiled(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64
         ctx->prof_off[j] = offsets[j] - offsets[0];
         ctx->coff[j] = (uint32_t)ctx->prof_off[j];
     }
+    // visiting order for the two-stream score kernel: longest first, so paired sweeps have similar lengths
+    ctx->corder.resize(n);
+    for (uint32_t j = 0; j < n; ++j) ctx->corder[j] = j;
+    std::stable_sort(ctx->corder.begin(), ctx->corder.end(), [&](uint32_t a, uint32_t b) {
+        return ctx->coff[a + 1] - ctx->coff[a] > ctx->coff[b + 1] - ctx->coff[b];
+    });
     // dense column-symbol codes: only the symbols that occur in the profiled set get a table row
     int dense[64];
     for (int i = 0; i < 64; ++i) dense[i] = -1;
