@@ -34,6 +34,7 @@
 // score (striped.rs:608-633: i8 holds 1..=254, i16 1..=65534).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace zoe_cuda {
@@ -97,27 +98,34 @@ __host__ __device__ inline int score_tab_bytes(int n_csym, int G, int K) { retur
 
 // One column step of one systolic stream: K rows, fully unrolled.  `tp` points at this lane's uint4 of the
 // column symbol's table row; (diag, E) enter from the lane above.
+// H is kept in two register sets (P = step parity): column j-1 is read from set P, column j is written to
+// set 1-P, so the loop-carried "diag = H[i]" needs no register moves.
 #define ZOE_SCORE_ROW(ST, W)                                     \
     {                                                            \
         uint32_t x = O::max3(ST##E, ST##F[i], go_s) - go_s;      \
         uint32_t H = O::addmax(ST##diag, W, x);                  \
-        ST##diag = ST##H[i];                                     \
+        ST##diag = ST##H[PO][i];                                 \
         ST##E = O::addmax(ST##E, neg_ge, H);                     \
         ST##F[i] = O::addmax(ST##F[i], neg_ge, H);               \
-        ST##H[i] = H;                                            \
-        if (i & 1)                                               \
+        ST##H[PN][i] = H;                                        \
+        if (i & 1) {                                             \
             ST##best = O::max3(ST##best, H, ST##hp);             \
-        else                                                     \
+        } else {                                                 \
             ST##hp = H;                                          \
+        }                                                        \
     }
 
+// Tried and rejected on B200 (scripts/variants.py, 400k reads, cfg 2): moving the running maximum to the FMA pipe
+// with HMNMX2 on the integer bit patterns (exact below 0x7C00) lowers the ALU count to 4.0 per pair but raises the
+// issue count; it measured 5.79 TCUPS against 6.18 (in place) / 6.45 (ping-pong) for the DPX max3 form.
+//
 // NS = number of column sequences swept concurrently by one group (1 or 2).  With NS = 2 every thread
 // carries two independent H/E/F recurrences that share the task's score table, which doubles the
 // instruction-level parallelism available to hide the 4-deep dependent chain per row (the ALU pipe, not the
 // issue slots or the latency, then bounds the kernel).  Column sequences are visited in `corder`
 // (longest first) so the two streams of a pair have similar lengths.
-template <int G, int K, bool PACKED, int NS>
-__global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
+template <int G, int K, bool PACKED, int NS, bool PP = (NS == 2 && K <= 19)>
+__global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_score_kernel(const ScoreParams p) {
     using O = Ops<PACKED>;
     constexpr int K4 = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;
@@ -222,13 +230,14 @@ __global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
                 csB = cc + cB0;
             }
 
-            uint32_t aH[K], aF[K], bH[NS == 2 ? K : 1], bF[NS == 2 ? K : 1];
+            constexpr int NP = PP ? 2 : 1;  // register sets of H (ping-pong or in place)
+            uint32_t aH[NP][K], aF[K], bH[NP][NS == 2 ? K : 1], bF[NS == 2 ? K : 1];
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-                aH[i] = 0;
+                aH[0][i] = aH[NP - 1][i] = 0;
                 aF[i] = 0;
                 if (NS == 2) {
-                    bH[i] = 0;
+                    bH[0][i] = bH[NP - 1][i] = 0;
                     bF[i] = 0;
                 }
             }
@@ -236,7 +245,9 @@ __global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
             uint32_t bbest = 0, bh_last = 0, be_out = 0, bh_up_prev = 0;
             const int nsteps = max(LA, LB) + G - 1;
 
-            for (int step = 0; step < nsteps; ++step) {
+            auto do_step = [&](auto parity, const int step) {
+                constexpr int PO = PP ? decltype(parity)::value : 0;      // set holding column j-1
+                constexpr int PN = PP ? 1 - decltype(parity)::value : 0;  // set receiving column j
                 uint32_t ah_in = __shfl_up_sync(FULL, ah_last, 1, G);
                 uint32_t ae_in = __shfl_up_sync(FULL, ae_out, 1, G);
                 uint32_t bh_in = 0, be_in = 0;
@@ -274,12 +285,12 @@ __global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
                     }
                     if (K & 1) {
                         abest = O::max2(abest, ahp);
-                        bbest = O::max2(bbest, bhp);
+                        if (NS == 2) bbest = O::max2(bbest, bhp);
                     }
-                    ah_last = aH[K - 1];
+                    ah_last = aH[PN][K - 1];
                     ae_out = aE;
                     if (NS == 2) {
-                        bh_last = bH[K - 1];
+                        bh_last = bH[PN][K - 1];
                         be_out = bE;
                     }
                 } else if (actA) {
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
                         }
                     }
                     if (K & 1) abest = O::max2(abest, ahp);
-                    ah_last = aH[K - 1];
+                    ah_last = aH[PN][K - 1];
                     ae_out = aE;
                 } else if (actB) {
                     const uint4 *tpB = tab_lane + (size_t)csB[j] * (K4 * G);
@@ -312,11 +323,17 @@ __global__ void __launch_bounds__(512) sw_score_kernel(const ScoreParams p) {
                         }
                     }
                     if (K & 1) bbest = O::max2(bbest, bhp);
-                    bh_last = bH[K - 1];
+                    bh_last = bH[PN][K - 1];
                     be_out = bE;
                 }
                 ah_up_prev = ah_in;
                 bh_up_prev = bh_in;
+            };
+            // A lane's active steps are consecutive, so its parity alternates exactly while it is active; before
+            // that both register sets are zero, after that they are never read again.
+            for (int step = 0; step < nsteps; step += 2) {
+                do_step(std::integral_constant<int, 0>{}, step);
+                if (step + 1 < nsteps) do_step(std::integral_constant<int, 1>{}, step + 1);
             }
 
             // ---- reduce the group's best and write the exact scores ----

@@ -5,6 +5,7 @@
 // computed by a CUDA kernel below.
 #include "../../include/zoe_cuda.h"
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -244,6 +245,21 @@ __global__ void __launch_bounds__(256) dpx_peak_kernel(uint32_t *out, int iters,
             if (KIND == 0) {
                 a[i] = __viaddmax_s16x2(a[i], c, b[i]);
                 b[i] = __viaddmax_s16x2(b[i], c, a[i]);
+            } else if (KIND == 2) {
+                // half2 max on the integer bit patterns: which pipe does HMNMX2 use?
+                __half2 ha = *reinterpret_cast<__half2 *>(&a[i]), hb = *reinterpret_cast<__half2 *>(&b[i]);
+                ha = __hmax2(ha, hb);
+                hb = __hmax2(hb, *reinterpret_cast<const __half2 *>(&c));
+                a[i] = *reinterpret_cast<uint32_t *>(&ha) + 1u;
+                b[i] = *reinterpret_cast<uint32_t *>(&hb) ^ a[i];
+            } else if (KIND == 3) {
+                // 4 DPX + 1 half2 max + 1 add per cell pair
+                uint32_t x = __vimax3_s16x2(a[i], b[i], g) - g;
+                uint32_t h = __viaddmax_s16x2(a[(i + 1) & 7], c, x);
+                a[i] = __viaddmax_s16x2(a[i], c, h);
+                b[i] = __viaddmax_s16x2(b[i], c, h);
+                __half2 hm = __hmax2(*reinterpret_cast<__half2 *>(&a[(i + 3) & 7]), *reinterpret_cast<__half2 *>(&h));
+                a[(i + 3) & 7] = *reinterpret_cast<uint32_t *>(&hm);
             } else {
                 // the score kernel's per-cell-pair mix: 1 max3 + 1 add + 3 addmax + 0.5 max3
                 uint32_t x = __vimax3_s16x2(a[i], b[i], g) - g;
@@ -296,8 +312,8 @@ int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan
     LaunchPlan bp;
     for (int cols_in_smem = 1; cols_in_smem >= 0; --cols_in_smem) {
         if (cols_in_smem && ctx->ccodes.size() > 96 * 1024) continue;
-        for (int threads : {512, 256, 128, 64, 32}) {
-            if (threads < k.G) continue;
+        for (int threads : {512, 384, 256, 128, 64, 32}) {
+            if (threads < k.G || threads % k.G) continue;
             size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem);
             if (smem > 227 * 1024) continue;
             int nb = 0;
@@ -420,6 +436,7 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
                  uint32_t n_ids) {
     const bool two_streams = packed && ctx->n_prof >= 2 && !getenv("ZOE_CUDA_ONE_STREAM");
     void (*fn)(const ScoreParams) = packed ? (two_streams ? k.packed2 : k.packed) : k.wide;
+
     LaunchPlan plan;
     int rc = plan_launch(ctx, k, fn, &plan);
     if (rc) return rc;
@@ -1296,6 +1313,10 @@ int zoe_cuda_dpx_peak(zoe_cuda_ctx *ctx, int kind, double *giga_lane_instr_per_s
         CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
         if (kind == 0)
             dpx_peak_kernel<0><<<blocks, threads, 0, d.stream>>>(out.as<uint32_t>(), iters, 12345u + rep);
+        else if (kind == 2)
+            dpx_peak_kernel<2><<<blocks, threads, 0, d.stream>>>(out.as<uint32_t>(), iters, 12345u + rep);
+        else if (kind == 3)
+            dpx_peak_kernel<3><<<blocks, threads, 0, d.stream>>>(out.as<uint32_t>(), iters, 12345u + rep);
         else
             dpx_peak_kernel<1><<<blocks, threads, 0, d.stream>>>(out.as<uint32_t>(), iters, 12345u + rep);
         CU(ctx, cudaGetLastError());
@@ -1307,7 +1328,8 @@ int zoe_cuda_dpx_peak(zoe_cuda_ctx *ctx, int kind, double *giga_lane_instr_per_s
     }
     out.release();
     // kind 0: 16 DPX instructions per inner iteration; kind 1: 8 cell pairs x 5.5 instructions
-    double instr_per_thread = (kind == 0) ? 16.0 * iters : 8.0 * 5.5 * iters;
+    // kind 2: 8 x (2 hmax2 + 2 integer ops); kind 3: 8 cell pairs x 6 instructions
+    double instr_per_thread = (kind == 0) ? 16.0 * iters : (kind == 2 ? 32.0 * iters : (kind == 3 ? 48.0 * iters : 8.0 * 5.5 * iters));
     double lanes = (double)blocks * threads;
     *giga_lane_instr_per_s = instr_per_thread * lanes / (best_ms * 1e-3) / 1e9;
     if (ms_out) *ms_out = best_ms;
