@@ -310,10 +310,15 @@ template <class Fn>
 int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan) {
     int best_warps = 0;
     LaunchPlan bp;
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) {
+        cudaGetLastError();
+        fa.maxThreadsPerBlock = 1024;
+    }
     for (int cols_in_smem = 1; cols_in_smem >= 0; --cols_in_smem) {
         if (cols_in_smem && ctx->ccodes.size() > 96 * 1024) continue;
         for (int threads : {512, 384, 256, 128, 64, 32}) {
-            if (threads < k.G || threads % k.G) continue;
+            if (threads < k.G || threads % k.G || threads > fa.maxThreadsPerBlock) continue;
             size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem);
             if (smem > 227 * 1024) continue;
             int nb = 0;
