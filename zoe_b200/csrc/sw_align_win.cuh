@@ -1,0 +1,694 @@
+// sw_align_win.cuh -- alignment with traceback in two passes over a checkpointed DP (sm_100a).
+//
+// Same contract as sw_align.cuh (zoe: sw_simd_align, src/alignment/sw/striped.rs:449-598 +
+// BackTrackable::to_alignment, src/alignment/types/backtrack.rs:290-342), different cost model.  A traceback
+// only ever consults cells between the alignment's start and end columns, so writing direction bits for the
+// whole n x m matrix (what zoe's CPU kernel must do, and what sw_align_fill_kernel does) wastes > 85 % of the
+// work when a 150-nt read is aligned against a 1.7-kb segment.  Here:
+//
+//   pass A  sw_align_scan_kernel     the score recurrence (4.5 ALU instr per packed cell pair, no direction
+//                                    bits) over all columns; it tracks the best cell exactly as zoe does (max H,
+//                                    then min r, then min c -- striped.rs:555-583) and parks the column state
+//                                    (H and the along-row gap state of every row) every CB columns.
+//   pairing win_classify / win_bucket_scan / win_scatter: a counting sort of the mapped pairs by
+//                                    (profiled sequence, checkpoint block), so two pairs that restart from
+//                                    the same column share one packed s16x2 task.
+//   pass B  sw_align_winfill_kernel  restarts from the checkpoint at or before c_end - (r_end + 1 + slack),
+//                                    recomputes that window with the five direction bits per cell.  The DP
+//                                    values inside the window are bit-identical to the full matrix because
+//                                    the restart state is the full matrix's own column.
+//   walk    sw_traceback_win_kernel  zoe's priority walk over the window; a walk that reaches the left edge
+//                                    of its window (a gap longer than the slack) is handed to the literal
+//                                    kernel, like a tie hazard.
+//
+// Checkpoint layout per pass-A task and profiled sequence: ckpt[kb-1][i4][lane] = uint4, the lane's vector
+// (H[0..K), F[0..K)) in 16-byte pieces; kb = 1 .. (L-1)/CB is the state entering column kb*CB.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sw_align.cuh"
+
+namespace zoe_cuda {
+
+__host__ __device__ inline int ckpt_vec4_per_lane(int K) { return (2 * K + 3) / 4; }
+
+struct WinParams {
+    ScoreParams s;               // sequences, tables, scoring (s.best unused; s.n_rseq = sequences in the chunk)
+    AlignEnd *ends;              // [n_rseq_total * n_cseq]
+    uint32_t chunk_first;        // first batch sequence of the chunk
+    // checkpoints (pass A writes, pass B reads)
+    uint4 *ckpt;
+    const uint64_t *ckpt_base;   // [n_cseq] uint4 offset of each profiled sequence inside a task's region
+    uint64_t ckpt_task_stride;   // uint4 per pass-A task
+    int cb_log2;                 // checkpoint spacing CB = 1 << cb_log2 columns
+    uint32_t slack;              // extra columns kept left of the shortest possible walk
+    // pairing
+    uint32_t nblk;               // checkpoint blocks per profiled sequence (key = cj * nblk + block)
+    uint32_t *hist;              // [n_cseq * nblk] bucket sizes, then bucket cursors
+    uint32_t *bucket_start;      // [n_cseq * nblk + 1] even-aligned exclusive scan
+    uint32_t *items;             // sorted global pair ids, 0xffffffff = empty slot
+    uint32_t *n_items;           // [1] total slots (even)
+    // pass B
+    uint32_t *flags;             // window flag words
+    uint64_t win_task_stride;    // words per pass-B task = Wmax * G * NW
+    uint32_t wmax;               // window capacity in columns
+};
+
+__device__ __forceinline__ uint32_t win_start(uint32_t r_end, uint32_t c_end, uint32_t slack, int cb_log2) {
+    const uint32_t need = r_end + 1 + slack;  // columns the walk may touch: #M <= r_end + 1, #I + 1 <= slack
+    const uint32_t lo = (c_end + 1 > need) ? (c_end + 1 - need) : 0;
+    return (lo >> cb_log2) << cb_log2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass A: scores, end cells, checkpoints
+// ---------------------------------------------------------------------------------------------
+template <int G, int K>
+__global__ void __launch_bounds__(512) sw_align_scan_kernel(const WinParams wp) {
+    using O = Ops<true>;
+    const ScoreParams &p = wp.s;
+    constexpr int K4 = (K + 3) / 4;
+    constexpr int CK4 = (2 * K + 3) / 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    const int tid = threadIdx.x;
+    const int lig = tid % G;
+    const int group_in_block = tid / G;
+    const int groups_per_block = blockDim.x / G;
+
+    const int tab_bytes = p.n_csym * K4 * G * 16;
+    uint4 *tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * tab_bytes);
+    uint8_t *s_lut = smem + (size_t)groups_per_block * tab_bytes;
+    int8_t *s_wk = reinterpret_cast<int8_t *>(s_lut + 256);
+    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
+    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
+    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
+    if (p.cols_in_smem)
+        for (uint32_t i = tid; i < p.ccodes_bytes; i += blockDim.x) s_cc[i] = p.ccodes[i];
+    __syncthreads();
+    const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
+
+    const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+    const uint32_t cb_mask = (1u << wp.cb_log2) - 1u;
+
+    const uint32_t total_groups = gridDim.x * groups_per_block;
+    const uint32_t trips = (p.n_tasks + total_groups - 1) / total_groups;
+    const uint32_t first = blockIdx.x * groups_per_block + group_in_block;
+
+    for (uint32_t trip = 0; trip < trips; ++trip) {
+        const uint32_t task = first + trip * total_groups;
+        const bool valid = task < p.n_tasks;
+        uint32_t id_lo = 0xffffffffu, id_hi = 0xffffffffu;
+        if (valid) {
+            const uint32_t a = 2 * task, b = 2 * task + 1;
+            id_lo = wp.chunk_first + a;
+            id_hi = (b < p.n_rseq) ? wp.chunk_first + b : 0xffffffffu;
+        }
+        uint64_t off_lo = 0, off_hi = 0;
+        int len_lo = 0, len_hi = 0;
+        if (id_lo != 0xffffffffu) {
+            off_lo = p.roff[id_lo];
+            len_lo = (int)(p.roff[id_lo + 1] - off_lo);
+        }
+        if (id_hi != 0xffffffffu) {
+            off_hi = p.roff[id_hi];
+            len_hi = (int)(p.roff[id_hi + 1] - off_hi);
+        }
+
+        __syncwarp();
+        for (int i4 = 0; i4 < K4; ++i4) {
+            int sym_lo[4], sym_hi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i4 * 4 + q, r = lig * K + i;
+                sym_lo[q] = (i < K && r < len_lo) ? (int)s_lut[p.rseq[off_lo + r]] : -1;
+                sym_hi[q] = (i < K && r < len_hi) ? (int)s_lut[p.rseq[off_hi + r]] : -1;
+            }
+            for (int s = 0; s < p.n_csym; ++s) {
+                const int8_t *wrow = s_wk + s * p.S;
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int wl = sym_lo[q] >= 0 ? (int)wrow[sym_lo[q]] : kPadWeight;
+                    const int wh = sym_hi[q] >= 0 ? (int)wrow[sym_hi[q]] : kPadWeight;
+                    w[q] = (uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16);
+                }
+                tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        __syncwarp();
+
+        uint4 *ck_task = wp.ckpt + (size_t)task * wp.ckpt_task_stride;
+
+        for (uint32_t cj = 0; cj < p.n_cseq; ++cj) {
+            const uint32_t c0 = p.coff[cj];
+            const int L = (int)(p.coff[cj + 1] - c0);
+            const uint8_t *cs = cc + c0;
+            uint4 *ck = ck_task + wp.ckpt_base[cj] + lig;
+
+            uint32_t Hrow[K], Frow[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                Hrow[i] = 0;
+                Frow[i] = 0;
+            }
+            uint32_t h_last = 0, e_out = 0, h_up_prev = 0;
+            int bv_lo = 0, bv_hi = 0, bi_lo = 0, bi_hi = 0, bj_lo = 0, bj_hi = 0;
+            const int nsteps = L + G - 1;
+
+            for (int step = 0; step < nsteps; ++step) {
+                uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G);
+                uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G);
+                if (lig == 0) {
+                    h_in = 0;
+                    e_in = 0;
+                }
+                const int j = step - lig;
+                if (j >= 0 && j < L) {
+                    const uint4 *tp = tab + (size_t)cs[j] * (K4 * G) + lig;
+                    uint32_t diag = h_up_prev;
+                    uint32_t E = e_in;
+                    uint32_t cm = 0, hprev = 0;
+#pragma unroll
+                    for (int i4 = 0; i4 < K4; ++i4) {
+                        const uint4 w4 = tp[i4 * G];
+                        const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int i = i4 * 4 + q;
+                            if (i < K) {
+                                uint32_t x = O::max3(E, Frow[i], go_s) - go_s;
+                                uint32_t H = O::addmax(diag, wv[q], x);
+                                diag = Hrow[i];
+                                E = O::addmax(E, neg_ge, H);
+                                Frow[i] = O::addmax(Frow[i], neg_ge, H);
+                                Hrow[i] = H;
+                                if (i & 1)
+                                    cm = O::max3(cm, H, hprev);
+                                else
+                                    hprev = H;
+                            }
+                        }
+                    }
+                    if (K & 1) cm = O::max2(cm, hprev);
+                    h_last = Hrow[K - 1];
+                    e_out = E;
+
+                    // ---- best-cell bookkeeping: (max H, min r, min c), striped.rs:555-583 ----
+                    const int cm_lo = (int)(int16_t)(cm & 0xffff);
+                    const int cm_hi = (int)(int16_t)(cm >> 16);
+                    if (cm_lo > 0 && cm_lo >= bv_lo) {
+                        int irow = K;
+#pragma unroll
+                        for (int i = K - 1; i >= 0; --i)
+                            if ((int)(int16_t)(Hrow[i] & 0xffff) == cm_lo) irow = i;
+                        if (cm_lo > bv_lo || irow < bi_lo) {
+                            bv_lo = cm_lo;
+                            bi_lo = irow;
+                            bj_lo = j;
+                        }
+                    }
+                    if (cm_hi > 0 && cm_hi >= bv_hi) {
+                        int irow = K;
+#pragma unroll
+                        for (int i = K - 1; i >= 0; --i)
+                            if ((int)(int16_t)(Hrow[i] >> 16) == cm_hi) irow = i;
+                        if (cm_hi > bv_hi || irow < bi_hi) {
+                            bv_hi = cm_hi;
+                            bi_hi = irow;
+                            bj_hi = j;
+                        }
+                    }
+
+                    // ---- checkpoint: the state entering column j + 1 when that is a block boundary ----
+                    if ((((uint32_t)(j + 1)) & cb_mask) == 0 && j + 1 < L && valid) {
+                        uint4 *dst = ck + (size_t)((((uint32_t)(j + 1)) >> wp.cb_log2) - 1) * (CK4 * G);
+                        uint32_t v[CK4 * 4];
+#pragma unroll
+                        for (int i = 0; i < CK4 * 4; ++i) v[i] = 0;
+#pragma unroll
+                        for (int i = 0; i < K; ++i) {
+                            v[i] = Hrow[i];
+                            v[K + i] = Frow[i];
+                        }
+#pragma unroll
+                        for (int q = 0; q < CK4; ++q) dst[q * G] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+                h_up_prev = h_in;
+            }
+
+            unsigned long long key_lo = ((unsigned long long)(uint32_t)bv_lo << 40) |
+                                        ((unsigned long long)(0xFFFFFu - (uint32_t)(lig * K + bi_lo)) << 20) |
+                                        (unsigned long long)(0xFFFFFu - (uint32_t)bj_lo);
+            unsigned long long key_hi = ((unsigned long long)(uint32_t)bv_hi << 40) |
+                                        ((unsigned long long)(0xFFFFFu - (uint32_t)(lig * K + bi_hi)) << 20) |
+                                        (unsigned long long)(0xFFFFFu - (uint32_t)bj_hi);
+#pragma unroll
+            for (int d = G / 2; d >= 1; d >>= 1) {
+                unsigned long long o = __shfl_xor_sync(FULL, key_lo, d, G);
+                key_lo = o > key_lo ? o : key_lo;
+                o = __shfl_xor_sync(FULL, key_hi, d, G);
+                key_hi = o > key_hi ? o : key_hi;
+            }
+            if (lig == 0 && valid) {
+                if (id_lo != 0xffffffffu) {
+                    AlignEnd e;
+                    int b = (int)(key_lo >> 40);
+                    e.best = (b >= p.ovf_thresh) ? -1 : b;
+                    e.r_end = 0xFFFFFu - (uint32_t)((key_lo >> 20) & 0xFFFFFu);
+                    e.c_end = 0xFFFFFu - (uint32_t)(key_lo & 0xFFFFFu);
+                    wp.ends[(size_t)id_lo * p.n_cseq + cj] = e;
+                }
+                if (id_hi != 0xffffffffu) {
+                    AlignEnd e;
+                    int b = (int)(key_hi >> 40);
+                    e.best = (b >= p.ovf_thresh) ? -1 : b;
+                    e.r_end = 0xFFFFFu - (uint32_t)((key_hi >> 20) & 0xFFFFFu);
+                    e.c_end = 0xFFFFFu - (uint32_t)(key_hi & 0xFFFFFu);
+                    wp.ends[(size_t)id_hi * p.n_cseq + cj] = e;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pairing: classify every pair of the chunk, counting-sort the mapped ones by (profiled, block)
+// ---------------------------------------------------------------------------------------------
+struct ClassifyParams {
+    const AlignEnd *ends;
+    const uint64_t *roff;
+    uint32_t n_cseq, chunk_first, n_slots;
+    int cb_log2;
+    uint32_t slack, nblk;
+    int all_exact;
+    uint32_t *hist;
+    int32_t *best_arr;
+    uint32_t *score;
+    uint8_t *status, *tier, *hazard;
+    uint32_t *ref_start, *ref_end, *query_start, *query_end, *cig_count;
+    unsigned long long *counters;  // [5] exact-list length, [8] packed overflows
+    uint32_t *hazard_list;
+};
+
+// Returns the bucket key of a pair that needs pass B, or 0xffffffff.
+__device__ __forceinline__ uint32_t win_key(const AlignEnd &e, uint32_t cj, uint32_t n, int all_exact, uint32_t slack,
+                                            int cb_log2, uint32_t nblk) {
+    if (e.best <= 0 || n == 0 || all_exact) return 0xffffffffu;
+    return cj * nblk + (win_start(e.r_end, e.c_end, slack, cb_log2) >> cb_log2);
+}
+
+__global__ void win_classify_kernel(const ClassifyParams t) {
+    const uint32_t pairs = t.n_slots * t.n_cseq;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= pairs) return;
+    const uint32_t seq = t.chunk_first + k / t.n_cseq, cj = k % t.n_cseq;
+    const size_t gid = (size_t)seq * t.n_cseq + cj;
+    const AlignEnd e = t.ends[gid];
+    const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
+    t.hazard[gid] = 0;
+    t.cig_count[gid] = 0;
+    t.best_arr[gid] = e.best;
+    if (e.best < 0) {  // packed lanes reached the overflow threshold: exact 32-bit score + literal kernel
+        t.status[gid] = 0xFF;
+        t.hazard[gid] = 1;
+        atomicAdd(&t.counters[8], 1ULL);
+        unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
+        t.hazard_list[slot] = (uint32_t)gid;
+        return;
+    }
+    if (e.best == 0 || n == 0) {
+        t.score[gid] = 0;
+        t.status[gid] = 2;  // Unmapped
+        t.tier[gid] = 8;
+        t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
+        return;
+    }
+    t.score[gid] = (uint32_t)e.best;
+    t.status[gid] = 0;
+    t.tier[gid] = tier_of((uint32_t)e.best);
+    if (t.all_exact) {
+        unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
+        t.hazard_list[slot] = (uint32_t)gid;
+        t.hazard[gid] = 1;
+        return;
+    }
+    atomicAdd(&t.hist[win_key(e, cj, n, 0, t.slack, t.cb_log2, t.nblk)], 1u);
+}
+
+// Single-block exclusive scan of the bucket sizes rounded up to even (a pass-B task holds two pairs of ONE
+// bucket); leaves hist zeroed so the scatter kernel can use it as the per-bucket cursor.
+__global__ void win_bucket_scan_kernel(uint32_t *hist, uint32_t n_keys, uint32_t *bucket_start, uint32_t *n_items) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_keys; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = 0;
+        if (i < n_keys) {
+            v = (hist[i] + 1u) & ~1u;
+            hist[i] = 0;
+        }
+        uint32_t incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0u;
+            uint32_t wi = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_warp[wid] + incl - v;
+        if (i < n_keys) bucket_start[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        bucket_start[n_keys] = s_carry;
+        *n_items = s_carry;
+    }
+}
+
+__global__ void win_scatter_kernel(const ClassifyParams t, const uint32_t *bucket_start, uint32_t *items) {
+    const uint32_t pairs = t.n_slots * t.n_cseq;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= pairs) return;
+    const uint32_t seq = t.chunk_first + k / t.n_cseq, cj = k % t.n_cseq;
+    const size_t gid = (size_t)seq * t.n_cseq + cj;
+    const AlignEnd e = t.ends[gid];
+    const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
+    const uint32_t key = win_key(e, cj, n, t.all_exact, t.slack, t.cb_log2, t.nblk);
+    if (key == 0xffffffffu) return;
+    const uint32_t slot = bucket_start[key] + atomicAdd(&t.hist[key], 1u);
+    items[slot] = (uint32_t)gid;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass B: direction bits for the window [ws, c_end] of every mapped pair
+// ---------------------------------------------------------------------------------------------
+template <int G, int K>
+__global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams wp) {
+    using O = Ops<true>;
+    const ScoreParams &p = wp.s;
+    constexpr int K4 = (K + 3) / 4;
+    constexpr int CK4 = (2 * K + 3) / 4;
+    constexpr int NW = (((K + 2) / 3) + 3) & ~3;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    const int tid = threadIdx.x;
+    const int lig = tid % G;
+    const int group_in_block = tid / G;
+    const int groups_per_block = blockDim.x / G;
+
+    const int tab_bytes = p.n_csym * K4 * G * 16;
+    uint4 *tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * tab_bytes);
+    uint8_t *s_lut = smem + (size_t)groups_per_block * tab_bytes;
+    int8_t *s_wk = reinterpret_cast<int8_t *>(s_lut + 256);
+    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
+    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
+    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
+    if (p.cols_in_smem)
+        for (uint32_t i = tid; i < p.ccodes_bytes; i += blockDim.x) s_cc[i] = p.ccodes[i];
+    __syncthreads();
+    const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
+
+    const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge), one_s = O::splat(1), c21 = O::splat(21);
+
+    const uint32_t n_tasks = *wp.n_items / 2;
+    const uint32_t total_groups = gridDim.x * groups_per_block;
+    const uint32_t trips = (n_tasks + total_groups - 1) / total_groups;
+    const uint32_t first = blockIdx.x * groups_per_block + group_in_block;
+
+    for (uint32_t trip = 0; trip < trips; ++trip) {
+        const uint32_t task = first + trip * total_groups;
+        const bool valid = task < n_tasks;
+        uint32_t g_lo = 0xffffffffu, g_hi = 0xffffffffu;
+        if (valid) {
+            g_lo = wp.items[2 * task];
+            g_hi = wp.items[2 * task + 1];
+        }
+        // the two pairs share (profiled sequence, window start); a bucket of odd size leaves g_hi empty
+        uint32_t cj = 0, ws = 0;
+        int we = -1;  // last column of the window
+        uint64_t off_lo = 0, off_hi = 0;
+        int len_lo = 0, len_hi = 0;
+        uint32_t seqA_lo = 0, seqA_hi = 0;  // chunk-relative sequence index (locates the checkpoint)
+        if (g_lo != 0xffffffffu) {
+            const uint32_t seq = g_lo / p.n_cseq;
+            cj = g_lo % p.n_cseq;
+            const AlignEnd e = wp.ends[g_lo];
+            ws = win_start(e.r_end, e.c_end, wp.slack, wp.cb_log2);
+            we = (int)e.c_end;
+            off_lo = p.roff[seq];
+            len_lo = (int)(p.roff[seq + 1] - off_lo);
+            seqA_lo = seq - wp.chunk_first;
+        }
+        if (g_hi != 0xffffffffu) {
+            const uint32_t seq = g_hi / p.n_cseq;
+            const AlignEnd e = wp.ends[g_hi];
+            we = max(we, (int)e.c_end);
+            off_hi = p.roff[seq];
+            len_hi = (int)(p.roff[seq + 1] - off_hi);
+            seqA_hi = seq - wp.chunk_first;
+        }
+
+        __syncwarp();
+        for (int i4 = 0; i4 < K4; ++i4) {
+            int sym_lo[4], sym_hi[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i4 * 4 + q, r = lig * K + i;
+                sym_lo[q] = (i < K && r < len_lo) ? (int)s_lut[p.rseq[off_lo + r]] : -1;
+                sym_hi[q] = (i < K && r < len_hi) ? (int)s_lut[p.rseq[off_hi + r]] : -1;
+            }
+            for (int s = 0; s < p.n_csym; ++s) {
+                const int8_t *wrow = s_wk + s * p.S;
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int wl = sym_lo[q] >= 0 ? (int)wrow[sym_lo[q]] : kPadWeight;
+                    const int wh = sym_hi[q] >= 0 ? (int)wrow[sym_hi[q]] : kPadWeight;
+                    w[q] = (uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16);
+                }
+                tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        __syncwarp();
+
+        // ---- restore the column state entering column ws ----
+        uint32_t Hrow[K], Frow[K];
+        {
+            uint32_t v[CK4 * 4];
+#pragma unroll
+            for (int i = 0; i < CK4 * 4; ++i) v[i] = 0;
+            if (ws > 0) {
+                const uint32_t kb = ws >> wp.cb_log2;
+                if (g_lo != 0xffffffffu) {
+                    const uint4 *src = wp.ckpt + (size_t)(seqA_lo >> 1) * wp.ckpt_task_stride + wp.ckpt_base[cj] +
+                                       (size_t)(kb - 1) * (CK4 * G) + lig;
+                    const int sh = (seqA_lo & 1) ? 16 : 0;
+#pragma unroll
+                    for (int q = 0; q < CK4; ++q) {
+                        const uint4 x = src[q * G];
+                        v[4 * q] |= (x.x >> sh) & 0xffffu;
+                        v[4 * q + 1] |= (x.y >> sh) & 0xffffu;
+                        v[4 * q + 2] |= (x.z >> sh) & 0xffffu;
+                        v[4 * q + 3] |= (x.w >> sh) & 0xffffu;
+                    }
+                }
+                if (g_hi != 0xffffffffu) {
+                    const uint4 *src = wp.ckpt + (size_t)(seqA_hi >> 1) * wp.ckpt_task_stride + wp.ckpt_base[cj] +
+                                       (size_t)(kb - 1) * (CK4 * G) + lig;
+                    const int sh = (seqA_hi & 1) ? 16 : 0;
+#pragma unroll
+                    for (int q = 0; q < CK4; ++q) {
+                        const uint4 x = src[q * G];
+                        v[4 * q] |= ((x.x >> sh) & 0xffffu) << 16;
+                        v[4 * q + 1] |= ((x.y >> sh) & 0xffffu) << 16;
+                        v[4 * q + 2] |= ((x.z >> sh) & 0xffffu) << 16;
+                        v[4 * q + 3] |= ((x.w >> sh) & 0xffffu) << 16;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                Hrow[i] = v[i];
+                Frow[i] = v[K + i];
+            }
+        }
+
+        const uint8_t *cs = cc + p.coff[cj];
+        uint32_t *fl = wp.flags + (size_t)task * wp.win_task_stride + (size_t)lig * NW;
+        const int ncols = we - (int)ws + 1;  // <= wp.wmax by construction
+        // lane l-1's last row of column ws-1 is lane l's diagonal at column ws
+        uint32_t h_last = Hrow[K - 1], e_out = 0, h_up_prev = 0;
+        // the groups of a warp hold different windows: the trip count must be warp-uniform for the shuffles
+        const int nsteps = __reduce_max_sync(FULL, ncols > 0 ? ncols + G - 1 : 0);
+
+        for (int step = 0; step < nsteps; ++step) {
+            uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G);
+            uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G);
+            if (lig == 0) {
+                h_in = 0;
+                e_in = 0;
+            }
+            const int jw = step - lig;  // window-relative column
+            if (jw >= 0 && jw < ncols) {
+                const uint4 *tp = tab + (size_t)cs[ws + jw] * (K4 * G) + lig;
+                uint32_t diag = h_up_prev;
+                uint32_t E = e_in;
+                uint32_t words[NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) words[w] = 0;
+#pragma unroll
+                for (int i4 = 0; i4 < K4; ++i4) {
+                    const uint4 w4 = tp[i4 * G];
+                    const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i4 * 4 + q;
+                        if (i < K) {
+                            const uint32_t Fi = Frow[i];
+                            uint32_t x = O::max3(E, Fi, go_s) - go_s;
+                            uint32_t H = O::addmax(diag, wv[q], x);
+                            diag = Hrow[i];
+                            uint32_t Hg = H + go_s;
+                            uint32_t nve = O::min2(Hg - E, one_s);    // 0 where E == H   (UP)
+                            uint32_t nhe = O::min2(Hg - Fi, one_s);   // 0 where F == H   (LEFT)
+                            uint32_t E2 = O::addmax(E, neg_ge, H);
+                            uint32_t F2 = O::addmax(Fi, neg_ge, H);
+                            uint32_t xv = O::min2(E2 - H, one_s);     // 1 where next-row E extends (UP_EXT)
+                            uint32_t xh = O::min2(F2 - H, one_s);     // 1 where next-col F extends (LEFT_EXT)
+                            uint32_t ns = O::min2(H, one_s);          // 0 where H == 0   (STOP)
+                            uint32_t code = c21 + 2u * xv + 8u * xh - nve - 4u * nhe - 16u * ns;
+                            words[i / 3] += code << (5 * (i % 3));
+                            E = E2;
+                            Frow[i] = F2;
+                            Hrow[i] = H;
+                        }
+                    }
+                }
+                h_last = Hrow[K - 1];
+                e_out = E;
+                if (valid) {
+#pragma unroll
+                    for (int w = 0; w < NW; w += 4)
+                        *reinterpret_cast<uint4 *>(fl + (size_t)jw * (G * NW) + w) =
+                            make_uint4(words[w], words[w + 1], words[w + 2], words[w + 3]);
+                }
+            }
+            h_up_prev = h_in;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// walk over the window flags
+// ---------------------------------------------------------------------------------------------
+struct TraceWinParams {
+    TraceParams t;               // outputs, lengths, hazard list (t.flags / t.flag_base / t.task_stride unused)
+    const uint32_t *items;
+    const uint32_t *n_items;
+    const uint32_t *wflags;
+    uint64_t win_task_stride;
+    int cb_log2;
+    uint32_t slack;
+};
+
+__global__ void sw_traceback_win_kernel(const TraceWinParams tw) {
+    const TraceParams &t = tw.t;
+    const uint32_t pslot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pslot >= *tw.n_items) return;
+    const uint32_t gid = tw.items[pslot];
+    if (gid == 0xffffffffu) return;
+    const uint32_t seq = gid / t.n_cseq, cj = gid % t.n_cseq;
+    const AlignEnd e = t.ends[gid];
+    const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
+    const uint32_t m = t.coff[cj + 1] - t.coff[cj];
+    const uint32_t ws = win_start(e.r_end, e.c_end, tw.slack, tw.cb_log2);
+    const uint32_t half = pslot & 1u;
+    const uint32_t *fl = tw.wflags + (size_t)(pslot >> 1) * tw.win_task_stride;
+    const int G = t.G, K = t.K, NW = t.NW;
+    auto cell = [&](uint32_t r, uint32_t c) -> uint32_t {
+        uint32_t lane = r / K, kk = r % K;
+        uint32_t w = fl[((size_t)(c - ws) * G + lane) * NW + kk / 3];
+        return (w >> (16 * half + 5 * (kk % 3))) & 31u;
+    };
+
+    const uint32_t k = gid - t.chunk_first * t.n_cseq;  // chunk-local pair index (CIGAR scratch slot)
+    CigarBack cg;
+    cg.init(t.cig_scratch + (size_t)k * t.cig_cap, t.cig_cap);
+    const uint32_t OP_UP = t.invert ? 1u /*I*/ : 2u /*D*/, OP_LEFT = t.invert ? 2u : 1u;
+
+    uint32_t r = e.r_end + 1, c = e.c_end + 1;
+    const uint32_t r_end1 = r, c_end1 = c;
+    cg.push(4u, t.invert ? (n - r_end1) : (m - c_end1));
+    uint32_t cur = cell(e.r_end, e.c_end);
+    int op = 0;  // 0 none, 1 D(up), 2 I(left), 3 M
+    bool hz = false;
+    while (!(cur & 16u) && r > 0 && c > 0) {
+        if ((cur & 1u) && (cur & 4u)) hz = true;
+        if (op == 1 && (cur & 2u)) {
+            r -= 1;
+        } else if (op == 2 && (cur & 8u)) {
+            c -= 1;
+        } else if (cur & 1u) {
+            op = 1;
+            r -= 1;
+        } else if (cur & 4u) {
+            op = 2;
+            c -= 1;
+        } else {
+            op = 3;
+            r -= 1;
+            c -= 1;
+        }
+        cg.push(op == 1 ? OP_UP : (op == 2 ? OP_LEFT : 0u), 1);
+        if (r == 0 || c == 0) break;       // zoe reads cell(max(r-1,0), max(c-1,0)) and then leaves the loop
+        if (c - 1 < ws) {                  // the walk left its window: hand the pair to the literal kernel
+            hz = true;
+            atomicAdd(&t.counters[10], 1ULL);
+            break;
+        }
+        cur = cell(r - 1, c - 1);
+    }
+    cg.push(4u, t.invert ? r : c);  // leading soft clip
+    cg.flush();
+
+    if (hz) {
+        unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
+        t.hazard_list[slot] = gid;
+        t.hazard[gid] = 1;
+        return;  // the exact kernel rewrites everything for this pair
+    }
+    if (cg.overflow) atomicAdd(&t.counters[6], 1ULL);
+    t.cig_count[gid] = cg.n;
+    if (t.invert) {  // ref_range <-> query_range (output.rs:418-419)
+        t.ref_start[gid] = c;
+        t.ref_end[gid] = c_end1;
+        t.query_start[gid] = r;
+        t.query_end[gid] = r_end1;
+    } else {
+        t.ref_start[gid] = r;
+        t.ref_end[gid] = r_end1;
+        t.query_start[gid] = c;
+        t.query_end[gid] = c_end1;
+    }
+}
+
+}  // namespace zoe_cuda
