@@ -329,16 +329,16 @@ def main():
     in_bytes = float(h_buf.nbytes + h_offs.nbytes + n * n_prof * 4)
     if mode == "align":  # one flag byte-ish per cell: 32 B per lane per column for 3x19 rows x 2 sequences
         in_bytes += float(prof.align_flag_bytes(n, 150))
-    traffic = None
+    traffic, traffic_source = None, None
     try:  # measured DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"cfg{args.config}/{mode}")
         if tr and args.n is None:
-            traffic = {"bytes": tr["dram_read_bytes"] + tr["dram_write_bytes"], "source": tr["source"]}
+            traffic, traffic_source = tr["dram_read_bytes"] + tr["dram_write_bytes"], tr["source"]
     except Exception:
         pass
     roofline = {
         "bound": "alu", "achieved": kernel_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
-        "traffic": traffic,
+        "traffic": traffic, "traffic_source": traffic_source,
         "note": ("integer max-plus (DPX on the ALU pipe) bound, not hbm/tensor: peak = live-measured "
                  "VIADDMNMX.S16x2 issue rate (%.0f G lane-instr/s) / %.2f instr per cell (the score recurrence; the "
                  "align fill kernel needs 4.75 more ALU instr per cell for its 5 direction bits); kernel = %s, "

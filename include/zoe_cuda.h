@@ -112,6 +112,16 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
                             uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
                             uint64_t cigar_cap, uint8_t *hazard);
 
+/* Tuning of the align pipeline (results never depend on it).
+ *   mode            0 = automatic, 1 = direction bits for the full matrix (what zoe's sw_simd_align stores,
+ *                   src/alignment/sw/striped.rs:446-598), 2 = checkpointed window: a score-rate scan parks the
+ *                   DP column every 2^checkpoint_log2 columns, the direction bits are recomputed only for the
+ *                   window the traceback can reach
+ *   checkpoint_log2 2..16 (default 7: 128 columns)
+ *   slack           columns kept left of the shortest possible walk (default 16); a walk that needs more
+ *                   is redone by the literal kernel and counted in zoe_cuda_stats.window_fallback */
+int zoe_cuda_set_align_options(zoe_cuda_ctx *ctx, int mode, int checkpoint_log2, int slack);
+
 /* ---- measurement hooks (not part of the zoe-facing surface) ---- */
 
 /* Device-resident variant of zoe_cuda_sw_score_batch for kernel-only timing: upload once with
@@ -132,6 +142,8 @@ typedef struct {
     uint64_t pairs, cells;
     uint64_t tier8, tier16, tier32, overflowed, unmapped;
     uint64_t rerun_wide, hazard;
+    uint64_t window_fallback; /* pairs whose walk left its checkpoint window (re-done by the literal kernel) */
+    uint64_t window_redo;     /* pairs whose best cell recurs in a later column (re-done with full-matrix flags) */
 } zoe_cuda_stats;
 int zoe_cuda_last_stats(const zoe_cuda_ctx *ctx, zoe_cuda_stats *out);
 

@@ -20,11 +20,14 @@ def osc(wm, go, ge):
     return O.Scoring(wm.weights, wm.mapping.index_map, go, ge)
 
 
-def check_align(targets, seqs, wm, go=-10, ge=-1, profiled_is_query=False, lanes=(32, 16, 8), expect_hazard=None):
+def check_align(targets, seqs, wm, go=-10, ge=-1, profiled_is_query=False, lanes=(32, 16, 8), expect_hazard=None,
+                align_options=None):
     """Compare every (seq, target) pair with ProfileSets::sw_align_from_i8 of the oracle."""
     targets = [bytes(t) for t in targets]
     seqs = [bytes(s) for s in seqs]
     prof = CudaProfiles(targets, wm, go, ge, lanes=lanes, profiled_is_query=profiled_is_query)
+    if align_options is not None:
+        prof.set_align_options(*align_options)
     src = SeqSrc.Reference(seqs) if profiled_is_query else SeqSrc.Query(seqs)
     got = prof.sw_align_batch(src)
     stats = prof.last_stats()
@@ -162,4 +165,82 @@ def test_align_edge_cases():
     # scores beyond the packed 16-bit range: exact 32-bit score + literal kernel (i32 tier)
     w = WeightMatrix.new(DNA_PROFILE_MAP, 127, -5, b"N")
     stats = check_align([b"A" * 600], [b"A" * 600, b"A" * 300, b"A" * 100 + b"C" + b"A" * 100], w)
+    assert stats["tier32"] == 1 and stats["rerun_wide"] >= 1
+
+
+# ---- the checkpointed-window pipeline (sw_align_win.cuh) must give the same answers as the full-matrix one ----
+WINDOW = CudaProfiles.ALIGN_WINDOW
+
+
+def _related_seqs(rng, targets, n, lo=4, hi=150, alphabet=b"ACGT"):
+    seqs = []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi))
+        s = synth.random_dna(rng, L)
+        if L > 24:
+            t = targets[int(rng.integers(0, len(targets)))]
+            k = min(L - 4, len(t) - 2, 120)
+            st = int(rng.integers(0, len(t) - k + 1))
+            frag = synth._mutate(rng, t[st:st + k], 0.06, 0.05, 0.05, np.frombuffer(alphabet, dtype=np.uint8))
+            k2 = min(len(frag), L - 2)
+            s[2:2 + k2] = frag[:k2]
+        seqs.append(s)
+    return seqs
+
+
+@pytest.mark.parametrize("cb_log2,slack", [(2, 1), (3, 2), (4, 8), (5, 16), (7, 16)])
+def test_window_pipeline_random_pairs_vs_oracle(cb_log2, slack):
+    rng = np.random.default_rng(101 + cb_log2)
+    fallbacks = 0
+    for (ma, mi, go, ge) in [(2, -5, -10, -1), (4, -2, -3, -1), (1, -1, -4, -2), (3, -1, -4, -1), (1, -1, -1, -1),
+                             (5, -4, -2, 0)]:
+        wm = WeightMatrix.new_dna_matrix(ma, mi, b"N")
+        targets = [synth.random_dna(rng, int(L)) for L in (37, 300, 64, 513)]
+        seqs = _related_seqs(rng, targets, 70)
+        stats = check_align(targets, seqs, wm, go, ge, align_options=(WINDOW, cb_log2, slack))
+        fallbacks += stats["window_fallback"]
+    if slack <= 2:
+        assert fallbacks > 0  # walks longer than the slack were handed to the literal kernel
+
+
+def test_window_pipeline_profiled_is_query_and_lane_presets():
+    rng = np.random.default_rng(131)
+    wm = WeightMatrix.new_dna_matrix(4, -2, b"N")
+    for lanes in [(16, 8, 4), (32, 16, 8), (64, 32, 16)]:
+        targets = [synth.random_dna(rng, int(L)) for L in (250, 90)]
+        seqs = _related_seqs(rng, targets, 50, lo=10, hi=130, alphabet=b"AC")
+        check_align(targets, seqs, wm, -3, -1, profiled_is_query=True, lanes=lanes, align_options=(WINDOW, 4, 6))
+
+
+def test_window_pipeline_config3_equals_full_matrix_pipeline():
+    """5000 cfg-3 reads: the two pipelines must agree on every output array, CIGAR words included."""
+    targets, reads = synth.config3(ROOT, n_reads=5000)
+    buf, offs = synth.fixed_len_batch(reads)
+    outs = []
+    for mode in (CudaProfiles.ALIGN_FULL, CudaProfiles.ALIGN_WINDOW):
+        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], W25, -10, -1)
+        prof.set_align_options(mode, 7, 16)
+        outs.append(prof.align_arrays(buf, offs))
+        st = prof.last_stats()
+        prof.close()
+    a, b = outs
+    n_words = int(a["cigar_off"][-1])
+    assert n_words == int(b["cigar_off"][-1]) and n_words > 5000
+    for k in ("score", "status", "tier", "ref_start", "ref_end", "query_start", "query_end", "cigar_off"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["cigar"][:n_words], b["cigar"][:n_words])
+    assert st["window_fallback"] < 50  # the default slack covers all but the rare long-gap reads
+
+
+def test_window_pipeline_config3_sample_vs_oracle():
+    targets, reads = synth.config3(ROOT, n_reads=300, seed=77)
+    check_align(targets, list(reads), W25, align_options=(WINDOW, 7, 16))
+
+
+def test_window_pipeline_protein_and_overflow():
+    targets, q = synth.config5(n_queries=30)
+    check_align(targets, list(q), BLOSUM_62, align_options=(WINDOW, 5, 12))
+    w = WeightMatrix.new(DNA_PROFILE_MAP, 127, -5, b"N")
+    stats = check_align([b"A" * 600], [b"A" * 600, b"A" * 300, b"A" * 100 + b"C" + b"A" * 100], w,
+                        align_options=(WINDOW, 6, 8))
     assert stats["tier32"] == 1 and stats["rerun_wide"] >= 1

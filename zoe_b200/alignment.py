@@ -187,6 +187,12 @@ class CudaProfiles:
     def new_with_w512(cls, targets, matrix, gap_open, gap_extend, **kw):
         return cls(targets, matrix, gap_open, gap_extend, lanes=(64, 32, 16), **kw)
 
+    ALIGN_AUTO, ALIGN_FULL, ALIGN_WINDOW = 0, 1, 2
+
+    def set_align_options(self, mode: int = 0, checkpoint_log2: int = 7, slack: int = 16):
+        """Tuning of the align pipeline (never changes results): see ``zoe_cuda_set_align_options``."""
+        self._check(self._lib.zoe_cuda_set_align_options(self._h, mode, checkpoint_log2, slack))
+
     def _check(self, rc: int):
         if rc == 0:
             return

@@ -39,7 +39,9 @@ struct AlignEnd {      // per pair, written by the fill kernel
     int32_t best;      // exact best score; -1 = needs the 32-bit kernel
     uint32_t r_end;    // 0-based row (streamed index) of the best cell
     uint32_t c_end;    // 0-based column (profiled index) of the best cell
+    uint32_t aux;      // windowed pipeline only (sw_align_win.cuh): window start, or kAmbiguousEnd
 };
+constexpr uint32_t kAmbiguousEnd = 0xffffffffu;
 
 struct AlignParams {
     ScoreParams s;               // sequences, tables, scoring (s.best unused)
@@ -260,21 +262,19 @@ __global__ void __launch_bounds__(512) sw_align_fill_kernel(const AlignParams ap
                 key_hi = o > key_hi ? o : key_hi;
             }
             if (lig == 0 && valid) {
-                if (id_lo != 0xffffffffu) {
-                    AlignEnd e;
+                if (id_lo != 0xffffffffu) {  // (aux belongs to the windowed pipeline: left alone)
+                    AlignEnd *e = ap.ends + (size_t)id_lo * p.n_cseq + cj;
                     int b = (int)(key_lo >> 40);
-                    e.best = (PACKED && b >= p.ovf_thresh) ? -1 : b;
-                    e.r_end = 0xFFFFFu - (uint32_t)((key_lo >> 20) & 0xFFFFFu);
-                    e.c_end = 0xFFFFFu - (uint32_t)(key_lo & 0xFFFFFu);
-                    ap.ends[(size_t)id_lo * p.n_cseq + cj] = e;
+                    e->best = (PACKED && b >= p.ovf_thresh) ? -1 : b;
+                    e->r_end = 0xFFFFFu - (uint32_t)((key_lo >> 20) & 0xFFFFFu);
+                    e->c_end = 0xFFFFFu - (uint32_t)(key_lo & 0xFFFFFu);
                 }
                 if (PACKED && id_hi != 0xffffffffu) {
-                    AlignEnd e;
+                    AlignEnd *e = ap.ends + (size_t)id_hi * p.n_cseq + cj;
                     int b = (int)(key_hi >> 40);
-                    e.best = (b >= p.ovf_thresh) ? -1 : b;
-                    e.r_end = 0xFFFFFu - (uint32_t)((key_hi >> 20) & 0xFFFFFu);
-                    e.c_end = 0xFFFFFu - (uint32_t)(key_hi & 0xFFFFFu);
-                    ap.ends[(size_t)id_hi * p.n_cseq + cj] = e;
+                    e->best = (b >= p.ovf_thresh) ? -1 : b;
+                    e->r_end = 0xFFFFFu - (uint32_t)((key_hi >> 20) & 0xFFFFFu);
+                    e->c_end = 0xFFFFFu - (uint32_t)(key_hi & 0xFFFFFu);
                 }
             }
         }
@@ -308,6 +308,7 @@ struct TraceParams {
     unsigned long long *counters;  // [5] exact-list length, [6] cigar overflow count, [8] packed overflows
     uint32_t *hazard_list;      // global pair ids that need the exact kernel
     int all_exact;              // gap_open == 0: every Some pair goes to the exact kernel
+    int only_ambiguous;         // seq_ids mode: redo only the pairs the windowed pipeline marked kAmbiguousEnd
 };
 
 // CIGAR builder writing backwards (the walk runs end -> start, the CIGAR is start -> end).
@@ -359,6 +360,7 @@ __global__ void sw_traceback_kernel(const TraceParams t) {
     const uint32_t seq = t.seq_ids ? t.seq_ids[seq_local] : t.chunk_first + seq_local;
     const size_t gid = (size_t)seq * t.n_cseq + cj;
     const AlignEnd e = t.ends[gid];
+    if (t.only_ambiguous && e.aux != kAmbiguousEnd) return;
     const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
     const uint32_t m = t.coff[cj + 1] - t.coff[cj];
     t.hazard[gid] = 0;
@@ -399,8 +401,8 @@ __global__ void sw_traceback_kernel(const TraceParams t) {
         return (w >> (16 * half + 5 * (kk % 3))) & 31u;
     };
 
-    CigarBack cg;
-    cg.init(t.cig_scratch + (size_t)k * t.cig_cap, t.cig_cap);
+    CigarBack cg;  // scratch rows are indexed by the chunk-local pair id (what cigar_gather_kernel expects)
+    cg.init(t.cig_scratch + (size_t)(t.seq_ids ? gid - (size_t)t.chunk_first * t.n_cseq : k) * t.cig_cap, t.cig_cap);
     // letters: zoe's walk emits D for an UP move (consumes a streamed residue) and I for a LEFT move;
     // invert() swaps them.
     const uint32_t OP_UP = t.invert ? 1u /*I*/ : 2u /*D*/, OP_LEFT = t.invert ? 2u : 1u;

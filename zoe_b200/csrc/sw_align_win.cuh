@@ -7,40 +7,50 @@
 // work when a 150-nt read is aligned against a 1.7-kb segment.  Here:
 //
 //   pass A  sw_align_scan_kernel     the score recurrence (4.5 ALU instr per packed cell pair, no direction
-//                                    bits) over all columns; it tracks the best cell exactly as zoe does (max H,
-//                                    then min r, then min c -- striped.rs:555-583) and parks the column state
-//                                    (H and the along-row gap state of every row) every CB columns.
+//                                    bits) over all columns.  Per lane it keeps, branch-free in packed 16-bit
+//                                    halves, the running maximum and the first / last column pair in which the
+//                                    maximum was reached, and it parks the systolic state every CB columns.
 //   pairing win_classify / win_bucket_scan / win_scatter: a counting sort of the mapped pairs by
 //                                    (profiled sequence, checkpoint block), so two pairs that restart from
 //                                    the same column share one packed s16x2 task.
 //   pass B  sw_align_winfill_kernel  restarts from the checkpoint at or before c_end - (r_end + 1 + slack),
-//                                    recomputes that window with the five direction bits per cell.  The DP
-//                                    values inside the window are bit-identical to the full matrix because
-//                                    the restart state is the full matrix's own column.
+//                                    recomputes that window with the five direction bits per cell, and pins the
+//                                    best cell down to zoe's (max H, min r, min c) -- striped.rs:555-583 -- inside
+//                                    the one column pair pass A pointed at.  The DP values inside the window are
+//                                    bit-identical to the full matrix because the restart state is the full
+//                                    matrix's own systolic state.
 //   walk    sw_traceback_win_kernel  zoe's priority walk over the window; a walk that reaches the left edge
 //                                    of its window (a gap longer than the slack) is handed to the literal
 //                                    kernel, like a tie hazard.
 //
-// Checkpoint layout per pass-A task and profiled sequence: ckpt[kb-1][i4][lane] = uint4, the lane's vector
-// (H[0..K), F[0..K)) in 16-byte pieces; kb = 1 .. (L-1)/CB is the state entering column kb*CB.
+// Which cell is "the" best cell?  zoe takes the smallest row, then the smallest column among the cells holding the
+// maximum.  Lanes own disjoint ascending row ranges, so the winner lies in the lowest lane that reaches the
+// maximum; inside that lane pass A knows the first column pair holding it.  If the same lane reaches the maximum
+// again in a later column pair (first != last) a smaller row could hide there: such pairs are marked
+// kAmbiguousEnd and redone by the full-matrix pipeline (sw_align.cuh).  [cfg 3: a fraction of the 5 % random reads]
+//
+// Checkpoint layout per pass-A task and profiled sequence: ckpt[kb-1][w][lane] = one 32-bit word of the lane's
+// vector (H[0..K), F[0..K), E leaving the last row, diagonal for the next column); kb = 1 .. (L-1)/CB
+// is the systolic state before step kb*CB, where lane l is about to compute column kb*CB - l (CB >= G).
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "sw_align.cuh"
 
 namespace zoe_cuda {
 
-__host__ __device__ inline int ckpt_vec4_per_lane(int K) { return (2 * K + 3) / 4; }
+__host__ __device__ inline int ckpt_words_per_lane(int K) { return 2 * K + 2; }
 
 struct WinParams {
     ScoreParams s;               // sequences, tables, scoring (s.best unused; s.n_rseq = sequences in the chunk)
     AlignEnd *ends;              // [n_rseq_total * n_cseq]
     uint32_t chunk_first;        // first batch sequence of the chunk
     // checkpoints (pass A writes, pass B reads)
-    uint4 *ckpt;
-    const uint64_t *ckpt_base;   // [n_cseq] uint4 offset of each profiled sequence inside a task's region
-    uint64_t ckpt_task_stride;   // uint4 per pass-A task
+    uint32_t *ckpt;
+    const uint64_t *ckpt_base;   // [n_cseq] word offset of each profiled sequence inside a task's region
+    uint64_t ckpt_task_stride;   // words per pass-A task
     int cb_log2;                 // checkpoint spacing CB = 1 << cb_log2 columns
     uint32_t slack;              // extra columns kept left of the shortest possible walk
     // pairing
@@ -53,7 +63,17 @@ struct WinParams {
     uint32_t *flags;             // window flag words
     uint64_t win_task_stride;    // words per pass-B task = Wmax * G * NW
     uint32_t wmax;               // window capacity in columns
+    unsigned long long *counters; // [7] internal consistency failures
 };
+
+// Pass A leaves (winning lane, even step of the first column pair); the best cell is one of that lane's K rows in
+// columns (s - lane, s + 1 - lane).  Upper bounds of its row / column, used to size the window before pass B
+// pins the cell down.
+__device__ __forceinline__ void end_bounds(uint32_t lane, uint32_t s_even, int K, uint32_t n, uint32_t L, uint32_t &r_hi,
+                                           uint32_t &c_hi) {
+    r_hi = min(lane * (uint32_t)K + (uint32_t)K - 1u, n - 1u);
+    c_hi = min(s_even + 1u - lane, L - 1u);  // the lane was active in the pair, so s_even + 1 >= lane
+}
 
 __device__ __forceinline__ uint32_t win_start(uint32_t r_end, uint32_t c_end, uint32_t slack, int cb_log2) {
     const uint32_t need = r_end + 1 + slack;  // columns the walk may touch: #M <= r_end + 1, #I + 1 <= slack
@@ -64,12 +84,21 @@ __device__ __forceinline__ uint32_t win_start(uint32_t r_end, uint32_t c_end, ui
 // ---------------------------------------------------------------------------------------------
 // pass A: scores, end cells, checkpoints
 // ---------------------------------------------------------------------------------------------
+// Same register-resident systolic sweep as sw_score_kernel (ping-pong H sets, no register moves).  Three things
+// keep the per-step overhead off the ALU pipe, which bounds the kernel:
+//   * steps G-1 .. L-1 have every lane active, so the steady loop carries no per-lane activity predicates;
+//   * the best-cell bookkeeping (max H, then min r, then min c -- striped.rs:555-583) is tested once per two
+//     columns with a packed "any half >= running best" test and handled in a cold branch;
+//   * checkpoints are taken at a warp-uniform step boundary (the whole systolic state, skewed by lane), so the
+//     test is a uniform-datapath compare.
+// State parked before step s0 = kb*CB (s0 even, s0 >= G): lane l holds column s0-1-l in H[0], its along-row gap
+// state F, the E leaving its last row and the diagonal it received at step s0-1.
 template <int G, int K>
-__global__ void __launch_bounds__(512) sw_align_scan_kernel(const WinParams wp) {
+__global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const WinParams wp) {
     using O = Ops<true>;
     const ScoreParams &p = wp.s;
     constexpr int K4 = (K + 3) / 4;
-    constexpr int CK4 = (2 * K + 3) / 4;
+    constexpr int CKW = 2 * K + 2;  // checkpoint words per lane
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint8_t smem[];
 
@@ -85,13 +114,20 @@ __global__ void __launch_bounds__(512) sw_align_scan_kernel(const WinParams wp) 
     uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
     for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
     for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
-    if (p.cols_in_smem)
-        for (uint32_t i = tid; i < p.ccodes_bytes; i += blockDim.x) s_cc[i] = p.ccodes[i];
+    // the profiled sequences are always staged in shared memory here (the host only picks this pipeline when
+    // they fit), so the per-step column-code load is an LDS with a 32-bit address
+    for (uint32_t i = tid; i < p.ccodes_bytes; i += blockDim.x) s_cc[i] = p.ccodes[i];
     __syncthreads();
-    const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
+    const uint8_t *cc = s_cc;
 
-    const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+    uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
     const uint32_t cb_mask = (1u << wp.cb_log2) - 1u;
+    const bool lane0 = lig == 0;  // lane 0 receives zeros from "above"
+    const uint32_t one_s = O::splat(1);
+    // loop invariants the compiler would otherwise rematerialise inside the hot loop (S2R + address arithmetic);
+    // the table offset stays a 32-bit offset into the shared array so the loads remain LDS.128
+    uint32_t tab_lane_off = (uint32_t)group_in_block * (uint32_t)tab_bytes + (uint32_t)lig * 16u;
+    asm volatile("" : "+r"(go_s), "+r"(neg_ge), "+r"(tab_lane_off));
 
     const uint32_t total_groups = gridDim.x * groups_per_block;
     const uint32_t trips = (p.n_tasks + total_groups - 1) / total_groups;
@@ -140,134 +176,153 @@ __global__ void __launch_bounds__(512) sw_align_scan_kernel(const WinParams wp) 
         }
         __syncwarp();
 
-        uint4 *ck_task = wp.ckpt + (size_t)task * wp.ckpt_task_stride;
+        uint32_t *ck_task = wp.ckpt + (size_t)task * wp.ckpt_task_stride;
 
         for (uint32_t cj = 0; cj < p.n_cseq; ++cj) {
             const uint32_t c0 = p.coff[cj];
             const int L = (int)(p.coff[cj + 1] - c0);
             const uint8_t *cs = cc + c0;
-            uint4 *ck = ck_task + wp.ckpt_base[cj] + lig;
+            uint32_t *ck = ck_task + wp.ckpt_base[cj] + lig;
 
-            uint32_t Hrow[K], Frow[K];
+            uint32_t H[2][K], F[K];
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-                Hrow[i] = 0;
-                Frow[i] = 0;
+                H[0][i] = H[1][i] = 0;
+                F[i] = 0;
             }
             uint32_t h_last = 0, e_out = 0, h_up_prev = 0;
-            int bv_lo = 0, bv_hi = 0, bi_lo = 0, bi_hi = 0, bj_lo = 0, bj_hi = 0;
+            // branch-free best bookkeeping, all packed per 16-bit half: running maximum, and the first / last
+            // step pair (s >> 1) in which this lane's column maximum reached it
+            uint32_t bestp = 0, firstp = 0, lastp = 0;
+            uint32_t cm = 0;               // maximum of the column(s) since the last bookkeeping
             const int nsteps = L + G - 1;
 
-            for (int step = 0; step < nsteps; ++step) {
-                uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G);
-                uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G);
-                if (lig == 0) {
-                    h_in = 0;
-                    e_in = 0;
+            // one column of this lane: K rows, H read from set PO (column j-1), written to set PN
+            auto column = [&](auto parity, const int j, const uint32_t h_in, const uint32_t e_in) {
+                constexpr int PO = decltype(parity)::value, PN = 1 - PO;
+                const uint4 *tp = reinterpret_cast<const uint4 *>(smem + tab_lane_off + (uint32_t)cs[j] * (uint32_t)(K4 * G * 16));
+                uint32_t diag = h_up_prev, E = e_in, hp = 0;
+#pragma unroll
+                for (int i4 = 0; i4 < K4; ++i4) {
+                    const uint4 w4 = tp[i4 * G];
+                    const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i4 * 4 + q;
+                        if (i < K) {
+                            const uint32_t x = O::max3(E, F[i], go_s) - go_s;
+                            const uint32_t Hn = O::addmax(diag, wv[q], x);
+                            diag = H[PO][i];
+                            E = O::addmax(E, neg_ge, Hn);
+                            F[i] = O::addmax(F[i], neg_ge, Hn);
+                            H[PN][i] = Hn;
+                            if (i & 1)
+                                cm = O::max3(cm, Hn, hp);
+                            else
+                                hp = Hn;
+                        }
+                    }
                 }
-                const int j = step - lig;
+                if (K & 1) cm = O::max2(cm, hp);
+                h_last = H[PN][K - 1];
+                e_out = E;
+            };
+            using I0 = std::integral_constant<int, 0>;
+            using I1 = std::integral_constant<int, 1>;
+            // m - bestp and m - cm are >= 0 in both halves, so the plain 32-bit subtractions are exact (FMA pipe);
+            // the 0/1 halves are widened to 0xffff masks by a multiply (FMA pipe); 5 ALU instructions in all.
+            auto bookkeeping = [&](const uint32_t s_even) {
+                const uint32_t pp = (s_even >> 1) * 0x00010001u;
+                const uint32_t m = O::max2(cm, bestp);
+                const uint32_t inc = O::min2(m - bestp, one_s) * 0xffffu;            // halves that grew
+                const uint32_t ge = (one_s - O::min2(m - cm, one_s)) * 0xffffu;      // halves with cm >= bestp
+                firstp = (firstp & ~inc) | (pp & inc);
+                lastp = (lastp & ~ge) | (pp & ge);
+                bestp = m;
+                cm = 0;
+            };
+            auto generic_step = [&](auto parity, const int s) {
+                const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1, G), h_in = lane0 ? 0u : h_sh;
+                const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
+                const int j = s - lig;
                 if (j >= 0 && j < L) {
-                    const uint4 *tp = tab + (size_t)cs[j] * (K4 * G) + lig;
-                    uint32_t diag = h_up_prev;
-                    uint32_t E = e_in;
-                    uint32_t cm = 0, hprev = 0;
-#pragma unroll
-                    for (int i4 = 0; i4 < K4; ++i4) {
-                        const uint4 w4 = tp[i4 * G];
-                        const uint32_t wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int i = i4 * 4 + q;
-                            if (i < K) {
-                                uint32_t x = O::max3(E, Frow[i], go_s) - go_s;
-                                uint32_t H = O::addmax(diag, wv[q], x);
-                                diag = Hrow[i];
-                                E = O::addmax(E, neg_ge, H);
-                                Frow[i] = O::addmax(Frow[i], neg_ge, H);
-                                Hrow[i] = H;
-                                if (i & 1)
-                                    cm = O::max3(cm, H, hprev);
-                                else
-                                    hprev = H;
-                            }
-                        }
-                    }
-                    if (K & 1) cm = O::max2(cm, hprev);
-                    h_last = Hrow[K - 1];
-                    e_out = E;
-
-                    // ---- best-cell bookkeeping: (max H, min r, min c), striped.rs:555-583 ----
-                    const int cm_lo = (int)(int16_t)(cm & 0xffff);
-                    const int cm_hi = (int)(int16_t)(cm >> 16);
-                    if (cm_lo > 0 && cm_lo >= bv_lo) {
-                        int irow = K;
-#pragma unroll
-                        for (int i = K - 1; i >= 0; --i)
-                            if ((int)(int16_t)(Hrow[i] & 0xffff) == cm_lo) irow = i;
-                        if (cm_lo > bv_lo || irow < bi_lo) {
-                            bv_lo = cm_lo;
-                            bi_lo = irow;
-                            bj_lo = j;
-                        }
-                    }
-                    if (cm_hi > 0 && cm_hi >= bv_hi) {
-                        int irow = K;
-#pragma unroll
-                        for (int i = K - 1; i >= 0; --i)
-                            if ((int)(int16_t)(Hrow[i] >> 16) == cm_hi) irow = i;
-                        if (cm_hi > bv_hi || irow < bi_hi) {
-                            bv_hi = cm_hi;
-                            bi_hi = irow;
-                            bj_hi = j;
-                        }
-                    }
-
-                    // ---- checkpoint: the state entering column j + 1 when that is a block boundary ----
-                    if ((((uint32_t)(j + 1)) & cb_mask) == 0 && j + 1 < L && valid) {
-                        uint4 *dst = ck + (size_t)((((uint32_t)(j + 1)) >> wp.cb_log2) - 1) * (CK4 * G);
-                        uint32_t v[CK4 * 4];
-#pragma unroll
-                        for (int i = 0; i < CK4 * 4; ++i) v[i] = 0;
-#pragma unroll
-                        for (int i = 0; i < K; ++i) {
-                            v[i] = Hrow[i];
-                            v[K + i] = Frow[i];
-                        }
-#pragma unroll
-                        for (int q = 0; q < CK4; ++q) dst[q * G] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
+                    column(parity, j, h_in, e_in);
+                    bookkeeping((uint32_t)s & ~1u);
                 }
                 h_up_prev = h_in;
+            };
+            auto checkpoint = [&](const int s) {  // the state before step s (s even: the last column is in set 0)
+                // 32-bit stores on purpose: a 128-bit store would pin H/F to aligned register quads in the hot loop
+                uint32_t *dst = ck + (size_t)(((uint32_t)s >> wp.cb_log2) - 1) * (CKW * G);
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    dst[i * G] = H[0][i];
+                    dst[(K + i) * G] = F[i];
+                }
+                dst[(2 * K) * G] = e_out;
+                dst[(2 * K + 1) * G] = h_up_prev;
+            };
+
+            int s = 0;
+            const int s_steady = min(G, nsteps);  // G is even and >= the first step with every lane active
+            for (; s < s_steady; ++s) {
+                if (s & 1)
+                    generic_step(I1{}, s);
+                else
+                    generic_step(I0{}, s);
+            }
+            for (; s + 1 < L; s += 2) {  // steps s and s+1: every lane has a column
+                if ((((uint32_t)s) & cb_mask) == 0 && valid) checkpoint(s);
+                {
+                    const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1, G), h_in = lane0 ? 0u : h_sh;
+                    const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
+                    column(I0{}, s - lig, h_in, e_in);
+                    h_up_prev = h_in;
+                }
+                {
+                    const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1, G), h_in = lane0 ? 0u : h_sh;
+                    const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
+                    column(I1{}, s + 1 - lig, h_in, e_in);
+                    h_up_prev = h_in;
+                }
+                bookkeeping((uint32_t)s);
+            }
+            for (; s < nsteps; ++s) {
+                if ((((uint32_t)s) & cb_mask) == 0 && s >= G && s < L && valid) checkpoint(s);
+                if (s & 1)
+                    generic_step(I1{}, s);
+                else
+                    generic_step(I0{}, s);
             }
 
-            unsigned long long key_lo = ((unsigned long long)(uint32_t)bv_lo << 40) |
-                                        ((unsigned long long)(0xFFFFFu - (uint32_t)(lig * K + bi_lo)) << 20) |
-                                        (unsigned long long)(0xFFFFFu - (uint32_t)bj_lo);
-            unsigned long long key_hi = ((unsigned long long)(uint32_t)bv_hi << 40) |
-                                        ((unsigned long long)(0xFFFFFu - (uint32_t)(lig * K + bi_hi)) << 20) |
-                                        (unsigned long long)(0xFFFFFu - (uint32_t)bj_hi);
+            // ---- the lowest lane holding the group's maximum wins (smallest rows); fetch its first / last pair ----
+            uint32_t key_lo = ((bestp & 0xffffu) << 8) | (uint32_t)(G - 1 - lig);
+            uint32_t key_hi = ((bestp >> 16) << 8) | (uint32_t)(G - 1 - lig);
 #pragma unroll
             for (int d = G / 2; d >= 1; d >>= 1) {
-                unsigned long long o = __shfl_xor_sync(FULL, key_lo, d, G);
-                key_lo = o > key_lo ? o : key_lo;
-                o = __shfl_xor_sync(FULL, key_hi, d, G);
-                key_hi = o > key_hi ? o : key_hi;
+                key_lo = max(key_lo, __shfl_xor_sync(FULL, key_lo, d, G));
+                key_hi = max(key_hi, __shfl_xor_sync(FULL, key_hi, d, G));
             }
+            const int wl_lo = G - 1 - (int)(key_lo & 0xffu), wl_hi = G - 1 - (int)(key_hi & 0xffu);
+            const uint32_t f_lo = __shfl_sync(FULL, firstp, wl_lo, G) & 0xffffu, l_lo = __shfl_sync(FULL, lastp, wl_lo, G) & 0xffffu;
+            const uint32_t f_hi = __shfl_sync(FULL, firstp, wl_hi, G) >> 16, l_hi = __shfl_sync(FULL, lastp, wl_hi, G) >> 16;
             if (lig == 0 && valid) {
                 if (id_lo != 0xffffffffu) {
                     AlignEnd e;
-                    int b = (int)(key_lo >> 40);
+                    const int b = (int)(key_lo >> 8);
                     e.best = (b >= p.ovf_thresh) ? -1 : b;
-                    e.r_end = 0xFFFFFu - (uint32_t)((key_lo >> 20) & 0xFFFFFu);
-                    e.c_end = 0xFFFFFu - (uint32_t)(key_lo & 0xFFFFFu);
+                    e.r_end = (uint32_t)wl_lo;   // winning lane, refined to a row by pass B
+                    e.c_end = 2u * f_lo;         // even step of the pair: columns (s - lane, s + 1 - lane)
+                    e.aux = (f_lo != l_lo) ? kAmbiguousEnd : 0u;
                     wp.ends[(size_t)id_lo * p.n_cseq + cj] = e;
                 }
                 if (id_hi != 0xffffffffu) {
                     AlignEnd e;
-                    int b = (int)(key_hi >> 40);
+                    const int b = (int)(key_hi >> 8);
                     e.best = (b >= p.ovf_thresh) ? -1 : b;
-                    e.r_end = 0xFFFFFu - (uint32_t)((key_hi >> 20) & 0xFFFFFu);
-                    e.c_end = 0xFFFFFu - (uint32_t)(key_hi & 0xFFFFFu);
+                    e.r_end = (uint32_t)wl_hi;
+                    e.c_end = 2u * f_hi;
+                    e.aux = (f_hi != l_hi) ? kAmbiguousEnd : 0u;
                     wp.ends[(size_t)id_hi * p.n_cseq + cj] = e;
                 }
             }
@@ -279,33 +334,30 @@ __global__ void __launch_bounds__(512) sw_align_scan_kernel(const WinParams wp) 
 // pairing: classify every pair of the chunk, counting-sort the mapped ones by (profiled, block)
 // ---------------------------------------------------------------------------------------------
 struct ClassifyParams {
-    const AlignEnd *ends;
+    AlignEnd *ends;
     const uint64_t *roff;
+    const uint32_t *coff;
     uint32_t n_cseq, chunk_first, n_slots;
+    int K;
     int cb_log2;
     uint32_t slack, nblk;
     int all_exact;
     uint32_t *hist;
+    uint8_t *redo_flag;            // [n_slots] 1 = the sequence has an ambiguous pair: full-matrix pipeline
     int32_t *best_arr;
     uint32_t *score;
     uint8_t *status, *tier, *hazard;
     uint32_t *ref_start, *ref_end, *query_start, *query_end, *cig_count;
-    unsigned long long *counters;  // [5] exact-list length, [8] packed overflows
+    unsigned long long *counters;  // [5] exact-list length, [8] packed overflows, [11] ambiguous pairs
     uint32_t *hazard_list;
 };
-
-// Returns the bucket key of a pair that needs pass B, or 0xffffffff.
-__device__ __forceinline__ uint32_t win_key(const AlignEnd &e, uint32_t cj, uint32_t n, int all_exact, uint32_t slack,
-                                            int cb_log2, uint32_t nblk) {
-    if (e.best <= 0 || n == 0 || all_exact) return 0xffffffffu;
-    return cj * nblk + (win_start(e.r_end, e.c_end, slack, cb_log2) >> cb_log2);
-}
 
 __global__ void win_classify_kernel(const ClassifyParams t) {
     const uint32_t pairs = t.n_slots * t.n_cseq;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= pairs) return;
-    const uint32_t seq = t.chunk_first + k / t.n_cseq, cj = k % t.n_cseq;
+    const uint32_t seq_local = k / t.n_cseq, cj = k % t.n_cseq;
+    const uint32_t seq = t.chunk_first + seq_local;
     const size_t gid = (size_t)seq * t.n_cseq + cj;
     const AlignEnd e = t.ends[gid];
     const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
@@ -318,6 +370,7 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         atomicAdd(&t.counters[8], 1ULL);
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
         t.hazard_list[slot] = (uint32_t)gid;
+        t.ends[gid].aux = kAmbiguousEnd - 1u;  // not bucketed
         return;
     }
     if (e.best == 0 || n == 0) {
@@ -325,6 +378,7 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         t.status[gid] = 2;  // Unmapped
         t.tier[gid] = 8;
         t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
+        t.ends[gid].aux = kAmbiguousEnd - 1u;
         return;
     }
     t.score[gid] = (uint32_t)e.best;
@@ -334,9 +388,28 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
         t.hazard_list[slot] = (uint32_t)gid;
         t.hazard[gid] = 1;
+        t.ends[gid].aux = kAmbiguousEnd - 1u;
         return;
     }
-    atomicAdd(&t.hist[win_key(e, cj, n, 0, t.slack, t.cb_log2, t.nblk)], 1u);
+    if (e.aux == kAmbiguousEnd) {  // the maximum recurs later in the winning lane: redo with the full matrix
+        t.redo_flag[seq_local] = 1;
+        atomicAdd(&t.counters[11], 1ULL);
+        return;
+    }
+    uint32_t r_hi, c_hi;
+    end_bounds(e.r_end, e.c_end, t.K, n, t.coff[cj + 1] - t.coff[cj], r_hi, c_hi);
+    const uint32_t ws = win_start(r_hi, c_hi, t.slack, t.cb_log2);
+    t.ends[gid].aux = ws;
+    atomicAdd(&t.hist[cj * t.nblk + (ws >> t.cb_log2)], 1u);
+}
+
+// Sequences flagged by win_classify_kernel -> list (chunk order is not preserved; results do not depend on it).
+__global__ void win_collect_redo_kernel(const uint8_t *redo_flag, uint32_t chunk_first, uint32_t n_slots, uint32_t *ids,
+                                        unsigned long long *counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots || !redo_flag[i]) return;
+    const unsigned long long slot = atomicAdd(&counters[12], 1ULL);
+    ids[slot] = chunk_first + i;
 }
 
 // Single-block exclusive scan of the bucket sizes rounded up to even (a pass-B task holds two pairs of ONE
@@ -389,10 +462,9 @@ __global__ void win_scatter_kernel(const ClassifyParams t, const uint32_t *bucke
     if (k >= pairs) return;
     const uint32_t seq = t.chunk_first + k / t.n_cseq, cj = k % t.n_cseq;
     const size_t gid = (size_t)seq * t.n_cseq + cj;
-    const AlignEnd e = t.ends[gid];
-    const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
-    const uint32_t key = win_key(e, cj, n, t.all_exact, t.slack, t.cb_log2, t.nblk);
-    if (key == 0xffffffffu) return;
+    const uint32_t ws = t.ends[gid].aux;
+    if (ws >= kAmbiguousEnd - 1u) return;  // unmapped / overflowed / literal-only / ambiguous
+    const uint32_t key = cj * t.nblk + (ws >> t.cb_log2);
     const uint32_t slot = bucket_start[key] + atomicAdd(&t.hist[key], 1u);
     items[slot] = (uint32_t)gid;
 }
@@ -405,7 +477,7 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
     using O = Ops<true>;
     const ScoreParams &p = wp.s;
     constexpr int K4 = (K + 3) / 4;
-    constexpr int CK4 = (2 * K + 3) / 4;
+    constexpr int CKW = 2 * K + 2;
     constexpr int NW = (((K + 2) / 3) + 3) & ~3;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint8_t smem[];
@@ -448,24 +520,38 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
         uint64_t off_lo = 0, off_hi = 0;
         int len_lo = 0, len_hi = 0;
         uint32_t seqA_lo = 0, seqA_hi = 0;  // chunk-relative sequence index (locates the checkpoint)
+        // where pass A saw the maximum: (winning lane, even step of the column pair), and its value
+        uint32_t ls_lo = 0xffffffffu, ls_hi = 0xffffffffu, fs_lo = 0, fs_hi = 0;
+        int best_lo = -1, best_hi = -1;
         if (g_lo != 0xffffffffu) {
             const uint32_t seq = g_lo / p.n_cseq;
             cj = g_lo % p.n_cseq;
             const AlignEnd e = wp.ends[g_lo];
-            ws = win_start(e.r_end, e.c_end, wp.slack, wp.cb_log2);
-            we = (int)e.c_end;
             off_lo = p.roff[seq];
             len_lo = (int)(p.roff[seq + 1] - off_lo);
+            uint32_t r_hi, c_hi;
+            end_bounds(e.r_end, e.c_end, K, (uint32_t)len_lo, p.coff[cj + 1] - p.coff[cj], r_hi, c_hi);
+            ws = e.aux;
+            we = (int)c_hi;
+            ls_lo = e.r_end;
+            fs_lo = e.c_end;
+            best_lo = e.best;
             seqA_lo = seq - wp.chunk_first;
         }
         if (g_hi != 0xffffffffu) {
             const uint32_t seq = g_hi / p.n_cseq;
             const AlignEnd e = wp.ends[g_hi];
-            we = max(we, (int)e.c_end);
             off_hi = p.roff[seq];
             len_hi = (int)(p.roff[seq + 1] - off_hi);
+            uint32_t r_hi, c_hi;
+            end_bounds(e.r_end, e.c_end, K, (uint32_t)len_hi, p.coff[cj + 1] - p.coff[cj], r_hi, c_hi);
+            we = max(we, (int)c_hi);
+            ls_hi = e.r_end;
+            fs_hi = e.c_end;
+            best_hi = e.best;
             seqA_hi = seq - wp.chunk_first;
         }
+        int bi_lo = K, bi_hi = K, bj_lo = 0, bj_hi = 0;  // best cell inside the pointed-at column pair
 
         __syncwarp();
         for (int i4 = 0; i4 < K4; ++i4) {
@@ -490,39 +576,28 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
         }
         __syncwarp();
 
-        // ---- restore the column state entering column ws ----
+        // ---- restore the systolic state before step ws (sw_align_scan_kernel's checkpoint layout) ----
         uint32_t Hrow[K], Frow[K];
+        uint32_t e_out = 0, h_up_prev = 0;
         {
-            uint32_t v[CK4 * 4];
+            uint32_t v[CKW];
 #pragma unroll
-            for (int i = 0; i < CK4 * 4; ++i) v[i] = 0;
+            for (int i = 0; i < CKW; ++i) v[i] = 0;
             if (ws > 0) {
                 const uint32_t kb = ws >> wp.cb_log2;
                 if (g_lo != 0xffffffffu) {
-                    const uint4 *src = wp.ckpt + (size_t)(seqA_lo >> 1) * wp.ckpt_task_stride + wp.ckpt_base[cj] +
-                                       (size_t)(kb - 1) * (CK4 * G) + lig;
+                    const uint32_t *src = wp.ckpt + (size_t)(seqA_lo >> 1) * wp.ckpt_task_stride + wp.ckpt_base[cj] +
+                                          (size_t)(kb - 1) * (CKW * G) + lig;
                     const int sh = (seqA_lo & 1) ? 16 : 0;
 #pragma unroll
-                    for (int q = 0; q < CK4; ++q) {
-                        const uint4 x = src[q * G];
-                        v[4 * q] |= (x.x >> sh) & 0xffffu;
-                        v[4 * q + 1] |= (x.y >> sh) & 0xffffu;
-                        v[4 * q + 2] |= (x.z >> sh) & 0xffffu;
-                        v[4 * q + 3] |= (x.w >> sh) & 0xffffu;
-                    }
+                    for (int i = 0; i < CKW; ++i) v[i] |= (src[i * G] >> sh) & 0xffffu;
                 }
                 if (g_hi != 0xffffffffu) {
-                    const uint4 *src = wp.ckpt + (size_t)(seqA_hi >> 1) * wp.ckpt_task_stride + wp.ckpt_base[cj] +
-                                       (size_t)(kb - 1) * (CK4 * G) + lig;
+                    const uint32_t *src = wp.ckpt + (size_t)(seqA_hi >> 1) * wp.ckpt_task_stride + wp.ckpt_base[cj] +
+                                          (size_t)(kb - 1) * (CKW * G) + lig;
                     const int sh = (seqA_hi & 1) ? 16 : 0;
 #pragma unroll
-                    for (int q = 0; q < CK4; ++q) {
-                        const uint4 x = src[q * G];
-                        v[4 * q] |= ((x.x >> sh) & 0xffffu) << 16;
-                        v[4 * q + 1] |= ((x.y >> sh) & 0xffffu) << 16;
-                        v[4 * q + 2] |= ((x.z >> sh) & 0xffffu) << 16;
-                        v[4 * q + 3] |= ((x.w >> sh) & 0xffffu) << 16;
-                    }
+                    for (int i = 0; i < CKW; ++i) v[i] |= ((src[i * G] >> sh) & 0xffffu) << 16;
                 }
             }
 #pragma unroll
@@ -530,15 +605,18 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                 Hrow[i] = v[i];
                 Frow[i] = v[K + i];
             }
+            e_out = v[2 * K];
+            h_up_prev = v[2 * K + 1];
         }
 
         const uint8_t *cs = cc + p.coff[cj];
         uint32_t *fl = wp.flags + (size_t)task * wp.win_task_stride + (size_t)lig * NW;
-        const int ncols = we - (int)ws + 1;  // <= wp.wmax by construction
-        // lane l-1's last row of column ws-1 is lane l's diagonal at column ws
-        uint32_t h_last = Hrow[K - 1], e_out = 0, h_up_prev = 0;
+        // The sweep resumes at step ws: lane l continues with column ws - l, so the flag buffer starts at column
+        // ws - (G-1); only columns >= ws are complete (and only those are consulted by the walk).
+        const int origin = (int)ws - (G - 1);
+        uint32_t h_last = Hrow[K - 1];
         // the groups of a warp hold different windows: the trip count must be warp-uniform for the shuffles
-        const int nsteps = __reduce_max_sync(FULL, ncols > 0 ? ncols + G - 1 : 0);
+        const int nsteps = __reduce_max_sync(FULL, we >= (int)ws ? we - (int)ws + G : 0);
 
         for (int step = 0; step < nsteps; ++step) {
             uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G);
@@ -547,9 +625,10 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                 h_in = 0;
                 e_in = 0;
             }
-            const int jw = step - lig;  // window-relative column
-            if (jw >= 0 && jw < ncols) {
-                const uint4 *tp = tab + (size_t)cs[ws + jw] * (K4 * G) + lig;
+            const int j = (int)ws + step - lig;  // column of this lane
+            if (j >= 0 && j <= we) {
+                const int jw = j - origin;
+                const uint4 *tp = tab + (size_t)cs[j] * (K4 * G) + lig;
                 uint32_t diag = h_up_prev;
                 uint32_t E = e_in;
                 uint32_t words[NW];
@@ -585,6 +664,28 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                 }
                 h_last = Hrow[K - 1];
                 e_out = E;
+                // ---- pin the best cell down: smallest row, then smallest column (striped.rs:555-583) ----
+                const uint32_t s_abs = ws + (uint32_t)step;
+                if ((uint32_t)lig == ls_lo && s_abs - fs_lo <= 1u) {
+                    int irow = K;
+#pragma unroll
+                    for (int i = K - 1; i >= 0; --i)
+                        if ((int)(int16_t)(Hrow[i] & 0xffffu) == best_lo) irow = i;
+                    if (irow < bi_lo) {
+                        bi_lo = irow;
+                        bj_lo = j;
+                    }
+                }
+                if ((uint32_t)lig == ls_hi && s_abs - fs_hi <= 1u) {
+                    int irow = K;
+#pragma unroll
+                    for (int i = K - 1; i >= 0; --i)
+                        if ((int)(int16_t)(Hrow[i] >> 16) == best_hi) irow = i;
+                    if (irow < bi_hi) {
+                        bi_hi = irow;
+                        bj_hi = j;
+                    }
+                }
                 if (valid) {
 #pragma unroll
                     for (int w = 0; w < NW; w += 4)
@@ -593,6 +694,23 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                 }
             }
             h_up_prev = h_in;
+        }
+        // the winning lane publishes the exact end cell (the walk starts there)
+        if ((uint32_t)lig == ls_lo) {
+            if (bi_lo < K) {
+                wp.ends[g_lo].r_end = ls_lo * K + (uint32_t)bi_lo;
+                wp.ends[g_lo].c_end = (uint32_t)bj_lo;
+            } else {
+                atomicAdd(&wp.counters[7], 1ULL);  // pass A and pass B disagree: reported as an internal error
+            }
+        }
+        if ((uint32_t)lig == ls_hi) {
+            if (bi_hi < K) {
+                wp.ends[g_hi].r_end = ls_hi * K + (uint32_t)bi_hi;
+                wp.ends[g_hi].c_end = (uint32_t)bj_hi;
+            } else {
+                atomicAdd(&wp.counters[7], 1ULL);
+            }
         }
     }
 }
@@ -620,13 +738,13 @@ __global__ void sw_traceback_win_kernel(const TraceWinParams tw) {
     const AlignEnd e = t.ends[gid];
     const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
     const uint32_t m = t.coff[cj + 1] - t.coff[cj];
-    const uint32_t ws = win_start(e.r_end, e.c_end, tw.slack, tw.cb_log2);
+    const uint32_t ws = e.aux;
     const uint32_t half = pslot & 1u;
     const uint32_t *fl = tw.wflags + (size_t)(pslot >> 1) * tw.win_task_stride;
     const int G = t.G, K = t.K, NW = t.NW;
     auto cell = [&](uint32_t r, uint32_t c) -> uint32_t {
         uint32_t lane = r / K, kk = r % K;
-        uint32_t w = fl[((size_t)(c - ws) * G + lane) * NW + kk / 3];
+        uint32_t w = fl[((size_t)(c - ws + (uint32_t)(G - 1)) * G + lane) * NW + kk / 3];
         return (w >> (16 * half + 5 * (kk % 3))) & 31u;
     };
 

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "sw_align.cuh"
+#include "sw_align_win.cuh"
 #include "sw_score.cuh"
 #include "sw_score_long.cuh"
 
@@ -75,6 +76,8 @@ struct Device {
     // align state
     DevBuf pbytes, ends, flags, flag_base, ref_start, ref_end, query_start, query_end, hazard, hazard_list;
     DevBuf cig_scratch, cig_count, cig_off, cig_out, ex_hbuf, ex_fbuf, ex_cig, weights;
+    // windowed align path (sw_align_win.cuh)
+    DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems, redo_flag, redo_ids, redo_flags;
     uint64_t cig_total = 0;
     // long-row score path
     DevBuf long_ids, long_bnd, long_queue;
@@ -89,12 +92,14 @@ struct KernelEntry {
     void (*wide)(const ScoreParams);
     void (*fill)(const AlignParams);
     void (*packed2)(const ScoreParams);  // two column sequences per sweep
+    void (*scan)(const WinParams);       // windowed align, pass A
+    void (*winfill)(const WinParams);    // windowed align, pass B
 };
 
 #define ZK(G, K) \
     KernelEntry {                                                                                          \
         G, K, sw_score_kernel<G, K, true, 1>, sw_score_kernel<G, K, false, 1>, sw_align_fill_kernel<G, K, true>, \
-            sw_score_kernel<G, K, true, 2>                                                                 \
+            sw_score_kernel<G, K, true, 2>, sw_align_scan_kernel<G, K>, sw_align_winfill_kernel<G, K>      \
     }
 
 // Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
@@ -138,6 +143,9 @@ struct zoe_cuda_ctx {
     bool staged = false;
     std::vector<uint32_t> staged_len;  // per streamed sequence (only kept when the long-row path is needed)
     uint64_t flag_budget_bytes = 0;  // 0 = auto (a fraction of free device memory)
+    int align_mode = 0;              // 0 = auto, 1 = full-matrix flags, 2 = checkpointed window
+    int win_cb_log2 = 7;             // checkpoint spacing (columns), log2
+    uint32_t win_slack = 16;         // columns kept left of the shortest possible walk
     // measurements
     float last_total_ms = 0.f, last_dp_ms = 0.f;
     uint32_t last_launches = 0;
@@ -725,19 +733,48 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     const uint32_t n_prof = ctx->n_prof;
     const size_t pairs = (size_t)d.n_count * n_prof;
 
-    // flag layout of one task: every profiled sequence back to back
-    std::vector<uint64_t> flag_base(n_prof);
-    uint64_t task_stride = 0;
-    for (uint32_t j = 0; j < n_prof; ++j) {
-        flag_base[j] = task_stride;
-        task_stride += (uint64_t)(ctx->coff[j + 1] - ctx->coff[j]) * k->G * NW;
+    // ---- which align pipeline? ----
+    // The checkpointed-window pipeline pays when the profiled sequences are much longer than the walk can
+    // be; gap_open == 0 sends every pair to the literal kernel anyway, so only the scores matter there.
+    int cb_log2 = ctx->win_cb_log2;
+    while ((1 << cb_log2) < k->G) ++cb_log2;  // a checkpoint is a step boundary with every lane active
+    const uint32_t CB = 1u << cb_log2;
+    // window capacity in columns: the walk's reach + the distance to the previous checkpoint + the lane skew
+    const uint32_t wmax = std::min<uint32_t>(ctx->max_prof_len, std::max<uint32_t>(ctx->staged_max_len, 1) + ctx->win_slack + CB) + k->G;
+    // (the scan kernel stages the profiled sequences in shared memory: they must fit)
+    const bool window_ok = ctx->go != 0 && ctx->ccodes.size() <= 96 * 1024;
+    bool use_window = window_ok && (uint64_t)ctx->max_prof_len >= 2ull * wmax;
+    if (ctx->align_mode == 1) use_window = false;
+    if (ctx->align_mode == 2) use_window = window_ok;
+    if (const char *e = getenv("ZOE_CUDA_ALIGN_MODE")) {
+        if (!strcmp(e, "full")) use_window = false;
+        if (!strcmp(e, "window")) use_window = window_ok;
     }
+
+    // flag layout of one task: every profiled sequence back to back (full-matrix pipeline), or one window
+    std::vector<uint64_t> flag_base(n_prof), ckpt_base(n_prof);
+    uint64_t task_stride = 0, ckpt_task_stride = 0;
+    const int CKW = ckpt_words_per_lane(k->K);
+    uint32_t nblk = 1;
+    for (uint32_t j = 0; j < n_prof; ++j) {
+        const uint64_t L = ctx->coff[j + 1] - ctx->coff[j];
+        flag_base[j] = task_stride;
+        task_stride += L * k->G * NW;
+        ckpt_base[j] = ckpt_task_stride;
+        ckpt_task_stride += ((L - 1) >> cb_log2) * (uint64_t)CKW * k->G;  // words
+        nblk = std::max<uint32_t>(nblk, (uint32_t)((L - 1) >> cb_log2) + 1);
+    }
+    const uint32_t n_keys = n_prof * nblk;
+    const uint64_t win_task_stride = (uint64_t)wmax * k->G * NW;  // words per pass-B task
     // chunk size from the flag-memory budget
     size_t free_b = 0, total_b = 0;
     CU(ctx, cudaMemGetInfo(&free_b, &total_b));
     uint64_t budget = ctx->flag_budget_bytes ? ctx->flag_budget_bytes : (uint64_t)(free_b * 0.55);
     budget = std::min<uint64_t>(budget, (uint64_t)48 << 30);
-    uint64_t tasks_cap = std::max<uint64_t>(1, budget / (task_stride * 4));
+    // bytes per pass-A task (two sequences): full = all flags; window = checkpoints + one window per pair
+    const uint64_t per_task_bytes = use_window ? (ckpt_task_stride * 4 + (uint64_t)n_prof * win_task_stride * 4)
+                                               : task_stride * 4;
+    uint64_t tasks_cap = std::max<uint64_t>(1, budget / std::max<uint64_t>(per_task_bytes, 1));
     uint64_t chunk_seqs = std::min<uint64_t>(d.n_count, tasks_cap * 2);
     if (chunk_seqs > 1) chunk_seqs &= ~1ULL;
     const uint32_t cig_cap = 2 * std::min<uint32_t>(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->max_prof_len) + 4;
@@ -746,7 +783,22 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     CU(ctx, cudaMemcpyAsync(d.flag_base.p, flag_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
     CU(ctx, cudaStreamSynchronize(d.stream));
     CU(ctx, d.ends.reserve(pairs * sizeof(AlignEnd)));
-    CU(ctx, d.flags.reserve(((chunk_seqs + 1) / 2) * task_stride * 4));
+    if (use_window) {
+        const uint64_t max_items = chunk_seqs * n_prof + n_keys + 2;  // every bucket rounds up to even
+        CU(ctx, d.flags.reserve((max_items / 2 + 1) * win_task_stride * 4));
+        CU(ctx, d.ckpt.reserve(std::max<uint64_t>(((chunk_seqs + 1) / 2) * ckpt_task_stride * 4, 16)));
+        CU(ctx, d.ckpt_base.reserve(n_prof * sizeof(uint64_t)));
+        CU(ctx, cudaMemcpyAsync(d.ckpt_base.p, ckpt_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        CU(ctx, d.win_hist.reserve(n_keys * sizeof(uint32_t)));
+        CU(ctx, d.win_bucket.reserve((n_keys + 1) * sizeof(uint32_t)));
+        CU(ctx, d.win_items.reserve(max_items * sizeof(uint32_t)));
+        CU(ctx, d.win_nitems.reserve(sizeof(uint32_t)));
+        CU(ctx, d.redo_flag.reserve(chunk_seqs));
+        CU(ctx, d.redo_ids.reserve((chunk_seqs + 1) * sizeof(uint32_t)));
+    } else {
+        CU(ctx, d.flags.reserve(((chunk_seqs + 1) / 2) * task_stride * 4));
+    }
     for (DevBuf *b : {&d.ref_start, &d.ref_end, &d.query_start, &d.query_end, &d.cig_count, &d.best, &d.score})
         CU(ctx, b->reserve(pairs * sizeof(uint32_t)));
     CU(ctx, d.status.reserve(pairs));
@@ -763,10 +815,19 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     { DebugTimer t; if (t.on) fprintf(stderr, "[zoe_cuda] align: chunk_seqs %llu task_stride %llu words, cig_cap %u\n", (unsigned long long)chunk_seqs, (unsigned long long)task_stride, cig_cap); }
 
     DebugTimer dbg;
-    LaunchPlan plan;
-    int rc = plan_launch(ctx, *k, k->fill, &plan);
+    LaunchPlan plan, plan_b;
+    int rc = use_window ? plan_launch(ctx, *k, k->scan, &plan) : plan_launch(ctx, *k, k->fill, &plan);
     if (rc) return rc;
-    CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    if (use_window && !plan.cols_in_smem)
+        return fail(ctx, ZOE_CUDA_E_STATE, "internal error: window pipeline planned without staged columns");
+    if (use_window) {
+        rc = plan_launch(ctx, *k, k->winfill, &plan_b);
+        if (rc) return rc;
+        CU(ctx, cudaFuncSetAttribute(k->scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        CU(ctx, cudaFuncSetAttribute(k->winfill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_b.smem));
+    } else {
+        CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    }
     dbg.lap("align: plan");
     const bool all_exact = (ctx->go == 0);
     const int invert = ctx->profiled_is_query ? 0 : 1;
@@ -803,11 +864,13 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         uint32_t groups_per_block = plan.threads / k->G;
         uint32_t blocks = std::min<uint32_t>((uint32_t)(d.sm_count * plan.blocks_per_sm),
                                              (p.n_tasks + groups_per_block - 1) / groups_per_block);
-        CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
-        k->fill<<<blocks, plan.threads, plan.smem, d.stream>>>(ap);
-        CU(ctx, cudaGetLastError());
-        CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
-        ctx->last_launches++;
+        if (!use_window) {
+            CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+            k->fill<<<blocks, plan.threads, plan.smem, d.stream>>>(ap);
+            CU(ctx, cudaGetLastError());
+            CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+            ctx->last_launches++;
+        }
 
         // ---- traceback ----
         CU(ctx, cudaMemsetAsync(ctr + 4, 0, 2 * sizeof(unsigned long long), d.stream));  // [4] wide seqs, [5] exact list
@@ -844,9 +907,128 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         t.hazard_list = d.hazard_list.as<uint32_t>();
         t.all_exact = all_exact ? 1 : 0;
         const uint32_t cpairs = cn * n_prof;
-        sw_traceback_kernel<<<(cpairs + 127) / 128, 128, 0, d.stream>>>(t);
-        CU(ctx, cudaGetLastError());
-        ctx->last_launches++;
+        if (!use_window) {
+            sw_traceback_kernel<<<(cpairs + 127) / 128, 128, 0, d.stream>>>(t);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+        } else {
+            // ---- checkpointed-window pipeline: scan -> classify -> bucket -> scatter -> window fill -> walk ----
+            WinParams wp{};
+            wp.s = p;
+            wp.ends = ap.ends;
+            wp.chunk_first = (uint32_t)c0;
+            wp.ckpt = d.ckpt.as<uint32_t>();
+            wp.ckpt_base = d.ckpt_base.as<uint64_t>();
+            wp.ckpt_task_stride = ckpt_task_stride;
+            wp.cb_log2 = cb_log2;
+            wp.slack = ctx->win_slack;
+            wp.nblk = nblk;
+            wp.hist = d.win_hist.as<uint32_t>();
+            wp.bucket_start = d.win_bucket.as<uint32_t>();
+            wp.items = d.win_items.as<uint32_t>();
+            wp.n_items = d.win_nitems.as<uint32_t>();
+            wp.flags = d.flags.as<uint32_t>();
+            wp.win_task_stride = win_task_stride;
+            wp.wmax = wmax;
+            wp.counters = ctr;
+            const uint64_t max_items = (uint64_t)cpairs + n_keys + 2;
+            CU(ctx, cudaMemsetAsync(d.win_hist.p, 0, n_keys * sizeof(uint32_t), d.stream));
+            CU(ctx, cudaMemsetAsync(d.win_items.p, 0xff, max_items * sizeof(uint32_t), d.stream));
+            CU(ctx, cudaMemsetAsync(d.redo_flag.p, 0, cn, d.stream));
+            CU(ctx, cudaMemsetAsync(ctr + 12, 0, sizeof(unsigned long long), d.stream));  // [12] redo list length
+            CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+            k->scan<<<blocks, plan.threads, plan.smem, d.stream>>>(wp);
+            CU(ctx, cudaGetLastError());
+            ClassifyParams cp{};
+            cp.ends = ap.ends;
+            cp.roff = p.roff;
+            cp.coff = p.coff;
+            cp.n_cseq = n_prof;
+            cp.chunk_first = (uint32_t)c0;
+            cp.n_slots = cn;
+            cp.K = k->K;
+            cp.redo_flag = d.redo_flag.as<uint8_t>();
+            cp.cb_log2 = cb_log2;
+            cp.slack = ctx->win_slack;
+            cp.nblk = nblk;
+            cp.all_exact = all_exact ? 1 : 0;
+            cp.hist = wp.hist;
+            cp.best_arr = t.best_arr;
+            cp.score = t.score;
+            cp.status = t.status;
+            cp.tier = t.tier;
+            cp.hazard = t.hazard;
+            cp.ref_start = t.ref_start;
+            cp.ref_end = t.ref_end;
+            cp.query_start = t.query_start;
+            cp.query_end = t.query_end;
+            cp.cig_count = t.cig_count;
+            cp.counters = ctr;
+            cp.hazard_list = t.hazard_list;
+            win_classify_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp);
+            CU(ctx, cudaGetLastError());
+            win_bucket_scan_kernel<<<1, 1024, 0, d.stream>>>(wp.hist, n_keys, wp.bucket_start, wp.n_items);
+            CU(ctx, cudaGetLastError());
+            win_scatter_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp, wp.bucket_start, wp.items);
+            CU(ctx, cudaGetLastError());
+            {
+                WinParams wb = wp;
+                wb.s.cols_in_smem = plan_b.cols_in_smem;
+                const uint32_t gpb = plan_b.threads / k->G;
+                const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_b.blocks_per_sm),
+                                                       (uint32_t)((max_items / 2 + gpb - 1) / gpb));
+                k->winfill<<<nb, plan_b.threads, plan_b.smem, d.stream>>>(wb);
+                CU(ctx, cudaGetLastError());
+            }
+            CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+            TraceWinParams tw{};
+            tw.t = t;
+            tw.items = wp.items;
+            tw.n_items = wp.n_items;
+            tw.wflags = wp.flags;
+            tw.win_task_stride = win_task_stride;
+            tw.cb_log2 = cb_log2;
+            tw.slack = ctx->win_slack;
+            sw_traceback_win_kernel<<<(uint32_t)((max_items + 127) / 128), 128, 0, d.stream>>>(tw);
+            CU(ctx, cudaGetLastError());
+            win_collect_redo_kernel<<<(cn + 255) / 256, 256, 0, d.stream>>>(cp.redo_flag, (uint32_t)c0, cn,
+                                                                            d.redo_ids.as<uint32_t>(), ctr);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches += 7;
+            // ---- sequences with an ambiguous end cell: the full-matrix pipeline on that (short) list ----
+            unsigned long long n_redo = 0;
+            CU(ctx, cudaMemcpyAsync(&n_redo, ctr + 12, sizeof(n_redo), cudaMemcpyDeviceToHost, d.stream));
+            CU(ctx, cudaStreamSynchronize(d.stream));
+            if (n_redo) {
+                LaunchPlan plan_f;
+                rc = plan_launch(ctx, *k, k->fill, &plan_f);
+                if (rc) return rc;
+                CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_f.smem));
+                const uint64_t sub_cap = std::max<uint64_t>(2, (((uint64_t)8 << 30) / (task_stride * 4)) * 2);  // <= 8 GB of flags
+                CU(ctx, d.redo_flags.reserve(((std::min<uint64_t>(n_redo, sub_cap) + 1) / 2) * task_stride * 4));
+                for (uint64_t r0 = 0; r0 < n_redo; r0 += sub_cap) {
+                    const uint32_t rn = (uint32_t)std::min<uint64_t>(sub_cap, n_redo - r0);
+                    AlignParams fa = ap;
+                    fa.s.task_ids = d.redo_ids.as<uint32_t>() + r0;
+                    fa.s.n_rseq = rn;
+                    fa.s.n_tasks = (rn + 1) / 2;
+                    fa.s.cols_in_smem = plan_f.cols_in_smem;
+                    fa.flags = d.redo_flags.as<uint32_t>();
+                    const uint32_t gpb = plan_f.threads / k->G;
+                    const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_f.blocks_per_sm), (fa.s.n_tasks + gpb - 1) / gpb);
+                    k->fill<<<nb, plan_f.threads, plan_f.smem, d.stream>>>(fa);
+                    CU(ctx, cudaGetLastError());
+                    TraceParams tr = t;
+                    tr.flags = fa.flags;
+                    tr.seq_ids = fa.s.task_ids;
+                    tr.n_slots = rn;
+                    tr.only_ambiguous = 1;
+                    sw_traceback_kernel<<<(rn * n_prof + 127) / 128, 128, 0, d.stream>>>(tr);
+                    CU(ctx, cudaGetLastError());
+                    ctx->last_launches += 2;
+                }
+            }
+        }
 
         unsigned long long hc[5] = {0, 0, 0, 0, 0};  // ctr[4..8]
         CU(ctx, cudaMemcpyAsync(hc, ctr + 4, sizeof(hc), cudaMemcpyDeviceToHost, d.stream));
@@ -951,9 +1133,13 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     ctx->last_launches++;
     unsigned long long tail[3] = {0, 0, 0};  // ctr[7] score mismatch, [8] overflow, [9] cigar total
     CU(ctx, cudaMemcpyAsync(tail, ctr + 7, sizeof(tail), cudaMemcpyDeviceToHost, d.stream));
-    unsigned long long cig_ovf = 0;
+    unsigned long long cig_ovf = 0, win_fb[2] = {0, 0};  // ctr[10] walks that left their window, [11] ambiguous ends
     CU(ctx, cudaMemcpyAsync(&cig_ovf, ctr + 6, sizeof(cig_ovf), cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaMemcpyAsync(win_fb, ctr + 10, sizeof(win_fb), cudaMemcpyDeviceToHost, d.stream));
     CU(ctx, cudaStreamSynchronize(d.stream));
+    ctx->stats.window_fallback += win_fb[0];
+    ctx->stats.window_redo += win_fb[1];
+    ctx->stats.hazard -= std::min<uint64_t>(ctx->stats.hazard, win_fb[0]);
     dbg.lap("align: compaction+tail");
     d.cig_total = tail[2];
     d.timed_kernel = false;  // several fill launches: report their sum instead of one event pair
@@ -1047,7 +1233,8 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.long_ids, &d.long_bnd,
-                          &d.long_queue})
+                          &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.redo_flag,
+                          &d.redo_ids, &d.redo_flags})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
@@ -1088,6 +1275,16 @@ int zoe_cuda_set_lanes(zoe_cuda_ctx *ctx, int lanes_i8, int lanes_i16, int lanes
     ctx->lanes[0] = lanes_i8;
     ctx->lanes[1] = lanes_i16;
     ctx->lanes[2] = lanes_i32;
+    return 0;
+}
+
+int zoe_cuda_set_align_options(zoe_cuda_ctx *ctx, int mode, int checkpoint_log2, int slack) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (mode < 0 || mode > 2 || checkpoint_log2 < 2 || checkpoint_log2 > 16 || slack < 1 || slack > (1 << 20))
+        return fail(ctx, ZOE_CUDA_E_BAD_ARG, "bad align options (mode %d, checkpoint_log2 %d, slack %d)", mode, checkpoint_log2, slack);
+    ctx->align_mode = mode;
+    ctx->win_cb_log2 = checkpoint_log2;
+    ctx->win_slack = (uint32_t)slack;
     return 0;
 }
 
