@@ -39,6 +39,27 @@
 
 namespace zoe_cuda {
 
+// Lane skew of the systolic sweep (columns between neighbouring lanes).  With a skew of 2 the value a lane needs from
+// the lane above was produced two steps earlier and shuffled during the previous step, so consecutive steps of a
+// lane are independent dependency chains and the shuffle latency is never exposed.
+#ifndef ZOE_SCORE_SKEW
+#define ZOE_SCORE_SKEW 2
+#endif
+constexpr int kSkew = ZOE_SCORE_SKEW;
+
+// Running maximum on the FMA pipe: the packed scores are non-negative 16-bit integers, and below 0x7C00 their bit
+// patterns order exactly like IEEE half-precision numbers, so HMNMX2 (half2 max, FMA pipe) can stand in for
+// VIMNMX3.S16x2 (ALU pipe, the pipe that bounds the kernel).  The packed overflow threshold is lowered accordingly
+// (kPackedLimit); a NaN pattern (>= 0x7C00) can never displace the running maximum, so detection stays exact.
+// MEASURED AND REJECTED on B200 (cfg 2, 400k reads): results stay bit-exact, but HMNMX2 issues on the ALU pipe as
+// well, so the ALU count rises from 4.59 to 5.07 per pair: 6.30 TCUPS against 6.84 with VIMNMX3.  Kept behind the
+// switch as a record of the experiment.
+#ifndef ZOE_SCORE_HMAX
+#define ZOE_SCORE_HMAX 0
+#endif
+constexpr bool kHalfMax = ZOE_SCORE_HMAX != 0;
+constexpr int kPackedLimit = kHalfMax ? 0x7C00 : 32767;  // packed lanes are exact while H < kPackedLimit - max weight
+
 constexpr int kPadWeight = -16384;  // score of a padding row (never wins a max, never wraps)
 
 struct ScoreParams {
@@ -93,6 +114,12 @@ struct Ops<false> {
     static __device__ __forceinline__ uint32_t splat(int v) { return (uint32_t)v; }
 };
 
+__device__ __forceinline__ uint32_t half2_max_bits(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
 // Shared-memory footprint helpers (host + device).
 __host__ __device__ inline int score_tab_bytes(int n_csym, int G, int K) { return n_csym * ((K + 3) / 4) * G * 16; }
 
@@ -108,17 +135,15 @@ __host__ __device__ inline int score_tab_bytes(int n_csym, int G, int K) { retur
         ST##E = O::addmax(ST##E, neg_ge, H);                     \
         ST##F[i] = O::addmax(ST##F[i], neg_ge, H);               \
         ST##H[PN][i] = H;                                        \
-        if (i & 1) {                                             \
+        if (PACKED && kHalfMax) {                                \
+            ST##best = half2_max_bits(ST##best, H);              \
+        } else if (i & 1) {                                      \
             ST##best = O::max3(ST##best, H, ST##hp);             \
         } else {                                                 \
             ST##hp = H;                                          \
         }                                                        \
     }
 
-// Tried and rejected on B200 (scripts/variants.py, 400k reads, cfg 2): moving the running maximum to the FMA pipe
-// with HMNMX2 on the integer bit patterns (exact below 0x7C00) lowers the ALU count to 4.0 per pair but raises the
-// issue count; it measured 5.79 TCUPS against 6.18 (in place) / 6.45 (ping-pong) for the DPX max3 form.
-//
 // NS = number of column sequences swept concurrently by one group (1 or 2).  With NS = 2 every thread
 // carries two independent H/E/F recurrences that share the task's score table, which doubles the
 // instruction-level parallelism available to hide the 4-deep dependent chain per row (the ALU pipe, not the
@@ -150,8 +175,15 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
     __syncthreads();
     const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
 
-    const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+    uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
     const uint4 *tab_lane = tab + lig;
+    // Loop invariants kept opaque so the compiler does not rematerialise them inside the hot loops (S2R + address
+    // arithmetic); the table offset stays a 32-bit offset into the shared array so the loads remain LDS.128.
+    uint32_t tab_lane_off = (uint32_t)group_in_block * (uint32_t)tab_bytes + (uint32_t)lig * 16u;
+    // lane 0 receives zeros from "above": multiplying by an opaque 0/1 keeps that on the FMA pipe (a SEL would
+    // take an ALU slot, and the ALU pipe is what bounds this kernel)
+    uint32_t nz = lig != 0 ? 1u : 0u;
+    asm volatile("" : "+r"(go_s), "+r"(neg_ge), "+r"(tab_lane_off), "+r"(nz));
 
     // Static round-robin task assignment: every group of a warp makes the same number of trips,
     // so the warp never diverges on the task loop (invalid trips run on empty sequences).
@@ -230,6 +262,9 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
                 csB = cc + cB0;
             }
 
+            // the same column codes through a pointer the compiler knows is shared memory (steady loops only)
+            const uint8_t *scA = s_cc + (csA - cc), *scB = s_cc + (csB - cc);
+
             constexpr int NP = PP ? 2 : 1;  // register sets of H (ping-pong or in place)
             uint32_t aH[NP][K], aF[K], bH[NP][NS == 2 ? K : 1], bF[NS == 2 ? K : 1];
 #pragma unroll
@@ -243,25 +278,41 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
             }
             uint32_t abest = 0, ah_last = 0, ae_out = 0, ah_up_prev = 0;
             uint32_t bbest = 0, bh_last = 0, be_out = 0, bh_up_prev = 0;
-            const int nsteps = max(LA, LB) + G - 1;
+            uint32_t a_pend_h = 0, a_pend_e = 0, b_pend_h = 0, b_pend_e = 0;  // kSkew == 2: shuffled one step ahead
+            const int nsteps = max(LA, LB) + kSkew * (G - 1);
+            // Values entering from the lane above.  Skew 1: shuffle the neighbour's outputs of this very step's
+            // predecessor and use them at once.  Skew 2: use what was shuffled during the previous step, then shuffle
+            // the neighbour's latest outputs for the next step -- nothing in this step waits for a shuffle.
+            auto exchange = [&](uint32_t &ah_in, uint32_t &ae_in, uint32_t &bh_in, uint32_t &be_in, const bool with_b) {
+                const uint32_t ah_sh = __shfl_up_sync(FULL, ah_last, 1, G), ae_sh = __shfl_up_sync(FULL, ae_out, 1, G);
+                uint32_t bh_sh = 0, be_sh = 0;
+                if (with_b) {
+                    bh_sh = __shfl_up_sync(FULL, bh_last, 1, G);
+                    be_sh = __shfl_up_sync(FULL, be_out, 1, G);
+                }
+                if (kSkew == 1) {
+                    ah_in = ah_sh * nz;
+                    ae_in = ae_sh * nz;
+                    bh_in = bh_sh * nz;
+                    be_in = be_sh * nz;
+                } else {
+                    ah_in = a_pend_h;
+                    ae_in = a_pend_e;
+                    bh_in = b_pend_h;
+                    be_in = b_pend_e;
+                    a_pend_h = ah_sh * nz;
+                    a_pend_e = ae_sh * nz;
+                    b_pend_h = bh_sh * nz;
+                    b_pend_e = be_sh * nz;
+                }
+            };
 
             auto do_step = [&](auto parity, const int step) {
                 constexpr int PO = PP ? decltype(parity)::value : 0;      // set holding column j-1
                 constexpr int PN = PP ? 1 - decltype(parity)::value : 0;  // set receiving column j
-                uint32_t ah_in = __shfl_up_sync(FULL, ah_last, 1, G);
-                uint32_t ae_in = __shfl_up_sync(FULL, ae_out, 1, G);
-                uint32_t bh_in = 0, be_in = 0;
-                if (NS == 2) {
-                    bh_in = __shfl_up_sync(FULL, bh_last, 1, G);
-                    be_in = __shfl_up_sync(FULL, be_out, 1, G);
-                }
-                if (lig == 0) {
-                    ah_in = 0;
-                    ae_in = 0;
-                    bh_in = 0;
-                    be_in = 0;
-                }
-                const int j = step - lig;
+                uint32_t ah_in, ae_in, bh_in, be_in;
+                exchange(ah_in, ae_in, bh_in, be_in, NS == 2);
+                const int j = step - kSkew * lig;
                 const bool actA = j >= 0 && j < LA;
                 const bool actB = NS == 2 && j >= 0 && j < LB;
                 if (actA && actB) {
@@ -283,7 +334,7 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
                             }
                         }
                     }
-                    if (K & 1) {
+                    if ((K & 1) && !(PACKED && kHalfMax)) {
                         abest = O::max2(abest, ahp);
                         if (NS == 2) bbest = O::max2(bbest, bhp);
                     }
@@ -306,7 +357,7 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
                             if (i < K) ZOE_SCORE_ROW(a, wa[q])
                         }
                     }
-                    if (K & 1) abest = O::max2(abest, ahp);
+                    if ((K & 1) && !(PACKED && kHalfMax)) abest = O::max2(abest, ahp);
                     ah_last = aH[PN][K - 1];
                     ae_out = aE;
                 } else if (actB) {
@@ -322,18 +373,100 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
                             if (i < K) ZOE_SCORE_ROW(b, wb[q])
                         }
                     }
-                    if (K & 1) bbest = O::max2(bbest, bhp);
+                    if ((K & 1) && !(PACKED && kHalfMax)) bbest = O::max2(bbest, bhp);
                     bh_last = bH[PN][K - 1];
                     be_out = bE;
                 }
                 ah_up_prev = ah_in;
                 bh_up_prev = bh_in;
             };
+            // Steady steps: every lane of the group has a column (steps G .. L-1), so no activity predicates, no
+            // per-lane branches; the column codes come from shared memory (LDS with a 32-bit address).  `BOTH`
+            // = both streams, else stream A alone (the longer sequence of the pair once B has run out).
+            auto steady_step = [&](auto parity, auto both, const int step) {
+                constexpr int PO = PP ? decltype(parity)::value : 0;
+                constexpr int PN = PP ? 1 - decltype(parity)::value : 0;
+                constexpr bool BOTH = NS == 2 && decltype(both)::value;
+                uint32_t ah_in, ae_in, bh_in, be_in;
+                exchange(ah_in, ae_in, bh_in, be_in, BOTH);
+                const int j = step - kSkew * lig;
+                const uint4 *tpA = reinterpret_cast<const uint4 *>(smem + tab_lane_off + (uint32_t)scA[j] * (uint32_t)(K4 * G * 16));
+                const uint4 *tpB = tpA;
+                if (BOTH) tpB = reinterpret_cast<const uint4 *>(smem + tab_lane_off + (uint32_t)scB[j] * (uint32_t)(K4 * G * 16));
+                uint32_t adiag = ah_up_prev, aE = ae_in, ahp = 0;
+                uint32_t bdiag = bh_up_prev, bE = be_in, bhp = 0;
+#pragma unroll
+                for (int i4 = 0; i4 < K4; ++i4) {
+                    const uint4 wa4 = tpA[i4 * G];
+                    uint4 wb4 = wa4;
+                    if (BOTH) wb4 = tpB[i4 * G];
+                    const uint32_t wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w};
+                    const uint32_t wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i4 * 4 + q;
+                        if (i < K) {
+                            ZOE_SCORE_ROW(a, wa[q])
+                            if (BOTH) ZOE_SCORE_ROW(b, wb[q])
+                        }
+                    }
+                }
+                if ((K & 1) && !(PACKED && kHalfMax)) {
+                    abest = O::max2(abest, ahp);
+                    if (BOTH) bbest = O::max2(bbest, bhp);
+                }
+                ah_last = aH[PN][K - 1];
+                ae_out = aE;
+                ah_up_prev = ah_in;
+                if (BOTH) {
+                    bh_last = bH[PN][K - 1];
+                    be_out = bE;
+                    bh_up_prev = bh_in;
+                }
+            };
+            using P0 = std::integral_constant<int, 0>;
+            using P1 = std::integral_constant<int, 1>;
             // A lane's active steps are consecutive, so its parity alternates exactly while it is active; before
             // that both register sets are zero, after that they are never read again.
-            for (int step = 0; step < nsteps; step += 2) {
-                do_step(std::integral_constant<int, 0>{}, step);
-                if (step + 1 < nsteps) do_step(std::integral_constant<int, 1>{}, step + 1);
+            // Five segments, one code copy each (the loop over segments is deliberately not unrolled):
+            //   0 generic [0, kSkew*G)      lanes switch on one by one
+            //   1 steady, both streams      every lane active in A and B
+            //   2 generic                   the shorter stream drains
+            //   3 steady, stream A alone    (the longer sequence of the pair)
+            //   4 generic                   tail: lanes switch off one by one
+            const bool fast = p.cols_in_smem && G % 2 == 0;
+            const int Lmin = NS == 2 ? min(LA, LB) : LA;
+            const bool solo = fast && NS == 2 && LA - Lmin > 3 * kSkew * G;
+            int seg_end[5];
+            seg_end[0] = fast ? min(kSkew * G, nsteps) : nsteps;
+            seg_end[1] = Lmin - 1;                                  // steady loops run while step + 1 < L
+            seg_end[2] = solo ? ((Lmin + kSkew * G) & ~1) : 0;
+            seg_end[3] = solo ? LA - 1 : 0;
+            seg_end[4] = nsteps;
+            int step = 0;
+#pragma unroll 1
+            for (int seg = 0; seg < 5; ++seg) {
+                const int end = seg_end[seg];
+                if (seg == 1) {
+                    if (fast)
+                        for (; step < end; step += 2) {
+                            steady_step(P0{}, std::true_type{}, step);
+                            steady_step(P1{}, std::true_type{}, step + 1);
+                        }
+                } else if (seg == 3) {
+                    if (NS == 2)
+                        for (; step < end; step += 2) {
+                            steady_step(P0{}, std::false_type{}, step);
+                            steady_step(P1{}, std::false_type{}, step + 1);
+                        }
+                } else {
+                    for (; step < end; ++step) {
+                        if (step & 1)
+                            do_step(P1{}, step);
+                        else
+                            do_step(P0{}, step);
+                    }
+                }
             }
 
             // ---- reduce the group's best and write the exact scores ----

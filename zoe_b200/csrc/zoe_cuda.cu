@@ -325,8 +325,9 @@ int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan
     }
     for (int cols_in_smem = 1; cols_in_smem >= 0; --cols_in_smem) {
         if (cols_in_smem && ctx->ccodes.size() > 96 * 1024) continue;
+        static const int env_max_threads = getenv("ZOE_CUDA_MAX_THREADS") ? atoi(getenv("ZOE_CUDA_MAX_THREADS")) : 1024;
         for (int threads : {512, 384, 256, 128, 64, 32}) {
-            if (threads < k.G || threads % k.G || threads > fa.maxThreadsPerBlock) continue;
+            if (threads < k.G || threads % k.G || threads > fa.maxThreadsPerBlock || threads > env_max_threads) continue;
             size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem);
             if (smem > 227 * 1024) continue;
             int nb = 0;
@@ -472,7 +473,7 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
     p.lut = d.lut.as<uint8_t>();
     p.go = ctx->go;
     p.ge = ctx->ge;
-    p.ovf_thresh = 32767 - std::max(ctx->max_weight, 0) - 1;
+    p.ovf_thresh = kPackedLimit - std::max(ctx->max_weight, 0) - 1;
     p.best = d.best.as<int32_t>();
     if (p.n_tasks == 0) return 0;
     CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -629,7 +630,7 @@ int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
     if (packed_ok) {
         rc = launch_score(ctx, d, *k, true, nullptr, 0);
         if (rc) return rc;
-        if (bound >= (uint64_t)(32767 - ctx->max_weight - 1)) {
+        if (bound >= (uint64_t)(kPackedLimit - ctx->max_weight - 1)) {
             // escalation: re-run the flagged sequences at 32 bits (or_else_overflowed, output.rs:81-83)
             uint32_t threads = 256, blocks = (uint32_t)((d.n_count + threads - 1) / threads);
             collect_wide_kernel<<<blocks, threads, 0, d.stream>>>(d.best.as<int32_t>(), (uint32_t)d.n_count,
