@@ -104,6 +104,32 @@ def test_protein_blosum62_vs_oracle():
     assert (tier == 16).any() and (tier == 8).any()
 
 
+def test_protein_ragged_lengths_shared_rows_kernel():
+    """The transposed (profiled-sequence-in-registers) kernel: ragged pairs, odd counts, pad columns, several
+    targets of different lengths, unusual residues (B, Z, X, *), and a scoring whose packed lanes overflow."""
+    rng = np.random.default_rng(41)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYBZX*", dtype=np.uint8)
+    targets = [aa[rng.integers(0, 20, L)] for L in (566, 97, 1024, 33)]
+    seqs = []
+    for k in range(75):  # odd number of sequences: the last task / trip is partial
+        L = int(rng.integers(64, 420)) if k else 420
+        q = aa[rng.integers(0, 24, L)]
+        t = targets[k % 4]
+        w = min(L, len(t)) - 6
+        st = int(rng.integers(0, len(t) - w + 1))
+        keep = rng.random(w) > 0.25
+        q[3:3 + w] = np.where(keep, t[st:st + w], q[3:3 + w])
+        seqs.append(q)
+    score, status, tier = check(targets, seqs, BLOSUM_62)
+    assert (tier == 16).any() and (tier == 8).any()
+    # packed overflow in the transposed kernel -> 32-bit re-run (i32 tier for the 600-mer)
+    wide = WeightMatrix(BLOSUM_62.mapping, np.where(np.eye(25, dtype=bool), 120, -4).astype(np.int8))
+    t600 = aa[rng.integers(0, 20, 600)]
+    qs = [t600.copy(), t600[:300].copy(), aa[rng.integers(0, 20, 200)], t600[100:400].copy()]
+    score, status, tier = check([t600], qs, wide)
+    assert int(tier[0, 0]) == 32 and int(score[0, 0]) == 600 * 120
+
+
 def test_i32_escalation():
     # match = 127: 600-mers score 76200 > 65534 -> i32 tier; 300-mers land in the i16 tier above 32767
     w = WeightMatrix.new(DNA_PROFILE_MAP, 127, -5, b"N")

@@ -15,6 +15,7 @@
 // an atomic queue, so warps stay balanced although lengths vary 5x.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "sw_score.cuh"
@@ -55,7 +56,11 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
     __syncthreads();
     const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
 
-    const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+    uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+    // loop invariants kept opaque (no rematerialisation in the hot loop); table offset as a 32-bit shared offset
+    uint32_t tab_lane_off = (uint32_t)warp * (uint32_t)tab_bytes + (uint32_t)lane * 16u;
+    uint32_t nz = lane != 0 ? 1u : 0u;  // lane 0 takes its inputs from the previous chunk's boundary row instead
+    asm volatile("" : "+r"(go_s), "+r"(neg_ge), "+r"(tab_lane_off), "+r"(nz));
     uint2 *bnd = lp.boundary + (size_t)(blockIdx.x * warps_per_block + warp) * lp.max_L;
 
     for (;;) {
@@ -87,6 +92,7 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
             const uint32_t c0 = p.coff[cj];
             const int L = (int)(p.coff[cj + 1] - c0);
             const uint8_t *cs = cc + c0;
+            const uint8_t *scs = s_cc + c0;  // the same codes through a pointer known to be shared memory
             uint32_t best = 0;
 
             for (int ch = 0; ch < nchunks; ++ch) {
@@ -115,64 +121,109 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
                 }
                 __syncwarp();
 
-                uint32_t Hrow[K], Frow[K];
+                // H in two register sets (ping-pong by step parity): no register moves for the diagonal
+                uint32_t H[2][K], F[K];
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
-                    Hrow[i] = 0;
-                    Frow[i] = 0;
+                    H[0][i] = H[1][i] = 0;
+                    F[i] = 0;
                 }
                 uint32_t h_last = 0, e_out = 0, h_up_prev = 0;
                 uint2 cur = make_uint2(0, 0), nxt = make_uint2(0, 0);
                 if (has_top && lane < L) cur = __ldcg(bnd + lane);
                 const int nsteps = L + G - 1;
+                const uint32_t top_on = has_top ? 1u - nz : 0u;  // 1 on lane 0 of a chunk that has a chunk above it
 
-                for (int step = 0; step < nsteps; ++step) {
+                // one column: FULLK = all K rows (a full chunk), else only the first k4_eff 4-row blocks
+                auto column = [&](auto parity, auto fullk, const int j, const uint32_t h_in, const uint32_t e_in, const uint32_t code) {
+                    constexpr int PO = decltype(parity)::value, PN = 1 - PO;
+                    constexpr bool FULLK = decltype(fullk)::value;
+                    const uint4 *tp = reinterpret_cast<const uint4 *>(smem + tab_lane_off + code * (uint32_t)(K4 * G * 16));
+                    uint32_t diag = h_up_prev;
+                    uint32_t E = e_in;
+#pragma unroll
+                    for (int i4 = 0; i4 < K4; ++i4) {
+                        if (FULLK || i4 < k4_eff) {
+                            const uint4 w4 = tp[i4 * G];
+                            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+                            uint32_t hp = 0;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int i = i4 * 4 + q;
+                                const uint32_t x = O::max3(E, F[i], go_s) - go_s;
+                                const uint32_t Hn = O::addmax(diag, w[q], x);
+                                diag = H[PO][i];
+                                E = O::addmax(E, neg_ge, Hn);
+                                F[i] = O::addmax(F[i], neg_ge, Hn);
+                                H[PN][i] = Hn;
+                                if (q & 1)
+                                    best = O::max3(best, Hn, hp);
+                                else
+                                    hp = Hn;
+                            }
+                            h_last = H[PN][i4 * 4 + 3];
+                        }
+                    }
+                    e_out = E;
+                    if (has_bottom && lane == G - 1) bnd[j] = make_uint2(h_last, e_out);
+                };
+                // inputs of this step: from the lane above, or (lane 0) from the boundary row of the chunk above
+                auto inputs = [&](const int step, uint32_t &h_in, uint32_t &e_in) {
                     if (has_top && (step & 31) == 0) {
                         const int idx = step + 32 + lane;
                         nxt = (idx < L) ? __ldcg(bnd + idx) : make_uint2(0, 0);
                     }
-                    uint32_t h_in = __shfl_up_sync(FULL, h_last, 1);
-                    uint32_t e_in = __shfl_up_sync(FULL, e_out, 1);
-                    const uint32_t h_top = __shfl_sync(FULL, cur.x, step & 31);
-                    const uint32_t e_top = __shfl_sync(FULL, cur.y, step & 31);
-                    if (lane == 0) {
-                        h_in = has_top ? h_top : 0;
-                        e_in = has_top ? e_top : 0;
-                    }
+                    const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1), e_sh = __shfl_up_sync(FULL, e_out, 1);
+                    const uint32_t h_top = __shfl_sync(FULL, cur.x, step & 31), e_top = __shfl_sync(FULL, cur.y, step & 31);
+                    h_in = h_sh * nz + h_top * top_on;
+                    e_in = e_sh * nz + e_top * top_on;
                     if ((step & 31) == 31) cur = nxt;
+                };
+                using P0 = std::integral_constant<int, 0>;
+                using P1 = std::integral_constant<int, 1>;
+                auto generic_step = [&](auto parity, const int step) {
+                    uint32_t h_in, e_in;
+                    inputs(step, h_in, e_in);
                     const int j = step - lane;
-                    if (j >= 0 && j < L) {
-                        const int s = cs[j];
-                        const uint4 *tp = tab + (size_t)s * (K4 * G) + lane;
-                        uint32_t diag = h_up_prev;
-                        uint32_t E = e_in;
-#pragma unroll
-                        for (int i4 = 0; i4 < K4; ++i4) {
-                            if (i4 < k4_eff) {
-                                const uint4 w4 = tp[i4 * G];
-                                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-                                uint32_t hp = 0;
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const int i = i4 * 4 + q;
-                                    uint32_t x = O::max3(E, Frow[i], go_s) - go_s;
-                                    uint32_t H = O::addmax(diag, w[q], x);
-                                    diag = Hrow[i];
-                                    E = O::addmax(E, neg_ge, H);
-                                    Frow[i] = O::addmax(Frow[i], neg_ge, H);
-                                    Hrow[i] = H;
-                                    if (q & 1)
-                                        best = O::max3(best, H, hp);
-                                    else
-                                        hp = H;
-                                }
-                                h_last = Hrow[i4 * 4 + 3];
+                    if (j >= 0 && j < L) column(parity, std::false_type{}, j, h_in, e_in, (uint32_t)cs[j]);
+                    h_up_prev = h_in;
+                };
+                auto steady_step = [&](auto parity, auto fullk, const int step) {
+                    uint32_t h_in, e_in;
+                    inputs(step, h_in, e_in);
+                    const int j = step - lane;
+                    column(parity, fullk, j, h_in, e_in, (uint32_t)scs[j]);
+                    h_up_prev = h_in;
+                };
+
+                // segments: ramp [0, G) generic; steady while step + 1 < L (every lane has a column); tail generic
+                const bool fast = p.cols_in_smem != 0;
+                const bool fullk = k4_eff == K4;
+                int seg_end[3] = {fast ? min(G, nsteps) : nsteps, L - 1, nsteps};
+                int step = 0;
+#pragma unroll 1
+                for (int seg = 0; seg < 3; ++seg) {
+                    const int end = seg_end[seg];
+                    if (seg == 1) {
+                        if (fast && fullk) {
+                            for (; step < end; step += 2) {
+                                steady_step(P0{}, std::true_type{}, step);
+                                steady_step(P1{}, std::true_type{}, step + 1);
+                            }
+                        } else if (fast) {
+                            for (; step < end; step += 2) {
+                                steady_step(P0{}, std::false_type{}, step);
+                                steady_step(P1{}, std::false_type{}, step + 1);
                             }
                         }
-                        e_out = E;
-                        if (has_bottom && lane == G - 1) bnd[j] = make_uint2(h_last, e_out);
+                    } else {
+                        for (; step < end; ++step) {
+                            if (step & 1)
+                                generic_step(P1{}, step);
+                            else
+                                generic_step(P0{}, step);
+                        }
                     }
-                    h_up_prev = h_in;
                 }
                 __syncwarp();
             }

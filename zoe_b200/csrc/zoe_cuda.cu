@@ -21,6 +21,7 @@
 #include "sw_align_win.cuh"
 #include "sw_score.cuh"
 #include "sw_score_long.cuh"
+#include "sw_score_rows.cuh"
 
 using namespace zoe_cuda;
 
@@ -489,6 +490,91 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
 
 
 // ---------------------------------------------------------------------------------------------
+// shared-rows score path: the profiled sequence is register-resident (large alphabets, sw_score_rows.cuh)
+// ---------------------------------------------------------------------------------------------
+struct RowsEntry {
+    int K;
+    void (*fn)(const RowsParams);
+};
+const RowsEntry kRowsKernels[] = {
+    {8, sw_score_rows_kernel<32, 8>},   {12, sw_score_rows_kernel<32, 12>}, {16, sw_score_rows_kernel<32, 16>},
+    {18, sw_score_rows_kernel<32, 18>}, {20, sw_score_rows_kernel<32, 20>}, {24, sw_score_rows_kernel<32, 24>},
+    {28, sw_score_rows_kernel<32, 28>}, {32, sw_score_rows_kernel<32, 32>},
+};
+
+bool rows_path_applies(const zoe_cuda_ctx *ctx) {
+    if (getenv("ZOE_CUDA_NO_ROWS_KERNEL")) return false;
+    // a per-task table of n_csym x rows x 4 B starves sw_score_kernel of occupancy for large alphabets; the
+    // transposed kernel needs the profiled sequences to fit one pass and a bounded staging area per warp
+    return ctx->n_csym > 8 && ctx->max_prof_len <= 1024 && ctx->staged_max_len <= 1024 && ctx->staged_max_len >= 64;
+}
+
+int launch_score_rows(zoe_cuda_ctx *ctx, Device &d) {
+    const RowsEntry *k = nullptr;
+    for (const RowsEntry &e : kRowsKernels)
+        if ((uint32_t)(32 * e.K) >= ctx->max_prof_len) {
+            k = &e;
+            break;
+        }
+    if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "profiled sequence too long for the shared-rows kernel");
+    RowsParams rp{};
+    ScoreParams &p = rp.s;
+    p.rseq = d.rseq.as<uint8_t>();
+    p.roff = d.roff.as<uint64_t>();
+    p.task_ids = nullptr;
+    p.n_rseq = (uint32_t)d.n_count;
+    p.n_tasks = (p.n_rseq + 1) / 2;
+    p.ccodes = d.ccodes.as<uint8_t>();
+    p.coff = d.coff.as<uint32_t>();
+    p.n_cseq = ctx->n_prof;
+    p.wk = d.wk.as<int8_t>();
+    p.n_csym = ctx->n_csym;
+    p.S = ctx->S;
+    p.lut = d.lut.as<uint8_t>();
+    p.go = ctx->go;
+    p.ge = ctx->ge;
+    p.ovf_thresh = 32767 - std::max(ctx->max_weight, 0) - 1;
+    p.best = d.best.as<int32_t>();
+    rp.max_rlen = ctx->staged_max_len;
+    const size_t tab = rows_tab_bytes(ctx->S, 32, k->K), stage = rows_stage_bytes(rp.max_rlen);
+    int best_warps = 0, best_threads = 0, best_blocks = 0;
+    size_t best_smem = 0;
+    cudaFuncAttributes fa{};
+    CU(ctx, cudaFuncGetAttributes(&fa, k->fn));
+    for (int threads : {384, 256, 128, 64}) {
+        if (threads > fa.maxThreadsPerBlock) continue;
+        const size_t smem = tab + stage * (threads / 32);
+        if (smem > 227 * 1024) continue;
+        if (cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k->fn, threads, smem) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        if (nb * threads / 32 > best_warps) {
+            best_warps = nb * threads / 32;
+            best_threads = threads;
+            best_blocks = nb;
+            best_smem = smem;
+        }
+    }
+    if (!best_warps) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "shared-rows kernel does not fit shared memory");
+    CU(ctx, cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best_smem));
+    const uint32_t trips = (p.n_tasks + 1) / 2, wpb = best_threads / 32;
+    const uint32_t blocks = std::min<uint32_t>((uint32_t)(d.sm_count * best_blocks), (trips + wpb - 1) / wpb);
+    for (uint32_t cj = 0; cj < ctx->n_prof; ++cj) {
+        rp.cj = cj;
+        k->fn<<<blocks, best_threads, best_smem, d.stream>>>(rp);
+        CU(ctx, cudaGetLastError());
+        ctx->last_launches++;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // long-row score path (rows > kMaxRowsSinglePass): chunked sweeps with a boundary row per warp
 // ---------------------------------------------------------------------------------------------
 constexpr int kLongK = 24;  // rows per lane per chunk: 32 x 24 = 768 rows, 16 warps per SM at DNA alphabet size
@@ -628,7 +714,7 @@ int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
     CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
     int rc;
     if (packed_ok) {
-        rc = launch_score(ctx, d, *k, true, nullptr, 0);
+        rc = rows_path_applies(ctx) ? launch_score_rows(ctx, d) : launch_score(ctx, d, *k, true, nullptr, 0);
         if (rc) return rc;
         if (bound >= (uint64_t)(kPackedLimit - ctx->max_weight - 1)) {
             // escalation: re-run the flagged sequences at 32 bits (or_else_overflowed, output.rs:81-83)
