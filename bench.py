@@ -327,8 +327,22 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     in_bytes = float(h_buf.nbytes + h_offs.nbytes + n * n_prof * 4)
-    if mode == "align":  # one flag byte-ish per cell: 32 B per lane per column for 3x19 rows x 2 sequences
-        in_bytes += float(prof.align_flag_bytes(n, 150))
+    maxlen = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
+    if mode == "score":
+        if matrix.S > 8 and max(len(t) for t in targets) <= 1024 and 64 <= maxlen <= 1024:
+            kname, instr = "sw_score_rows_kernel (profiled sequence in registers, shared table)", "4.5 ALU + 2 FMA-pipe"
+        elif maxlen > 1024:
+            kname, instr = "sw_score_long_kernel (chunked rows, boundary rows through L2)", "4.5 ALU + 1 FMA-pipe"
+        else:
+            kname, instr = "sw_score_kernel (two column streams, ping-pong register sets)", "4.5 ALU + 1 FMA-pipe"
+    else:
+        # checkpointed-window pipeline: checkpoints (2K+2 words x 8 lanes per 128 columns per read pair) plus
+        # ~5 bits per cell of direction flags for the window of each mapped pair (about 150+16+64+8 columns)
+        kname = "sw_align_scan_kernel + sw_align_winfill_kernel (checkpointed window; DESIGN.md 4.3)"
+        instr = "4.5 ALU per cell pair in the scan, 9.5 ALU + 11 FMA-pipe in the window fill"
+        ck = (n / 2) * sum((len(t) - 1) // 128 for t in targets) * 40 * 8 * 4
+        fl = (n * n_prof / 2) * 240 * 8 * 8 * 4
+        in_bytes += float(ck + fl)
     traffic, traffic_source = None, None
     try:  # measured DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"cfg{args.config}/{mode}")
@@ -340,10 +354,9 @@ def main():
         "bound": "alu", "achieved": kernel_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
         "traffic": traffic, "traffic_source": traffic_source,
         "note": ("integer max-plus (DPX on the ALU pipe) bound, not hbm/tensor: peak = live-measured "
-                 "VIADDMNMX.S16x2 issue rate (%.0f G lane-instr/s) / %.2f instr per cell (the score recurrence; the "
-                 "align fill kernel needs 4.75 more ALU instr per cell for its 5 direction bits); kernel = %s, "
-                 "avg of %d steps, CUDA events on the library stream"
-                 % (dpx_g, DPX_INSTR_PER_CELL, "sw_score_kernel" if mode == "score" else "sw_align_fill_kernel", len(dp_ms))),
+                 "VIADDMNMX.S16x2 issue rate (%.0f G lane-instr/s) / %.2f ALU instr per cell (4.5 per packed s16x2 cell "
+                 "pair: the score recurrence); kernel = %s, %s per cell pair; avg of %d steps, CUDA events on the "
+                 "library stream" % (dpx_g, DPX_INSTR_PER_CELL, kname, instr, len(dp_ms))),
         "hbm": {"algorithmic_bytes_per_launch": in_bytes, "achieved_gbs": in_bytes / (float(np.mean(dp_ms)) * 1e-3) / 1e9,
                 "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "frac": in_bytes / (float(np.mean(dp_ms)) * 1e-3) / 1e9 / hbm_peak},
