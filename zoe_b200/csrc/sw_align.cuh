@@ -517,6 +517,22 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
                                        : x.hbuf + (size_t)slot * 4 * x.vcap;
         int32_t *store = load + x.vcap, *es = store + x.vcap, *max_row = es + x.vcap;
         uint8_t *bt = x.fbuf + (size_t)slot * x.fcap;
+        // the flag bytes of the row being computed live in shared memory (the lazy-F pass reads and rewrites them);
+        // a finished row is copied to the per-slot global scratch the traceback reads
+        uint8_t *frow = x.rows_in_smem ? reinterpret_cast<uint8_t *>(ex_smem + (size_t)warps_per_block * 4 * x.vcap) +
+                                             (size_t)(threadIdx.x / 32) * 2 * x.vcap
+                                       : nullptr;
+        // profiled symbol indices and the weight matrix staged in shared memory: the inner loop would otherwise
+        // chain three global loads (residue -> index -> weight) per vector
+        uint8_t *pidx = frow ? frow + x.vcap : nullptr;
+        const int8_t *wmat = x.weights;
+        if (frow) {
+            int8_t *ws = reinterpret_cast<int8_t *>(ex_smem + (size_t)warps_per_block * 4 * x.vcap) +
+                         (size_t)warps_per_block * 2 * x.vcap + (size_t)(threadIdx.x / 32) * 4096;
+            for (int i = lane; i < m; i += 32) pidx[i] = x.lut[P[i]];
+            for (int i = lane; i < x.S * x.S; i += 32) ws[i] = x.weights[i];
+            wmat = ws;
+        }
         for (int i = lane; i < nv * N; i += 32) {
             load[i] = 0;
             store[i] = 0;
@@ -529,7 +545,7 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
 
         for (int r = 0; r < n; ++r) {
             const int ref_index = x.lut[R[r]];
-            const int8_t *wrow = x.weights + ref_index * x.S;
+            const int8_t *wrow = wmat + ref_index * x.S;
             int F[2] = {0, 0}, H[2], rowmax[2] = {0, 0};
             // H = store[nv-1].shift_elements_right(MIN)
 #pragma unroll
@@ -548,14 +564,15 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
                 load = store;
                 store = sw;
             }
-            uint8_t *brow = bt + (size_t)r * nv * N;
+            uint8_t *grow = bt + (size_t)r * nv * N;
+            uint8_t *brow = frow ? frow : grow;
             for (int v = 0; v < nv; ++v) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     int l = lane + 32 * q;
                     if (q < NL && l < N) {
                         int cidx = v + l * nv;
-                        int w = cidx < m ? (int)wrow[x.lut[P[cidx]]] : 0;
+                        int w = cidx < m ? (int)wrow[pidx ? pidx[cidx] : x.lut[P[cidx]]] : 0;
                         int E = es[(size_t)v * N + l];
                         int h = max(H[q] + w, 0);  // saturating_add, floor at MIN
                         h = max(max(h, E), F[q]);
@@ -623,6 +640,17 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
                 if (broke) break;
             }
             __syncwarp();
+            if (frow) {  // publish the finished row
+                const int nb = nv * N;
+                if ((nb & 3) == 0) {
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(frow);
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(grow);
+                    for (int i = lane; i < nb / 4; i += 32) dst[i] = src[i];
+                } else {
+                    for (int i = lane; i < nb; i += 32) grow[i] = frow[i];
+                }
+                __syncwarp();
+            }
             int rb = max(rowmax[0], rowmax[1]);
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) rb = max(rb, __shfl_xor_sync(FULL, rb, d));

@@ -1149,7 +1149,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         if (n_exact > 0) {
             // ---- literal striped emulation for hazard / overflow / gap_open == 0 pairs ----
             const uint32_t slots = (std::min<uint32_t>(n_exact, (uint32_t)d.sm_count * 16) + 3u) & ~3u;  // whole blocks
-            const uint64_t vcap = (uint64_t)ctx->max_prof_len + 64;
+            const uint64_t vcap = ((uint64_t)ctx->max_prof_len + 64 + 3) & ~3ull;  // multiple of 4: rows stay word-aligned
             const uint64_t fcap = (uint64_t)std::max<uint32_t>(ctx->staged_max_len, 1) * vcap;
             CU(ctx, d.ex_hbuf.reserve((size_t)slots * 4 * vcap * sizeof(int32_t)));
             CU(ctx, d.ex_fbuf.reserve((size_t)slots * fcap));
@@ -1185,7 +1185,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             x.cig_cap = cig_cap;
             x.counters = ctr;
             // four warps per block when their H/E rows fit in shared memory, else global scratch
-            const size_t rows_bytes = (size_t)4 * vcap * sizeof(int32_t);
+            // per warp: H/E rows + the current flag row + profiled symbol indices + the weight matrix (<= 64 x 64)
+            const size_t rows_bytes = (size_t)4 * vcap * sizeof(int32_t) + 2 * vcap + 4096;
             x.rows_in_smem = rows_bytes * 4 <= 200 * 1024 ? 1 : 0;
             const size_t ex_smem = x.rows_in_smem ? rows_bytes * 4 : 0;
             if (ex_smem > 48 * 1024)
