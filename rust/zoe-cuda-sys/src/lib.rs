@@ -33,6 +33,8 @@ pub struct zoe_cuda_stats {
     pub unmapped: u64,
     pub rerun_wide: u64,
     pub hazard: u64,
+    pub window_fallback: u64,
+    pub window_redo: u64,
 }
 
 unsafe extern "C" {
@@ -44,6 +46,7 @@ unsafe extern "C" {
         profiled_is_query: c_int,
     ) -> c_int;
     pub fn zoe_cuda_set_lanes(ctx: *mut zoe_cuda_ctx, lanes_i8: c_int, lanes_i16: c_int, lanes_i32: c_int) -> c_int;
+    pub fn zoe_cuda_set_align_options(ctx: *mut zoe_cuda_ctx, mode: c_int, checkpoint_log2: c_int, slack: c_int) -> c_int;
     pub fn zoe_cuda_set_profiled(ctx: *mut zoe_cuda_ctx, concat: *const u8, offsets: *const u64, n: u32) -> c_int;
     pub fn zoe_cuda_sw_score_batch(
         ctx: *mut zoe_cuda_ctx, streamed_concat: *const u8, offsets: *const u64, n: u64, score: *mut u32,
