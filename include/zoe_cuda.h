@@ -112,6 +112,18 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
                             uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
                             uint64_t cigar_cap, uint8_t *hazard);
 
+/* Which of zoe's integer types may report a result (default 8..32 signed = ProfileSets::sw_*_from_i8).
+ *   first_bits..last_bits   8/16/32: the escalation chain starts at first_bits and stops at last_bits:
+ *                 (8,32) = sw_score_from_i8 / sw_align_from_i8, (16,32) = ..._from_i16, (32,32) = ..._from_i32
+ *                 (src/alignment/profile_set.rs:71-179); first == last = a standalone StripedProfile<T,N,S>
+ *                 (src/alignment/profile.rs:440-446, 515-519).  A score beyond last_bits is ZOE_CUDA_OVERFLOWED.
+ *   is_unsigned   1: the u8/u16/u32 profiles zoe builds from a biased matrix (WeightMatrix::to_biased_matrix,
+ *                 src/data/matrices/mod.rs:471-491): a type holds scores <= MAX - bias - 1
+ *                 (score_to_maybe_aligned, src/alignment/sw/striped.rs:608-633); the weights passed to
+ *                 zoe_cuda_set_scoring stay the signed ones, the bias is derived from them.
+ * `tier` outputs report the bit width of the type that produced the result. */
+int zoe_cuda_set_width_policy(zoe_cuda_ctx *ctx, int first_bits, int last_bits, int is_unsigned);
+
 /* Tuning of the align pipeline (results never depend on it).
  *   mode            0 = automatic, 1 = direction bits for the full matrix (what zoe's sw_simd_align stores,
  *                   src/alignment/sw/striped.rs:446-598), 2 = checkpointed window: a score-rate scan parks the

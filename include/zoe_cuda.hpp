@@ -116,6 +116,17 @@ class CudaProfiles {
     size_t n_profiled() const { return targets_.size(); }
 
     // out[i * n_profiled + j] == profiles[j].sw_score_from_i8(&seqs[i])
+    // Which zoe integer types may report a result: (8,32) = sw_*_from_i8 (default), (16,32) = ..._from_i16,
+    // (32,32) = ..._from_i32 (profile_set.rs:71-179); first == last = a standalone StripedProfile<T,N,S>;
+    // is_unsigned = the u8/u16/u32 profiles over the biased matrix (matrices/mod.rs:471-491).
+    void set_width_policy(int first_bits, int last_bits, bool is_unsigned) {
+        check(zoe_cuda_set_width_policy(ctx_, first_bits, last_bits, is_unsigned ? 1 : 0));
+    }
+    // Tuning only (never changes results): 0 auto, 1 full-matrix direction bits, 2 checkpointed window.
+    void set_align_options(int mode, int checkpoint_log2 = 7, int slack = 16) {
+        check(zoe_cuda_set_align_options(ctx_, mode, checkpoint_log2, slack));
+    }
+
     std::vector<MaybeAligned<uint32_t>> sw_score_batch(const std::vector<std::string> &seqs) {
         std::vector<uint8_t> buf;
         std::vector<uint64_t> off;

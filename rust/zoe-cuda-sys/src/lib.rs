@@ -46,6 +46,7 @@ unsafe extern "C" {
         profiled_is_query: c_int,
     ) -> c_int;
     pub fn zoe_cuda_set_lanes(ctx: *mut zoe_cuda_ctx, lanes_i8: c_int, lanes_i16: c_int, lanes_i32: c_int) -> c_int;
+    pub fn zoe_cuda_set_width_policy(ctx: *mut zoe_cuda_ctx, first_bits: c_int, last_bits: c_int, is_unsigned: c_int) -> c_int;
     pub fn zoe_cuda_set_align_options(ctx: *mut zoe_cuda_ctx, mode: c_int, checkpoint_log2: c_int, slack: c_int) -> c_int;
     pub fn zoe_cuda_set_profiled(ctx: *mut zoe_cuda_ctx, concat: *const u8, offsets: *const u64, n: u32) -> c_int;
     pub fn zoe_cuda_sw_score_batch(

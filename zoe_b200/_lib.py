@@ -17,7 +17,7 @@ SYMBOLS = [
     "zoe_cuda_create", "zoe_cuda_destroy", "zoe_cuda_last_error", "zoe_cuda_set_scoring", "zoe_cuda_set_lanes",
     "zoe_cuda_set_profiled", "zoe_cuda_sw_score_batch", "zoe_cuda_sw_align_batch", "zoe_cuda_stage_streamed",
     "zoe_cuda_run_score_staged", "zoe_cuda_run_align_staged", "zoe_cuda_fetch_scores", "zoe_cuda_last_timing",
-    "zoe_cuda_last_stats", "zoe_cuda_dpx_peak", "zoe_cuda_stream", "zoe_cuda_set_align_options",
+    "zoe_cuda_last_stats", "zoe_cuda_dpx_peak", "zoe_cuda_stream", "zoe_cuda_set_align_options", "zoe_cuda_set_width_policy",
 ]
 
 
@@ -53,6 +53,7 @@ def load() -> C.CDLL:
     lib.zoe_cuda_set_scoring.argtypes = [p, C.POINTER(C.c_int8), C.c_int, u8p, C.c_int8, C.c_int8, C.c_int]
     lib.zoe_cuda_set_lanes.argtypes = [p, C.c_int, C.c_int, C.c_int]
     lib.zoe_cuda_set_align_options.argtypes = [p, C.c_int, C.c_int, C.c_int]
+    lib.zoe_cuda_set_width_policy.argtypes = [p, C.c_int, C.c_int, C.c_int]
     lib.zoe_cuda_set_profiled.argtypes = [p, u8p, u64p, C.c_uint32]
     lib.zoe_cuda_sw_score_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p]
     lib.zoe_cuda_sw_align_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p, u32p, u32p, u32p, u32p, u32p,

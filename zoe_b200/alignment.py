@@ -193,6 +193,12 @@ class CudaProfiles:
         """Tuning of the align pipeline (never changes results): see ``zoe_cuda_set_align_options``."""
         self._check(self._lib.zoe_cuda_set_align_options(self._h, mode, checkpoint_log2, slack))
 
+    def set_width_policy(self, first_bits: int = 8, last_bits: int = 32, unsigned: bool = False):
+        """Which zoe integer types may report a result: ``(8, 32)`` = ``sw_*_from_i8`` (default), ``(16, 32)`` =
+        ``..._from_i16``, ``(32, 32)`` = ``..._from_i32`` (profile_set.rs:71-179); ``first == last`` = a standalone
+        ``StripedProfile<T, N, S>``; ``unsigned`` = zoe's u8/u16/u32 profiles over the biased matrix."""
+        self._check(self._lib.zoe_cuda_set_width_policy(self._h, first_bits, last_bits, int(unsigned)))
+
     def _check(self, rc: int):
         if rc == 0:
             return

@@ -309,6 +309,7 @@ struct TraceParams {
     uint32_t *hazard_list;      // global pair ids that need the exact kernel
     int all_exact;              // gap_open == 0: every Some pair goes to the exact kernel
     int only_ambiguous;         // seq_ids mode: redo only the pairs the windowed pipeline marked kAmbiguousEnd
+    TierPolicy tp;
 };
 
 // CIGAR builder writing backwards (the walk runs end -> start, the CIGAR is start -> end).
@@ -347,7 +348,6 @@ struct CigarBack {
     }
 };
 
-__device__ __forceinline__ uint8_t tier_of(uint32_t score) { return score <= 254 ? 8 : (score <= 65534 ? 16 : 32); }
 
 // Emit zoe's Alignment from a completed walk.  (r, c) = 0-based start, (r_end1, c_end1) = exclusive
 // ends, n / m = streamed / profiled lengths.  The walk pushed its ops already (un-inverted letters are
@@ -381,9 +381,17 @@ __global__ void sw_traceback_kernel(const TraceParams t) {
         t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
         return;
     }
+    const uint8_t tier = tier_for(t.tp, (uint32_t)e.best);
+    if (tier == 0) {  // beyond the widest allowed integer type: Overflowed (striped.rs:555-562)
+        t.score[gid] = 0;
+        t.status[gid] = 1;
+        t.tier[gid] = t.tp.last;
+        t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
+        return;
+    }
     t.score[gid] = (uint32_t)e.best;
     t.status[gid] = 0;
-    t.tier[gid] = tier_of((uint32_t)e.best);
+    t.tier[gid] = tier;
     if (t.all_exact) {
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
         t.hazard_list[slot] = (uint32_t)gid;
@@ -487,6 +495,7 @@ struct ExactParams {
     uint32_t *cig_count;
     uint32_t cig_cap;
     unsigned long long *counters;  // [6] cigar overflow, [7] score mismatch (internal check)
+    TierPolicy tp;
 };
 
 // Values are kept in true (un-offset) form: zoe stores x + T::MIN and saturates, so saturation at MIN is a
@@ -506,7 +515,9 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
         const uint8_t *P = x.pbytes + x.coff[cj];
         const int m = (int)(x.coff[cj + 1] - x.coff[cj]);
         const uint32_t want = x.score_in[gid];
-        const int N = want <= 254 ? x.lanes8 : (want <= 65534 ? x.lanes16 : x.lanes32);
+        const uint8_t want_tier = tier_for(x.tp, want);
+        if (want_tier == 0) continue;  // Overflowed in every allowed type: nothing to align (warp-uniform)
+        const int N = want_tier == 8 ? x.lanes8 : (want_tier == 16 ? x.lanes16 : x.lanes32);
         const int nv = (m + N - 1) / N;
         // lane t owns SIMD lanes t and t+32 (N <= 64)
         const int NL = (N + 31) / 32;

@@ -350,6 +350,7 @@ struct ClassifyParams {
     uint32_t *ref_start, *ref_end, *query_start, *query_end, *cig_count;
     unsigned long long *counters;  // [5] exact-list length, [8] packed overflows, [11] ambiguous pairs
     uint32_t *hazard_list;
+    TierPolicy tp;
 };
 
 __global__ void win_classify_kernel(const ClassifyParams t) {
@@ -381,9 +382,18 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         t.ends[gid].aux = kAmbiguousEnd - 1u;
         return;
     }
+    const uint8_t tier = tier_for(t.tp, (uint32_t)e.best);
+    if (tier == 0) {  // beyond the widest allowed integer type: Overflowed
+        t.score[gid] = 0;
+        t.status[gid] = 1;
+        t.tier[gid] = t.tp.last;
+        t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
+        t.ends[gid].aux = kAmbiguousEnd - 1u;
+        return;
+    }
     t.score[gid] = (uint32_t)e.best;
     t.status[gid] = 0;
-    t.tier[gid] = tier_of((uint32_t)e.best);
+    t.tier[gid] = tier;
     if (t.all_exact) {
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
         t.hazard_list[slot] = (uint32_t)gid;

@@ -62,6 +62,21 @@ constexpr int kPackedLimit = kHalfMax ? 0x7C00 : 32767;  // packed lanes are exa
 
 constexpr int kPadWeight = -16384;  // score of a padding row (never wins a max, never wraps)
 
+// Which zoe integer types may report a score (src/alignment/sw/striped.rs:608-633): the chain starts at `first` bits and
+// escalates up to `last` bits (ProfileSets::sw_*_from_i8 / _i16 / _i32, src/alignment/profile_set.rs:71-118; a
+// standalone StripedProfile<T,N,S> is first == last).  lim* = the largest score the tier can report:
+// signed T: 2*MAX (254 / 65534 / 2^32-2); unsigned T with a biased matrix: MAX - bias - 1.
+struct TierPolicy {
+    uint32_t lim8, lim16, lim32;
+    uint8_t first, last;
+};
+__host__ __device__ inline uint8_t tier_for(const TierPolicy &tp, uint32_t score) {  // 0 = Overflowed
+    if (tp.first <= 8 && score <= tp.lim8) return 8;
+    if (tp.first <= 16 && tp.last >= 16 && score <= tp.lim16) return 16;
+    if (tp.last >= 32 && score <= tp.lim32) return 32;
+    return 0;
+}
+
 struct ScoreParams {
     const uint8_t *rseq;       // batch sequences, raw bytes (device)
     const uint64_t *roff;      // n_rseq + 1 offsets into rseq

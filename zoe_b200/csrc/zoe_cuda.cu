@@ -127,6 +127,9 @@ struct zoe_cuda_ctx {
     int profiled_is_query = 0;
     int max_weight = 0;
     int lanes[3] = {32, 16, 8};
+    int bias = 0;                     // |min(0, smallest weight)|: to_biased_matrix, src/data/matrices/mod.rs:448-491
+    int first_bits = 8, last_bits = 32, is_unsigned = 0;
+    TierPolicy tp{254u, 65534u, 4294967294u, 8, 32};
     // profiled
     bool have_profiled = false;
     uint32_t n_prof = 0;
@@ -173,6 +176,24 @@ int fail(zoe_cuda_ctx *ctx, int code, const char *fmt, ...) {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
+// Largest score each allowed integer type can report (striped.rs:608-633): signed T holds best - MIN < MAX - MIN, i.e.
+// score <= 2*MAX; unsigned T with a biased matrix needs best + bias + 1 not to overflow, i.e. score <= MAX - bias - 1.
+void refresh_tier_policy(zoe_cuda_ctx *ctx) {
+    TierPolicy &tp = ctx->tp;
+    if (ctx->is_unsigned) {
+        const uint32_t b = (uint32_t)ctx->bias;
+        tp.lim8 = 255u - b - 1u;
+        tp.lim16 = 65535u - b - 1u;
+        tp.lim32 = 4294967295u - b - 1u;
+    } else {
+        tp.lim8 = 254u;
+        tp.lim16 = 65534u;
+        tp.lim32 = 4294967294u;
+    }
+    tp.first = (uint8_t)ctx->first_bits;
+    tp.last = (uint8_t)ctx->last_bits;
+}
+
 // zoe: validate_profile_args, src/alignment/profile.rs:32-44
 int validate_profile_args(uint64_t len, int gap_open, int gap_extend) {
     if (len == 0) return ZOE_CUDA_E_EMPTY_SEQUENCE;
@@ -185,9 +206,9 @@ int validate_profile_args(uint64_t len, int gap_open, int gap_extend) {
 // score/status/tier from the exact best score: src/alignment/sw/striped.rs:608-633 applied along
 // the escalation chain of src/alignment/profile_set.rs:71-78.
 __global__ void finalize_scores_kernel(const int32_t *best, uint64_t n, uint32_t *score, uint8_t *status,
-                                       uint8_t *tier, unsigned long long *counters) {
+                                       uint8_t *tier, unsigned long long *counters, const TierPolicy tp) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long c8 = 0, c16 = 0, c32 = 0, cun = 0;
+    unsigned long long c8 = 0, c16 = 0, c32 = 0, cun = 0, cov = 0;
     if (i < n) {
         int32_t b = best[i];
         uint32_t s = (uint32_t)b;
@@ -196,15 +217,20 @@ __global__ void finalize_scores_kernel(const int32_t *best, uint64_t n, uint32_t
             s = 0;
             st = ZOE_CUDA_UNMAPPED;  // Unmapped does not escalate: it is decided in the i8 tier
             cun = 1;
-        } else if (b <= 254) {
-            t = 8;
-            c8 = 1;
-        } else if (b <= 65534) {
-            t = 16;
-            c16 = 1;
         } else {
-            t = 32;
-            c32 = 1;
+            t = tier_for(tp, s);
+            if (t == 8) {
+                c8 = 1;
+            } else if (t == 16) {
+                c16 = 1;
+            } else if (t == 32) {
+                c32 = 1;
+            } else {  // beyond the widest allowed integer type
+                s = 0;
+                st = ZOE_CUDA_OVERFLOWED;
+                t = tp.last;
+                cov = 1;
+            }
         }
         score[i] = s;
         status[i] = st;
@@ -216,12 +242,14 @@ __global__ void finalize_scores_kernel(const int32_t *best, uint64_t n, uint32_t
         c16 += __shfl_xor_sync(0xffffffffu, c16, d);
         c32 += __shfl_xor_sync(0xffffffffu, c32, d);
         cun += __shfl_xor_sync(0xffffffffu, cun, d);
+        cov += __shfl_xor_sync(0xffffffffu, cov, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (c8) atomicAdd(&counters[0], c8);
         if (c16) atomicAdd(&counters[1], c16);
         if (c32) atomicAdd(&counters[2], c32);
         if (cun) atomicAdd(&counters[3], cun);
+        if (cov) atomicAdd(&counters[13], cov);
     }
 }
 
@@ -700,7 +728,7 @@ int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
         uint32_t blocks = (uint32_t)((pairs + threads - 1) / threads);
         finalize_scores_kernel<<<blocks, threads, 0, d.stream>>>(d.best.as<int32_t>(), pairs, d.score.as<uint32_t>(),
                                                                  d.status.as<uint8_t>(), d.tier.as<uint8_t>(),
-                                                                 d.counters.as<unsigned long long>());
+                                                                 d.counters.as<unsigned long long>(), ctx->tp);
         CU(ctx, cudaGetLastError());
         ctx->last_launches++;
         return 0;
@@ -745,7 +773,7 @@ int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
         uint32_t blocks = (uint32_t)((pairs + threads - 1) / threads);
         finalize_scores_kernel<<<blocks, threads, 0, d.stream>>>(d.best.as<int32_t>(), pairs, d.score.as<uint32_t>(),
                                                                  d.status.as<uint8_t>(), d.tier.as<uint8_t>(),
-                                                                 d.counters.as<unsigned long long>());
+                                                                 d.counters.as<unsigned long long>(), ctx->tp);
         CU(ctx, cudaGetLastError());
         ctx->last_launches++;
     }
@@ -757,15 +785,16 @@ int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
 // align pipeline (one device): chunks of batch sequences -> fill -> traceback -> exact -> compaction
 // ---------------------------------------------------------------------------------------------
 __global__ void apply_wide_scores_kernel(const uint32_t *list, uint32_t n, const int32_t *best, uint32_t *score,
-                                         uint8_t *status, uint8_t *tier) {
+                                         uint8_t *status, uint8_t *tier, const TierPolicy tp) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t gid = list[i];
     if (status[gid] != 0xFF) return;
     int32_t b = best[gid];
-    score[gid] = b > 0 ? (uint32_t)b : 0u;
-    status[gid] = b > 0 ? ZOE_CUDA_SOME : ZOE_CUDA_UNMAPPED;
-    tier[gid] = b <= 254 ? 8 : (b <= 65534 ? 16 : 32);
+    const uint8_t t = b > 0 ? tier_for(tp, (uint32_t)b) : tp.first;
+    score[gid] = (b > 0 && t) ? (uint32_t)b : 0u;
+    status[gid] = b > 0 ? (t ? ZOE_CUDA_SOME : ZOE_CUDA_OVERFLOWED) : ZOE_CUDA_UNMAPPED;
+    tier[gid] = t ? t : tp.last;
 }
 
 __global__ void collect_wide_range_kernel(const int32_t *best, uint32_t first, uint32_t count, uint32_t n_cseq,
@@ -781,14 +810,16 @@ __global__ void collect_wide_range_kernel(const int32_t *best, uint32_t first, u
     }
 }
 
-__global__ void count_status_kernel(const uint32_t *score, const uint8_t *status, uint64_t n,
+__global__ void count_status_kernel(const uint8_t *tier, const uint8_t *status, uint64_t n,
                                     unsigned long long *counters) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long c8 = 0, c16 = 0, c32 = 0, cun = 0;
+    unsigned long long c8 = 0, c16 = 0, c32 = 0, cun = 0, cov = 0;
     if (i < n) {
         if (status[i] == ZOE_CUDA_SOME) {
-            uint32_t s = score[i];
-            if (s <= 254) c8 = 1; else if (s <= 65534) c16 = 1; else c32 = 1;
+            const uint8_t t = tier[i];
+            if (t == 8) c8 = 1; else if (t == 16) c16 = 1; else c32 = 1;
+        } else if (status[i] == ZOE_CUDA_OVERFLOWED) {
+            cov = 1;
         } else {
             cun = 1;
         }
@@ -798,12 +829,14 @@ __global__ void count_status_kernel(const uint32_t *score, const uint8_t *status
         c16 += __shfl_xor_sync(0xffffffffu, c16, d);
         c32 += __shfl_xor_sync(0xffffffffu, c32, d);
         cun += __shfl_xor_sync(0xffffffffu, cun, d);
+        cov += __shfl_xor_sync(0xffffffffu, cov, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (c8) atomicAdd(&counters[0], c8);
         if (c16) atomicAdd(&counters[1], c16);
         if (c32) atomicAdd(&counters[2], c32);
         if (cun) atomicAdd(&counters[3], cun);
+        if (cov) atomicAdd(&counters[13], cov);
     }
 }
 
@@ -993,6 +1026,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         t.counters = ctr;
         t.hazard_list = d.hazard_list.as<uint32_t>();
         t.all_exact = all_exact ? 1 : 0;
+        t.tp = ctx->tp;
         const uint32_t cpairs = cn * n_prof;
         if (!use_window) {
             sw_traceback_kernel<<<(cpairs + 127) / 128, 128, 0, d.stream>>>(t);
@@ -1039,6 +1073,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             cp.slack = ctx->win_slack;
             cp.nblk = nblk;
             cp.all_exact = all_exact ? 1 : 0;
+            cp.tp = ctx->tp;
             cp.hist = wp.hist;
             cp.best_arr = t.best_arr;
             cp.score = t.score;
@@ -1141,7 +1176,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             rc = launch_score(ctx, d, *k, false, d.wide_ids.as<uint32_t>(), (uint32_t)n_wide);
             if (rc) return rc;
             apply_wide_scores_kernel<<<(n_exact + 255) / 256, 256, 0, d.stream>>>(
-                d.hazard_list.as<uint32_t>(), n_exact, d.best.as<int32_t>(), t.score, t.status, t.tier);
+                d.hazard_list.as<uint32_t>(), n_exact, d.best.as<int32_t>(), t.score, t.status, t.tier, ctx->tp);
             CU(ctx, cudaGetLastError());
             ctx->last_launches += 2;
             ctx->stats.rerun_wide += hc[4];
@@ -1184,6 +1219,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             x.cig_count = t.cig_count;
             x.cig_cap = cig_cap;
             x.counters = ctr;
+            x.tp = ctx->tp;
             // four warps per block when their H/E rows fit in shared memory, else global scratch
             // per warp: H/E rows + the current flag row + profiled symbol indices + the weight matrix (<= 64 x 64)
             const size_t rows_bytes = (size_t)4 * vcap * sizeof(int32_t) + 2 * vcap + 4096;
@@ -1215,7 +1251,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     }
     // tier histogram + totals
     CU(ctx, cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), d.stream));
-    count_status_kernel<<<(uint32_t)((pairs + 255) / 256), 256, 0, d.stream>>>(d.score.as<uint32_t>(), d.status.as<uint8_t>(),
+    count_status_kernel<<<(uint32_t)((pairs + 255) / 256), 256, 0, d.stream>>>(d.tier.as<uint8_t>(), d.status.as<uint8_t>(),
                                                                               pairs, ctr);
     CU(ctx, cudaGetLastError());
     ctx->last_launches++;
@@ -1266,6 +1302,7 @@ int gather_stats(zoe_cuda_ctx *ctx) {
         ctx->stats.tier16 += c[1];
         ctx->stats.tier32 += c[2];
         ctx->stats.unmapped += c[3];
+        ctx->stats.overflowed += c[13];
     }
     ctx->stats.pairs = ctx->staged_n * ctx->n_prof;
     ctx->stats.cells = ctx->staged_cells;
@@ -1350,6 +1387,8 @@ int zoe_cuda_set_scoring(zoe_cuda_ctx *ctx, const int8_t *weights, int S, const 
     ctx->ge = -(int)gap_extend;
     ctx->profiled_is_query = profiled_is_query ? 1 : 0;
     ctx->max_weight = *std::max_element(ctx->weights.begin(), ctx->weights.end());
+    ctx->bias = std::max(0, -(int)*std::min_element(ctx->weights.begin(), ctx->weights.end()));
+    refresh_tier_policy(ctx);
     ctx->have_scoring = true;
     ctx->have_profiled = false;
     ctx->staged = false;
@@ -1363,6 +1402,18 @@ int zoe_cuda_set_lanes(zoe_cuda_ctx *ctx, int lanes_i8, int lanes_i16, int lanes
     ctx->lanes[0] = lanes_i8;
     ctx->lanes[1] = lanes_i16;
     ctx->lanes[2] = lanes_i32;
+    return 0;
+}
+
+int zoe_cuda_set_width_policy(zoe_cuda_ctx *ctx, int first_bits, int last_bits, int is_unsigned) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    auto ok = [](int b) { return b == 8 || b == 16 || b == 32; };
+    if (!ok(first_bits) || !ok(last_bits) || first_bits > last_bits)
+        return fail(ctx, ZOE_CUDA_E_BAD_ARG, "bad width policy (%d..%d bits)", first_bits, last_bits);
+    ctx->first_bits = first_bits;
+    ctx->last_bits = last_bits;
+    ctx->is_unsigned = is_unsigned ? 1 : 0;
+    refresh_tier_policy(ctx);
     return 0;
 }
 
