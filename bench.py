@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--n", type=int, default=None, help="override the number of streamed sequences per GPU")
+    ap.add_argument("--mode", default=None, choices=["score", "align", "ranges"],
+                    help="override the workload's mode (ranges = sw_score_ranges: score + alignment ranges, no traceback matrix)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -200,6 +202,9 @@ def main():
     from zoe_b200 import CudaProfiles
 
     name, matrix, go, ge, targets, (buf, offs), mode = make_workload(args.config, args.n, rank)
+    if args.mode:
+        mode = args.mode
+        name += f" [mode {mode}]"
     if in_process_devices > 1:
         prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, n_devices=in_process_devices)
     else:
@@ -238,7 +243,7 @@ def main():
         return float(t.item())
 
     stream = torch.cuda.ExternalStream(prof.stream_handle(0), device=torch.device("cuda", local_rank))
-    run_staged = prof.run_score_staged if mode == "score" else prof.run_align_staged
+    run_staged = {"score": prof.run_score_staged, "align": prof.run_align_staged, "ranges": prof.run_ranges_staged}[mode]
 
     # ---------------- device-resident leg (`value`) ----------------
     prof.stage(h_buf, h_offs)
@@ -284,6 +289,31 @@ def main():
                "h2d_bytes_per_step": int(h_buf.nbytes + h_offs.nbytes),
                "d2h_bytes_per_step": int(h_score.nbytes + h_status.nbytes + h_tier.nbytes),
                "ms_per_step": e2e_ms / args.steps, "result_checksum": int(h_score.sum(dtype=np.uint64))}
+
+    if mode == "ranges":
+        t_out = {k: torch.empty(n * n_prof, dtype=torch.int32).pin_memory() for k in
+                 ("score", "ref_start", "ref_end", "query_start", "query_end")}
+        t_b = {k: torch.empty(n * n_prof, dtype=torch.uint8).pin_memory() for k in ("status", "tier")}
+        outs = {k: v.numpy().view(np.uint32) for k, v in t_out.items()}
+        outs.update({k: v.numpy() for k, v in t_b.items()})
+        for _ in range(min(args.warmup, 2)):
+            prof.ranges_into(h_buf, h_offs, outs)
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev2.record(stream)
+        for _ in range(args.steps):
+            prof.ranges_into(h_buf, h_offs, outs)
+            launches += prof.last_timing()["kernel_launches"]
+        ev3.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), wall_ms))
+        e2e = {"value": total_cells * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(h_buf.nbytes + h_offs.nbytes),
+               "d2h_bytes_per_step": int(n * n_prof * (5 * 4 + 2)),
+               "ms_per_step": e2e_ms / args.steps,
+               "result_checksum": int(outs["score"].sum(dtype=np.uint64)) ^ int(outs["ref_start"].sum(dtype=np.uint64))}
 
     if mode == "align":
         cap = n * n_prof * 8 + 1024
@@ -335,6 +365,9 @@ def main():
             kname, instr = "sw_score_long_kernel (chunked rows, boundary rows through L2)", "4.5 ALU + 1 FMA-pipe"
         else:
             kname, instr = "sw_score_kernel (two column streams, ping-pong register sets)", "4.5 ALU + 1 FMA-pipe"
+    elif mode == "ranges":
+        kname = "sw_ends_kernel forward + reverse (score + end cell with in-loop best-cell bookkeeping)"
+        instr = "4.5 ALU + 1 FMA-pipe per cell pair plus per-column bookkeeping; the reverse pass covers the truncated matrix"
     else:
         # checkpointed-window pipeline: checkpoints (2K+2 words x 8 lanes per 128 columns per read pair) plus
         # ~5 bits per cell of direction flags for the window of each mapped pair (about 150+16+64+8 columns)
@@ -381,6 +414,28 @@ def main():
         mism = int((g_status != c_status).sum() + (g_score[some] != c_score[some]).sum()
                    + (g_tier[some] != c_tier[some]).sum())
         parity = {"checked_pairs": int(n_sample * n_prof), "mismatches": mism, "against": "cpu port (oracle/zoe_sw_cpu.cpp)"}
+
+    if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "ranges":
+        from oracle import oracle as O
+        sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
+        n_sample = min(n, 600)
+        t0 = time.perf_counter()
+        mism = 0
+        for i in range(n_sample):
+            s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
+            for j, tg in enumerate(targets):
+                rc, score, rr, qr, _ = O.sw_score_ranges_from(bytes(tg), s_i, sc, streamed_is_query=True)
+                k = i * n_prof + j
+                ok = int(outs["status"][k]) == rc
+                if ok and rc == 0:
+                    ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
+                          int(outs["query_start"][k]), int(outs["query_end"][k])) == (score, rr[0], rr[1], qr[0], qr[1])
+                mism += 0 if ok else 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of sw_simd_score_ranges + escalation ({dt:.1f} s); "
+                         "not vectorised -- a checker, not a tuned baseline"}
+        parity = {"checked_pairs": n_sample * n_prof, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c (score, ranges)"}
 
     if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "align":
         from oracle import oracle as O

@@ -112,6 +112,17 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
                             uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
                             uint64_t cigar_cap, uint8_t *hazard);
 
+/* Batched ProfileSets::sw_score_ranges_from_i8 (src/alignment/profile_set.rs:313-322 -> sw_simd_score_ranges,
+ * src/alignment/sw/striped.rs:355-388): score plus the 0-based half-open alignment ranges, without a traceback
+ * matrix (a forward pass finds the end cell, a reverse pass over the truncated, reversed sequences finds the start:
+ * sw_simd_score_ends / sw_simd_score_ends_reverse, striped.rs:153-336).  ref_end / query_end are what
+ * StripedProfile::sw_score_ends reports (profile.rs:456-460).  Ranges follow zoe's output after make_alignment, i.e.
+ * swapped when profiled_is_query == 0 (src/alignment/mod.rs:176-190); they are 0 when status != ZOE_CUDA_SOME.
+ * Streamed sequences up to 1024 residues. */
+int zoe_cuda_sw_score_ranges_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
+                                   uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
+                                   uint32_t *query_start, uint32_t *query_end);
+
 /* Which of zoe's integer types may report a result (default 8..32 signed = ProfileSets::sw_*_from_i8).
  *   first_bits..last_bits   8/16/32: the escalation chain starts at first_bits and stops at last_bits:
  *                 (8,32) = sw_score_from_i8 / sw_align_from_i8, (16,32) = ..._from_i16, (32,32) = ..._from_i32
@@ -142,6 +153,7 @@ int zoe_cuda_set_align_options(zoe_cuda_ctx *ctx, int mode, int checkpoint_log2,
 int zoe_cuda_stage_streamed(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n);
 int zoe_cuda_run_score_staged(zoe_cuda_ctx *ctx);
 int zoe_cuda_run_align_staged(zoe_cuda_ctx *ctx);
+int zoe_cuda_run_ranges_staged(zoe_cuda_ctx *ctx);
 int zoe_cuda_fetch_scores(zoe_cuda_ctx *ctx, uint32_t *score, uint8_t *status, uint8_t *tier);
 
 /* Timing of the most recent batch/staged call, from CUDA events on the library's own streams

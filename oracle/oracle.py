@@ -194,6 +194,30 @@ def sw_align_from(profiled: bytes, streamed: bytes, sc: Scoring, lanes=(32, 16, 
     return rc, (_mk_aln(a, ops, lens) if rc == SOME else None), tier.value
 
 
+def striped_score_ranges(profiled: bytes, streamed: bytes, sc: Scoring, bits: int, lanes: int, signed: bool = True,
+                         streamed_is_query: bool = False):
+    """``StripedProfile::sw_score_ranges(SeqSrc)`` -> (status, score, ref_range, query_range)."""
+    score = C.c_uint32(0)
+    v = [C.c_uint64(0) for _ in range(4)]
+    s = sc.c()
+    rc = lib().zo_striped_score_ranges(_buf(profiled), C.c_uint64(len(profiled)), _buf(streamed),
+                                       C.c_uint64(len(streamed)), C.byref(s), bits, int(signed), lanes,
+                                       int(streamed_is_query), C.byref(score), *[C.byref(x) for x in v])
+    return rc, score.value, (v[0].value, v[1].value), (v[2].value, v[3].value)
+
+
+def sw_score_ranges_from(profiled: bytes, streamed: bytes, sc: Scoring, lanes=(32, 16, 8), first_bits: int = 8,
+                         streamed_is_query: bool = False):
+    """``ProfileSets::sw_score_ranges_from_i{8,16,32}(SeqSrc)`` -> (status, score, ref_range, query_range, tier)."""
+    score, tier = C.c_uint32(0), C.c_int(0)
+    v = [C.c_uint64(0) for _ in range(4)]
+    s = sc.c()
+    rc = lib().zo_sw_score_ranges_from(_buf(profiled), C.c_uint64(len(profiled)), _buf(streamed),
+                                       C.c_uint64(len(streamed)), C.byref(s), first_bits, lanes[0], lanes[1], lanes[2],
+                                       int(streamed_is_query), C.byref(score), *[C.byref(x) for x in v], C.byref(tier))
+    return rc, score.value, (v[0].value, v[1].value), (v[2].value, v[3].value), tier.value
+
+
 def striped_profile(profiled: bytes, sc: Scoring, bits: int, lanes: int, signed: bool = True) -> np.ndarray:
     """The striped profile as an ``[S, nv, N]`` int32 array (profile.rs:270-306)."""
     nv = C.c_int(0)

@@ -469,9 +469,11 @@ static int zo_striped_align_profile(const zo_profile *p, const uint8_t *referenc
     return status;
 }
 
-/* ---- src/alignment/sw/striped.rs:213-336 sw_simd_score_ends_dir::<FORWARD=true> ---- */
-static int zo_striped_score_ends_profile(const zo_profile *p, const uint8_t *reference, uint64_t n, uint32_t *score,
-                                         uint64_t *ref_end, uint64_t *query_end) {
+/* ---- src/alignment/sw/striped.rs:213-336 sw_simd_score_ends_dir::<FORWARD> ----
+ * forward != 0: (ref_idx, query_idx) = exclusive ends; forward == 0: the reference is read back to front, the profile
+ * is expected to be the reversed one, and (ref_idx, query_idx) = inclusive starts (:323-329). */
+static int zo_striped_score_ends_dir(const zo_profile *p, const uint8_t *reference, uint64_t n, int forward,
+                                     uint32_t *score, uint64_t *ref_end, uint64_t *query_end) {
     if (n == 0) return ZO_UNMAPPED;
     const zo_type *t = &p->t;
     const int N = p->N, nv = p->nv;
@@ -486,7 +488,7 @@ static int zo_striped_score_ends_profile(const zo_profile *p, const uint8_t *ref
     uint64_t r_end = n - 1;
     int status = -1;
     for (uint64_t r = 0; r < n; r++) {
-        int ref_index = p->map[reference[r]];
+        int ref_index = p->map[reference[forward ? r : n - 1 - r]]; /* :247 */
         for (int i = 0; i < N; i++) F[i] = min;
         shr(H, store + (size_t)(nv - 1) * N, N, min);
         if (r > 1 && r_end == r - 2) {
@@ -567,11 +569,21 @@ static int zo_striped_score_ends_profile(const zo_profile *p, const uint8_t *ref
             }
         }
         status = zo_score_to_maybe_aligned(p, best, score);
-        *ref_end = r_end + 1;
-        *query_end = c_end + 1;
+        if (forward) { /* :323-329 */
+            *ref_end = r_end + 1;
+            *query_end = c_end + 1;
+        } else {
+            *ref_end = n - 1 - r_end;
+            *query_end = p->seq_len - 1 - c_end;
+        }
     }
     free(buf);
     return status;
+}
+
+static int zo_striped_score_ends_profile(const zo_profile *p, const uint8_t *reference, uint64_t n, uint32_t *score,
+                                         uint64_t *ref_end, uint64_t *query_end) {
+    return zo_striped_score_ends_dir(p, reference, n, 1, score, ref_end, query_end);
 }
 
 /* ---- src/alignment/types/output.rs:396-425 Alignment::invert ---- */
@@ -639,6 +651,65 @@ int zo_striped_score_ends(const uint8_t *profiled, uint64_t m, const uint8_t *st
     *score = 0;
     rc = zo_striped_score_ends_profile(&p, streamed, n, score, ref_end, query_end);
     zo_profile_free(&p);
+    return rc;
+}
+
+/* ---- src/alignment/sw/striped.rs:355-388 sw_simd_score_ranges: forward ends, then the reverse pass over
+ * reference[..ref_end] with the reversed profile of query[..query_end].  StripedProfile::reverse_from_forward
+ * (profile.rs:314-350) equals StripedProfile::new of the reversed prefix (asserted by zoe's own test,
+ * sw/test.rs:197-262), which is how the reversed profile is obtained here.
+ * Output ranges are 0-based half-open; streamed_is_query != 0 <=> SeqSrc::Query(streamed): ranges swapped
+ * (make_alignment, alignment/mod.rs:176-190). ---- */
+int zo_striped_score_ranges(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                            int bits, int is_signed, int lanes, int streamed_is_query, uint32_t *score, uint64_t *ref_start,
+                            uint64_t *ref_end, uint64_t *query_start, uint64_t *query_end) {
+    zo_profile p;
+    int rc = zo_profile_new(&p, profiled, m, sc, bits, is_signed, lanes);
+    if (rc) return rc;
+    *score = 0;
+    uint64_t re = 0, qe = 0;
+    rc = zo_striped_score_ends_profile(&p, streamed, n, score, &re, &qe);
+    zo_profile_free(&p);
+    if (rc != ZO_SOME) return rc;
+    if (qe == 0 || qe > m) return ZO_UNMAPPED; /* reverse_from_forward -> None, :372-374 */
+    uint8_t *rev = (uint8_t *)malloc(qe);
+    for (uint64_t i = 0; i < qe; i++) rev[i] = profiled[qe - 1 - i];
+    zo_profile pr;
+    rc = zo_profile_new(&pr, rev, qe, sc, bits, is_signed, lanes);
+    free(rev);
+    if (rc) return rc;
+    uint32_t score2 = 0;
+    uint64_t rs = 0, qs = 0;
+    rc = zo_striped_score_ends_dir(&pr, streamed, re, 0, &score2, &rs, &qs);
+    zo_profile_free(&pr);
+    if (rc != ZO_SOME) return rc;
+    if (streamed_is_query) {
+        *ref_start = qs;
+        *ref_end = qe;
+        *query_start = rs;
+        *query_end = re;
+    } else {
+        *ref_start = rs;
+        *ref_end = re;
+        *query_start = qs;
+        *query_end = qe;
+    }
+    return score2 == *score ? ZO_SOME : -100; /* debug_assert_eq!(score, score2), :381 */
+}
+
+/* ProfileSets::sw_score_ranges_from_i8 / _i16 / _i32: profile_set.rs:313-359 */
+int zo_sw_score_ranges_from(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                            int first_bits, int lanes8, int lanes16, int lanes32, int streamed_is_query, uint32_t *score,
+                            uint64_t *ref_start, uint64_t *ref_end, uint64_t *query_start, uint64_t *query_end, int *tier) {
+    int bitsv[3] = {8, 16, 32}, lanesv[3] = {lanes8, lanes16, lanes32};
+    int rc = ZO_OVERFLOWED;
+    for (int k = 0; k < 3; k++) {
+        if (bitsv[k] < first_bits) continue;
+        *tier = bitsv[k];
+        rc = zo_striped_score_ranges(profiled, m, streamed, n, sc, bitsv[k], 1, lanesv[k], streamed_is_query, score,
+                                     ref_start, ref_end, query_start, query_end);
+        if (rc != ZO_OVERFLOWED) return rc;
+    }
     return rc;
 }
 

@@ -58,6 +58,12 @@ unsafe extern "C" {
         status: *mut u8, tier: *mut u8, ref_start: *mut u32, ref_end: *mut u32, query_start: *mut u32,
         query_end: *mut u32, cigar: *mut u32, cigar_off: *mut u64, cigar_cap: u64, hazard: *mut u8,
     ) -> c_int;
+    pub fn zoe_cuda_sw_score_ranges_batch(
+        ctx: *mut zoe_cuda_ctx, streamed_concat: *const u8, offsets: *const u64, n: u64, score: *mut u32,
+        status: *mut u8, tier: *mut u8, ref_start: *mut u32, ref_end: *mut u32, query_start: *mut u32,
+        query_end: *mut u32,
+    ) -> c_int;
+    pub fn zoe_cuda_run_ranges_staged(ctx: *mut zoe_cuda_ctx) -> c_int;
     pub fn zoe_cuda_stage_streamed(ctx: *mut zoe_cuda_ctx, streamed_concat: *const u8, offsets: *const u64, n: u64) -> c_int;
     pub fn zoe_cuda_run_score_staged(ctx: *mut zoe_cuda_ctx) -> c_int;
     pub fn zoe_cuda_run_align_staged(ctx: *mut zoe_cuda_ctx) -> c_int;

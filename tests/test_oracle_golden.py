@@ -227,3 +227,23 @@ def test_striped_equals_scalar_random():
             if rc_s == O.SOME:
                 assert a_v.score == a_s.score and a_v.ref_range == a_s.ref_range and a_v.query_range == a_s.query_range
                 assert O.striped_score(p, r, sc, bits, lanes) == (O.SOME, a_s.score)
+
+
+def test_sw_simd_locations_and_ranges():
+    """sw/test.rs:197-262 (sw_simd_locations, sw_simd_ranges) and the doc example profile_set.rs:293-310."""
+    sc = sc_of(W25)
+    for query, reference in [(b"GGGGGGGCCCCCAAAA", b"TTTTTTCCTTTTTTTTCCCCCTTTTT"), (b"CCCCA", b"TAAAA")]:
+        rc_s, aln_scalar = O.scalar_align(query, reference, sc)
+        rc, score, ref_range, query_range = O.striped_score_ranges(query, reference, sc, 8, 8, signed=False)
+        assert rc == rc_s == O.SOME and score == aln_scalar.score
+        assert ref_range == tuple(aln_scalar.ref_range) and query_range == tuple(aln_scalar.query_range)
+        rc_e, s_e, ref_end, query_end = O.striped_score_ends(query, reference, sc, 8, 8, signed=False)
+        assert (rc_e, s_e, ref_end, query_end) == (O.SOME, score, ref_range[1], query_range[1])
+    sc42 = O.Scoring(W42.weights, W42.mapping.index_map, -3, -1)
+    rc, score, ref_range, query_range, tier = O.sw_score_ranges_from(
+        b"CGTTCGCCATAAAGGGGG", b"ATGCATCGATCGATCGATCGATCGATCGATGC", sc42, lanes=(32, 16, 8))
+    assert (rc, score, ref_range, query_range, tier) == (O.SOME, 26, (14, 31), (0, 15), 8)
+    # SeqSrc::Query(streamed): the ranges swap sides (alignment/mod.rs:176-190)
+    rc, score, ref_range, query_range, _ = O.sw_score_ranges_from(
+        b"CGTTCGCCATAAAGGGGG", b"ATGCATCGATCGATCGATCGATCGATCGATGC", sc42, streamed_is_query=True)
+    assert (rc, score, ref_range, query_range) == (O.SOME, 26, (0, 15), (14, 31))

@@ -8,6 +8,7 @@ from .alignment import (  # noqa: F401
     CudaProfiles,
     MaybeAligned,
     ProfileError,
+    ScoreAndRanges,
     SeqSrc,
     ZoeCudaError,
 )

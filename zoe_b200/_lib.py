@@ -18,6 +18,7 @@ SYMBOLS = [
     "zoe_cuda_set_profiled", "zoe_cuda_sw_score_batch", "zoe_cuda_sw_align_batch", "zoe_cuda_stage_streamed",
     "zoe_cuda_run_score_staged", "zoe_cuda_run_align_staged", "zoe_cuda_fetch_scores", "zoe_cuda_last_timing",
     "zoe_cuda_last_stats", "zoe_cuda_dpx_peak", "zoe_cuda_stream", "zoe_cuda_set_align_options", "zoe_cuda_set_width_policy",
+    "zoe_cuda_sw_score_ranges_batch", "zoe_cuda_run_ranges_staged",
 ]
 
 
@@ -58,6 +59,8 @@ def load() -> C.CDLL:
     lib.zoe_cuda_sw_score_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p]
     lib.zoe_cuda_sw_align_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p, u32p, u32p, u32p, u32p, u32p,
                                             u64p, C.c_uint64, u8p]
+    lib.zoe_cuda_sw_score_ranges_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p, u32p, u32p, u32p, u32p]
+    lib.zoe_cuda_run_ranges_staged.argtypes = [p]
     lib.zoe_cuda_stage_streamed.argtypes = [p, u8p, u64p, C.c_uint64]
     lib.zoe_cuda_run_score_staged.argtypes = [p]
     lib.zoe_cuda_run_align_staged.argtypes = [p]

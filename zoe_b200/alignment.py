@@ -113,6 +113,15 @@ class Alignment:
     query_len: int
 
 
+@dataclass(frozen=True)
+class ScoreAndRanges:
+    """zoe's ``ScoreAndRanges<u32>`` (src/alignment/types/output.rs): score + 0-based half-open ranges."""
+
+    score: int
+    ref_range: tuple
+    query_range: tuple
+
+
 _CIGAR_OPS = {0: "M", 1: "I", 2: "D", 4: "S"}
 
 
@@ -315,6 +324,54 @@ class CudaProfiles:
             _p(out["status"], C.c_uint8), _p(out["tier"], C.c_uint8), _p(out["ref_start"], C.c_uint32),
             _p(out["ref_end"], C.c_uint32), _p(out["query_start"], C.c_uint32), _p(out["query_end"], C.c_uint32),
             _p(out["cigar"], C.c_uint32), _p(out["cigar_off"], C.c_uint64), len(out["cigar"]), _p(out["hazard"], C.c_uint8)))
+
+    def ranges_arrays(self, buf: np.ndarray, offs: np.ndarray):
+        """``sw_score_ranges`` for a packed batch: dict of flat arrays (pair index = i*n_profiled+j)."""
+        n = len(offs) - 1
+        pairs = max(n * self.n_profiled, 1)
+        out = {k: np.zeros(pairs, dtype=np.uint32) for k in ("score", "ref_start", "ref_end", "query_start", "query_end")}
+        out.update({k: np.zeros(pairs, dtype=np.uint8) for k in ("status", "tier")})
+        self._check(self._lib.zoe_cuda_sw_score_ranges_batch(
+            self._h, _p(buf, C.c_uint8), _p(offs, C.c_uint64), n, _p(out["score"], C.c_uint32),
+            _p(out["status"], C.c_uint8), _p(out["tier"], C.c_uint8), _p(out["ref_start"], C.c_uint32),
+            _p(out["ref_end"], C.c_uint32), _p(out["query_start"], C.c_uint32), _p(out["query_end"], C.c_uint32)))
+        return out
+
+    def ranges_into(self, buf: np.ndarray, offs: np.ndarray, out: dict):
+        """Like :meth:`ranges_arrays` but into caller-owned (ideally pinned) arrays."""
+        self._check(self._lib.zoe_cuda_sw_score_ranges_batch(
+            self._h, _p(buf, C.c_uint8), _p(offs, C.c_uint64), len(offs) - 1, _p(out["score"], C.c_uint32),
+            _p(out["status"], C.c_uint8), _p(out["tier"], C.c_uint8), _p(out["ref_start"], C.c_uint32),
+            _p(out["ref_end"], C.c_uint32), _p(out["query_start"], C.c_uint32), _p(out["query_end"], C.c_uint32)))
+
+    def run_ranges_staged(self):
+        self._check(self._lib.zoe_cuda_run_ranges_staged(self._h))
+
+    def sw_score_ranges_batch(self, src: "SeqSrc"):
+        """``out[i][j] == profiles[j].sw_score_ranges_from_i8(SeqSrc::X(seqs[i]))`` as
+        ``MaybeAligned[ScoreAndRanges]`` (profile_set.rs:313-322)."""
+        want_pq = src.kind == "Reference"
+        if want_pq != self.profiled_is_query:
+            raise ValueError(
+                f"this CudaProfiles was built with profiled_is_query={self.profiled_is_query}; "
+                f"SeqSrc.{src.kind} needs the opposite orientation")
+        seqs = [bytes(s) for s in src.seq]
+        buf, offs = _pack(seqs)
+        a = self.ranges_arrays(buf, offs)
+        out = []
+        for i in range(len(seqs)):
+            row = []
+            for j in range(self.n_profiled):
+                k = i * self.n_profiled + j
+                st = int(a["status"][k])
+                if st != _lib.SOME:
+                    row.append(self._maybe(st, None))
+                else:
+                    row.append(MaybeAligned.some(ScoreAndRanges(
+                        int(a["score"][k]), (int(a["ref_start"][k]), int(a["ref_end"][k])),
+                        (int(a["query_start"][k]), int(a["query_end"][k])))))
+            out.append(row)
+        return out
 
     def align_flag_bytes(self, n_seqs: int, seq_len: int) -> int:
         """Bytes of direction flags one align pass writes (8 lanes x 32 B per column per sequence pair for <= 152 rows)."""

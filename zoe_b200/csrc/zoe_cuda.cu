@@ -22,6 +22,7 @@
 #include "sw_score.cuh"
 #include "sw_score_long.cuh"
 #include "sw_score_rows.cuh"
+#include "sw_ranges.cuh"
 
 using namespace zoe_cuda;
 
@@ -79,6 +80,7 @@ struct Device {
     DevBuf cig_scratch, cig_count, cig_off, cig_out, ex_hbuf, ex_fbuf, ex_cig, weights;
     // windowed align path (sw_align_win.cuh)
     DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems, redo_flag, redo_ids, redo_flags;
+    DevBuf starts;  // ranges: reverse-pass results
     uint64_t cig_total = 0;
     // long-row score path
     DevBuf long_ids, long_bnd, long_queue;
@@ -95,12 +97,15 @@ struct KernelEntry {
     void (*packed2)(const ScoreParams);  // two column sequences per sweep
     void (*scan)(const WinParams);       // windowed align, pass A
     void (*winfill)(const WinParams);    // windowed align, pass B
+    void (*ends)(const EndsParams);      // score + end cell (ranges), packed
+    void (*ends_wide)(const EndsParams); // ... 32-bit
 };
 
 #define ZK(G, K) \
     KernelEntry {                                                                                          \
         G, K, sw_score_kernel<G, K, true, 1>, sw_score_kernel<G, K, false, 1>, sw_align_fill_kernel<G, K, true>, \
-            sw_score_kernel<G, K, true, 2>, sw_align_scan_kernel<G, K>, sw_align_winfill_kernel<G, K>      \
+            sw_score_kernel<G, K, true, 2>, sw_align_scan_kernel<G, K>, sw_align_winfill_kernel<G, K>,     \
+            sw_ends_kernel<G, K, true>, sw_ends_kernel<G, K, false>                                         \
     }
 
 // Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
@@ -1273,6 +1278,126 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ranges pipeline (one device): forward ends -> bucket by (profiled, c_end) -> reverse ends -> ranges
+// ---------------------------------------------------------------------------------------------
+int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
+    if (d.n_count == 0) return 0;
+    CU(ctx, cudaSetDevice(d.id));
+    if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass)
+        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "streamed sequences longer than %d are not supported by the ranges path yet",
+                    kMaxRowsSinglePass);
+    const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
+    if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
+    const uint32_t n_prof = ctx->n_prof;
+    const size_t pairs = (size_t)d.n_count * n_prof;
+    if (pairs >= 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "too many pairs for one ranges call");
+    // packed 16-bit lanes only when no pair can reach their limit (otherwise everything runs at 32 bits)
+    const uint64_t bound = (uint64_t)std::min<uint32_t>(ctx->staged_max_len, ctx->max_prof_len) * (uint64_t)std::max(ctx->max_weight, 0);
+    const bool packed = bound < (uint64_t)(32767 - std::max(ctx->max_weight, 0) - 1 - ctx->go);
+    void (*fn)(const EndsParams) = packed ? k->ends : k->ends_wide;
+    LaunchPlan plan;
+    int rc = plan_launch(ctx, *k, fn, &plan);
+    if (rc) return rc;
+    CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+
+    const uint32_t key_stride = ctx->max_prof_len;
+    const uint64_t n_keys = (uint64_t)n_prof * key_stride;
+    const uint64_t max_items = pairs + n_keys + 2;
+    CU(ctx, d.ends.reserve(pairs * sizeof(AlignEnd)));
+    CU(ctx, d.starts.reserve(pairs * sizeof(AlignEnd)));
+    for (DevBuf *b : {&d.ref_start, &d.ref_end, &d.query_start, &d.query_end, &d.score})
+        CU(ctx, b->reserve(pairs * sizeof(uint32_t)));
+    CU(ctx, d.status.reserve(pairs));
+    CU(ctx, d.tier.reserve(pairs));
+    CU(ctx, d.win_hist.reserve(n_keys * sizeof(uint32_t)));
+    CU(ctx, d.win_bucket.reserve((n_keys + 1) * sizeof(uint32_t)));
+    CU(ctx, d.win_items.reserve(max_items * sizeof(uint32_t)));
+    CU(ctx, d.win_nitems.reserve(sizeof(uint32_t)));
+    CU(ctx, d.counters.reserve(16 * sizeof(unsigned long long)));
+    CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
+    CU(ctx, cudaMemsetAsync(d.win_hist.p, 0, n_keys * sizeof(uint32_t), d.stream));
+    CU(ctx, cudaMemsetAsync(d.win_items.p, 0xff, max_items * sizeof(uint32_t), d.stream));
+    unsigned long long *ctr = d.counters.as<unsigned long long>();
+
+    EndsParams ep{};
+    ScoreParams &p = ep.s;
+    p.rseq = d.rseq.as<uint8_t>();
+    p.roff = d.roff.as<uint64_t>();
+    p.n_rseq = (uint32_t)d.n_count;
+    p.n_tasks = packed ? (p.n_rseq + 1) / 2 : p.n_rseq;
+    p.ccodes = d.ccodes.as<uint8_t>();
+    p.coff = d.coff.as<uint32_t>();
+    p.n_cseq = n_prof;
+    p.ccodes_bytes = (uint32_t)ctx->ccodes.size();
+    p.cols_in_smem = plan.cols_in_smem;
+    p.wk = d.wk.as<int8_t>();
+    p.n_csym = ctx->n_csym;
+    p.S = ctx->S;
+    p.lut = d.lut.as<uint8_t>();
+    p.go = ctx->go;
+    p.ge = ctx->ge;
+    p.ovf_thresh = 0x7fffffff;  // packed lanes cannot overflow here (static bound above)
+    ep.chunk_first = 0;
+    ep.items = nullptr;
+    ep.n_items = nullptr;
+    ep.ends_in = nullptr;
+    ep.out = d.ends.as<AlignEnd>();
+    const uint32_t gpb = plan.threads / k->G;
+    const uint32_t max_blocks = (uint32_t)(d.sm_count * plan.blocks_per_sm);
+    CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+    fn<<<std::min<uint32_t>(max_blocks, (p.n_tasks + gpb - 1) / gpb), plan.threads, plan.smem, d.stream>>>(ep);
+    CU(ctx, cudaGetLastError());
+
+    RangesParams rp{};
+    rp.ends = d.ends.as<AlignEnd>();
+    rp.starts = d.starts.as<AlignEnd>();
+    rp.roff = p.roff;
+    rp.n_cseq = n_prof;
+    rp.chunk_first = 0;
+    rp.n_slots = (uint32_t)d.n_count;
+    rp.key_stride = key_stride;
+    rp.hist = d.win_hist.as<uint32_t>();
+    rp.score = d.score.as<uint32_t>();
+    rp.status = d.status.as<uint8_t>();
+    rp.tier = d.tier.as<uint8_t>();
+    rp.ref_start = d.ref_start.as<uint32_t>();
+    rp.ref_end = d.ref_end.as<uint32_t>();
+    rp.query_start = d.query_start.as<uint32_t>();
+    rp.query_end = d.query_end.as<uint32_t>();
+    rp.counters = ctr;
+    rp.invert = ctx->profiled_is_query ? 0 : 1;
+    rp.tp = ctx->tp;
+    const uint32_t pb = (uint32_t)((pairs + 255) / 256);
+    ranges_classify_kernel<<<pb, 256, 0, d.stream>>>(rp);
+    CU(ctx, cudaGetLastError());
+    win_bucket_scan_kernel<<<1, 1024, 0, d.stream>>>(rp.hist, (uint32_t)n_keys, d.win_bucket.as<uint32_t>(), d.win_nitems.as<uint32_t>());
+    CU(ctx, cudaGetLastError());
+    ranges_scatter_kernel<<<pb, 256, 0, d.stream>>>(rp, d.win_bucket.as<uint32_t>(), d.win_items.as<uint32_t>());
+    CU(ctx, cudaGetLastError());
+
+    EndsParams er = ep;
+    er.items = d.win_items.as<uint32_t>();
+    er.n_items = d.win_nitems.as<uint32_t>();
+    er.ends_in = d.ends.as<AlignEnd>();
+    er.out = d.starts.as<AlignEnd>();
+    const uint64_t max_tasks = packed ? max_items / 2 : max_items;
+    fn<<<std::min<uint32_t>(max_blocks, (uint32_t)((max_tasks + gpb - 1) / gpb)), plan.threads, plan.smem, d.stream>>>(er);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+    d.timed_kernel = true;
+    ranges_finalize_kernel<<<pb, 256, 0, d.stream>>>(rp);
+    CU(ctx, cudaGetLastError());
+    count_status_kernel<<<pb, 256, 0, d.stream>>>(d.tier.as<uint8_t>(), d.status.as<uint8_t>(), pairs, ctr);
+    CU(ctx, cudaGetLastError());
+    ctx->last_launches += 7;
+    unsigned long long mism = 0;
+    CU(ctx, cudaMemcpyAsync(&mism, ctr + 7, sizeof(mism), cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    if (mism) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: reverse pass disagreed with the forward score on %llu pairs", mism);
+    return 0;
+}
+
 int sync_and_time(zoe_cuda_ctx *ctx) {
     float total = 0.f, dp = 0.f;
     for (Device &d : ctx->devs) {
@@ -1359,7 +1484,7 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.long_ids, &d.long_bnd,
                           &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.redo_flag,
-                          &d.redo_ids, &d.redo_flags})
+                          &d.redo_ids, &d.redo_flags, &d.starts})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
@@ -1624,6 +1749,55 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
     if (n == 0) cigar_off[0] = 0;
     dbg.lap("align: d2h");
     rc = sync_and_time(ctx);
+    if (rc) return rc;
+    return gather_stats(ctx);
+}
+
+int zoe_cuda_sw_score_ranges_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
+                                   uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
+                                   uint32_t *query_start, uint32_t *query_end) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    begin_call(ctx);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    if (rc) return rc;
+    for (Device &d : ctx->devs) {
+        rc = run_ranges_on_device(ctx, d);
+        if (rc) return rc;
+    }
+    for (Device &d : ctx->devs) {
+        if (d.n_count == 0) continue;
+        CU(ctx, cudaSetDevice(d.id));
+        size_t first = (size_t)d.n_first * ctx->n_prof, pairs = (size_t)d.n_count * ctx->n_prof;
+        auto d2h = [&](void *dst, const DevBuf &src, size_t elem) -> cudaError_t {
+            if (!dst) return cudaSuccess;
+            return cudaMemcpyAsync((uint8_t *)dst + first * elem, src.p, pairs * elem, cudaMemcpyDeviceToHost, d.stream);
+        };
+        CU(ctx, d2h(score, d.score, 4));
+        CU(ctx, d2h(status, d.status, 1));
+        CU(ctx, d2h(tier, d.tier, 1));
+        CU(ctx, d2h(ref_start, d.ref_start, 4));
+        CU(ctx, d2h(ref_end, d.ref_end, 4));
+        CU(ctx, d2h(query_start, d.query_start, 4));
+        CU(ctx, d2h(query_end, d.query_end, 4));
+    }
+    rc = sync_and_time(ctx);
+    if (rc) return rc;
+    return gather_stats(ctx);
+}
+
+int zoe_cuda_run_ranges_staged(zoe_cuda_ctx *ctx) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (!ctx->staged) return fail(ctx, ZOE_CUDA_E_STATE, "nothing staged");
+    begin_call(ctx);
+    for (Device &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+    }
+    for (Device &d : ctx->devs) {
+        int rc = run_ranges_on_device(ctx, d);
+        if (rc) return rc;
+    }
+    int rc = sync_and_time(ctx);
     if (rc) return rc;
     return gather_stats(ctx);
 }
