@@ -43,7 +43,7 @@ def test_fastq_ingestion_to_packed_batch():
     assert names == ["r1 desc", "r2"] and bytes(buf) == b"ACGTTTTTTT" and offs.tolist() == [0, 4, 10]
     assert quals == [b"IIII", b"!!!!!!"]
     for bad, msg in [(b"r1\nACGT\n+\nIIII\n", "Missing '@'"), (b"@\nACGT\n+\nIIII\n", "Missing FASTQ header"),
-                     (b"@r\n\n+\nIIII\n", "Missing FASTQ sequence"), (b"@r\nACGT\nIIII\n", "Missing '+' line"),
+                     (b"@r\n\n+\nIIII\n", "Missing FASTQ sequence"), (b"@r\nACGT\nIIII\n", r"Missing '\+' line"),
                      (b"@r\nACGT\n+\n\n", "Missing FASTQ quality"), (b"@r\nACGT\n+\nII\n", "length mismatch")]:
         with pytest.raises(ValueError, match=msg):
             list(read_fastq(bad))
