@@ -37,6 +37,8 @@
 #include <type_traits>
 #include <cuda_runtime.h>
 
+#include "tma_stage.cuh"
+
 namespace zoe_cuda {
 
 // Lane skew of the systolic sweep (columns between neighbouring lanes).  With a skew of 2 the value a lane needs from
@@ -164,7 +166,10 @@ __host__ __device__ inline int score_tab_bytes(int n_csym, int G, int K) { retur
 // instruction-level parallelism available to hide the 4-deep dependent chain per row (the ALU pipe, not the
 // issue slots or the latency, then bounds the kernel).  Column sequences are visited in `corder`
 // (longest first) so the two streams of a pair have similar lengths.
-template <int G, int K, bool PACKED, int NS, bool PP = (NS == 2 && K <= 19)>
+#ifndef ZOE_SCORE_PP
+#define ZOE_SCORE_PP 1
+#endif
+template <int G, int K, bool PACKED, int NS, bool PP = (ZOE_SCORE_PP && NS == 2 && K <= 19)>
 __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_score_kernel(const ScoreParams p) {
     using O = Ops<PACKED>;
     constexpr int K4 = (K + 3) / 4;
@@ -185,8 +190,7 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
 
     for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
     for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
-    if (p.cols_in_smem)
-        for (uint32_t i = tid; i < p.ccodes_bytes; i += blockDim.x) s_cc[i] = p.ccodes[i];
+    if (p.cols_in_smem) stage_with_tma(s_cc, p.ccodes, p.ccodes_bytes);  // one TMA bulk copy per CTA
     __syncthreads();
     const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
 

@@ -51,8 +51,7 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
     uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
     for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
     for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
-    if (p.cols_in_smem)
-        for (uint32_t i = tid; i < p.ccodes_bytes; i += blockDim.x) s_cc[i] = p.ccodes[i];
+    if (p.cols_in_smem) stage_with_tma(s_cc, p.ccodes, p.ccodes_bytes);  // one TMA bulk copy per CTA
     __syncthreads();
     const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
 
