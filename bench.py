@@ -88,7 +88,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -97,7 +97,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [time.time()])
+
+    def window(self, t0: float, t1: float):
+        """Keep only the samples taken inside [t0, t1] (the sampler is started before the warm-up so that the
+        start-up cost of nvidia-smi -- tens of ms of driver lock -- never lands inside the timed region)."""
+        rows = [r for r in self.rows if t0 <= r[-1] <= t1]
+        if rows:
+            self.rows = rows
 
     def stop(self):
         if not self.proc:
@@ -108,6 +115,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        self.rows = [r[:-1] for r in self.rows]
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -177,6 +185,7 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="override the number of streamed sequences per GPU")
     ap.add_argument("--mode", default=None, choices=["score", "align", "ranges"],
                     help="override the workload's mode (ranges = sw_score_ranges: score + alignment ranges, no traceback matrix)")
+    ap.add_argument("--align-opts", default=None, help="mode,checkpoint_log2,slack for zoe_cuda_set_align_options (tuning)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -209,6 +218,8 @@ def main():
         prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, n_devices=in_process_devices)
     else:
         prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, devices=[local_rank])
+    if args.align_opts:
+        prof.set_align_options(*[int(x) for x in args.align_opts.split(",")])
     n = len(offs) - 1
     n_prof = len(targets)
     prof_total = sum(len(t) for t in targets)
@@ -247,14 +258,15 @@ def main():
 
     # ---------------- device-resident leg (`value`) ----------------
     prof.stage(h_buf, h_offs)
-    for _ in range(args.warmup):
-        run_staged()
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        run_staged()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dp_ms, launches = [], 0
+    t_region0 = time.time()
     ev0.record(stream)
     for _ in range(args.steps):
         run_staged()
@@ -263,6 +275,8 @@ def main():
         launches += tm["kernel_launches"]
     ev1.record(stream)
     barrier()
+    if rank == 0:
+        sampler.window(t_region0, time.time())
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     stats = prof.last_stats()
