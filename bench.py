@@ -383,12 +383,12 @@ def main():
         kname = "sw_ends_kernel forward + reverse (score + end cell with in-loop best-cell bookkeeping)"
         instr = "4.5 ALU + 1 FMA-pipe per cell pair plus per-column bookkeeping; the reverse pass covers the truncated matrix"
     else:
-        # checkpointed-window pipeline: checkpoints (2K+2 words x 8 lanes per 128 columns per read pair) plus
-        # ~5 bits per cell of direction flags for the window of each mapped pair (about 150+16+64+8 columns)
+        # checkpointed-window pipeline: checkpoints (2K+2 words x 8 lanes per 64 columns per read pair) plus
+        # ~5 bits per cell of direction flags for the window of each mapped pair (about 150+16+32+8+10 columns)
         kname = "sw_align_scan_kernel + sw_align_winfill_kernel (checkpointed window; DESIGN.md 4.3)"
         instr = "4.5 ALU per cell pair in the scan, 9.5 ALU + 11 FMA-pipe in the window fill"
-        ck = (n / 2) * sum((len(t) - 1) // 128 for t in targets) * 40 * 8 * 4
-        fl = (n * n_prof / 2) * 240 * 8 * 8 * 4
+        ck = (n / 2) * sum((len(t) - 1) // 64 for t in targets) * 40 * 8 * 4
+        fl = (n * n_prof / 2) * 216 * 8 * 8 * 4
         in_bytes += float(ck + fl)
     traffic, traffic_source = None, None
     try:  # measured DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture

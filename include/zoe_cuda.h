@@ -140,7 +140,7 @@ int zoe_cuda_set_width_policy(zoe_cuda_ctx *ctx, int first_bits, int last_bits, 
  *                   src/alignment/sw/striped.rs:446-598), 2 = checkpointed window: a score-rate scan parks the
  *                   DP column every 2^checkpoint_log2 columns, the direction bits are recomputed only for the
  *                   window the traceback can reach
- *   checkpoint_log2 2..16 (default 7: 128 columns)
+ *   checkpoint_log2 2..16 (default 6: 64 columns)
  *   slack           columns kept left of the shortest possible walk (default 16); a walk that needs more
  *                   is redone by the literal kernel and counted in zoe_cuda_stats.window_fallback */
 int zoe_cuda_set_align_options(zoe_cuda_ctx *ctx, int mode, int checkpoint_log2, int slack);

@@ -123,7 +123,7 @@ class CudaProfiles {
         check(zoe_cuda_set_width_policy(ctx_, first_bits, last_bits, is_unsigned ? 1 : 0));
     }
     // Tuning only (never changes results): 0 auto, 1 full-matrix direction bits, 2 checkpointed window.
-    void set_align_options(int mode, int checkpoint_log2 = 7, int slack = 16) {
+    void set_align_options(int mode, int checkpoint_log2 = 6, int slack = 16) {
         check(zoe_cuda_set_align_options(ctx_, mode, checkpoint_log2, slack));
     }
 

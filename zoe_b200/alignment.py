@@ -198,7 +198,7 @@ class CudaProfiles:
 
     ALIGN_AUTO, ALIGN_FULL, ALIGN_WINDOW = 0, 1, 2
 
-    def set_align_options(self, mode: int = 0, checkpoint_log2: int = 7, slack: int = 16):
+    def set_align_options(self, mode: int = 0, checkpoint_log2: int = 6, slack: int = 16):
         """Tuning of the align pipeline (never changes results): see ``zoe_cuda_set_align_options``."""
         self._check(self._lib.zoe_cuda_set_align_options(self._h, mode, checkpoint_log2, slack))
 

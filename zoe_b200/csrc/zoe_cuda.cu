@@ -69,6 +69,7 @@ struct DevBuf {
 struct Device {
     int id = 0;
     int sm_count = 0;
+    size_t free_at_create = 0;  // cudaMemGetInfo is slow (tens of ms on a 180 GB part): asked once
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     // scoring + profiled (replicated on every device)
@@ -153,7 +154,7 @@ struct zoe_cuda_ctx {
     std::vector<uint32_t> staged_len;  // per streamed sequence (only kept when the long-row path is needed)
     uint64_t flag_budget_bytes = 0;  // 0 = auto (a fraction of free device memory)
     int align_mode = 0;              // 0 = auto, 1 = full-matrix flags, 2 = checkpointed window
-    int win_cb_log2 = 7;             // checkpoint spacing (columns), log2
+    int win_cb_log2 = 6;             // checkpoint spacing (columns), log2 (64: measured best on cfg 3, 70.3 vs 73.6 ms at 128)
     uint32_t win_slack = 16;         // columns kept left of the shortest possible walk
     // measurements
     float last_total_ms = 0.f, last_dp_ms = 0.f;
@@ -892,8 +893,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     const uint32_t n_keys = n_prof * nblk;
     const uint64_t win_task_stride = (uint64_t)wmax * k->G * NW;  // words per pass-B task
     // chunk size from the flag-memory budget
-    size_t free_b = 0, total_b = 0;
-    CU(ctx, cudaMemGetInfo(&free_b, &total_b));
+    DebugTimer dbg0;
+    const size_t free_b = d.free_at_create;
     uint64_t budget = ctx->flag_budget_bytes ? ctx->flag_budget_bytes : (uint64_t)(free_b * 0.55);
     budget = std::min<uint64_t>(budget, (uint64_t)48 << 30);
     // bytes per pass-A task (two sequences): full = all flags; window = checkpoints + one window per pair
@@ -907,6 +908,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     CU(ctx, d.flag_base.reserve(n_prof * sizeof(uint64_t)));
     CU(ctx, cudaMemcpyAsync(d.flag_base.p, flag_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
     CU(ctx, cudaStreamSynchronize(d.stream));
+    dbg0.lap("align: flag_base upload");
     CU(ctx, d.ends.reserve(pairs * sizeof(AlignEnd)));
     if (use_window) {
         const uint64_t max_items = chunk_seqs * n_prof + n_keys + 2;  // every bucket rounds up to even
@@ -937,6 +939,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     CU(ctx, d.counters.reserve(16 * sizeof(unsigned long long)));
     CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
     unsigned long long *ctr = d.counters.as<unsigned long long>();
+    dbg0.lap("align: reserves");
     { DebugTimer t; if (t.on) fprintf(stderr, "[zoe_cuda] align: chunk_seqs %llu task_stride %llu words, cig_cap %u\n", (unsigned long long)chunk_seqs, (unsigned long long)task_stride, cig_cap); }
 
     DebugTimer dbg;
@@ -1463,6 +1466,7 @@ int zoe_cuda_create(zoe_cuda_ctx **out, const int *device_ids, int n_devices) {
         d.id = device_ids ? device_ids[k] : k;
         if (d.id < 0 || d.id >= count || cudaSetDevice(d.id) != cudaSuccess ||
             cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.id) != cudaSuccess ||
+            [&] { size_t tot = 0; return cudaMemGetInfo(&d.free_at_create, &tot); }() != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&d.ev_begin) != cudaSuccess || cudaEventCreate(&d.ev_end) != cudaSuccess ||
             cudaEventCreate(&d.ev_k0) != cudaSuccess || cudaEventCreate(&d.ev_k1) != cudaSuccess) {
