@@ -14,7 +14,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sw_align.cuh"
@@ -158,8 +161,9 @@ struct zoe_cuda_ctx {
     uint32_t win_slack = 16;         // columns kept left of the shortest possible walk
     // measurements
     float last_total_ms = 0.f, last_dp_ms = 0.f;
-    uint32_t last_launches = 0;
+    std::atomic<uint32_t> last_launches{0};
     zoe_cuda_stats stats{};
+    std::mutex mu;  // guards err / stats / last_dp_ms when the devices of one call are driven by parallel host threads
 };
 
 namespace {
@@ -170,7 +174,10 @@ int fail(zoe_cuda_ctx *ctx, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->err = buf;
+    }
     return code;
 }
 
@@ -709,7 +716,10 @@ int run_score_long_on_device(zoe_cuda_ctx *ctx, Device &d) {
             if (n_wide) {
                 rc = launch_score_long<false>(ctx, d, d.wide_ids.as<uint32_t>(), (uint32_t)n_wide);
                 if (rc) return rc;
-                ctx->stats.rerun_wide += n_wide * ctx->n_prof;
+                {
+                    std::lock_guard<std::mutex> lk(ctx->mu);
+                    ctx->stats.rerun_wide += n_wide * ctx->n_prof;
+                }
             }
         }
     } else {
@@ -765,7 +775,10 @@ int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
             if (n_wide) {
                 rc = launch_score(ctx, d, *k, false, d.wide_ids.as<uint32_t>(), (uint32_t)n_wide);
                 if (rc) return rc;
-                ctx->stats.rerun_wide += n_wide * ctx->n_prof;
+                {
+                    std::lock_guard<std::mutex> lk(ctx->mu);
+                    ctx->stats.rerun_wide += n_wide * ctx->n_prof;
+                }
             }
         }
     } else {
@@ -1187,7 +1200,10 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                 d.hazard_list.as<uint32_t>(), n_exact, d.best.as<int32_t>(), t.score, t.status, t.tier, ctx->tp);
             CU(ctx, cudaGetLastError());
             ctx->last_launches += 2;
-            ctx->stats.rerun_wide += hc[4];
+            {
+                std::lock_guard<std::mutex> lk(ctx->mu);
+                ctx->stats.rerun_wide += hc[4];
+            }
         }
         if (n_exact > 0) {
             // ---- literal striped emulation for hazard / overflow / gap_open == 0 pairs ----
@@ -1238,7 +1254,10 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             sw_align_exact_kernel<<<slots / 4, 128, ex_smem, d.stream>>>(x);
             CU(ctx, cudaGetLastError());
             ctx->last_launches++;
-            ctx->stats.hazard += n_exact - hc[4];
+            {
+                std::lock_guard<std::mutex> lk(ctx->mu);
+                ctx->stats.hazard += n_exact - hc[4];
+            }
         }
         // ---- CIGAR compaction, chained through the device-side running base ctr[9] ----
         cigar_scan_kernel<<<1, 1024, 0, d.stream>>>(t.cig_count, (uint64_t)c0 * n_prof, cpairs, d.cig_off.as<uint64_t>(),
@@ -1269,13 +1288,16 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     CU(ctx, cudaMemcpyAsync(&cig_ovf, ctr + 6, sizeof(cig_ovf), cudaMemcpyDeviceToHost, d.stream));
     CU(ctx, cudaMemcpyAsync(win_fb, ctr + 10, sizeof(win_fb), cudaMemcpyDeviceToHost, d.stream));
     CU(ctx, cudaStreamSynchronize(d.stream));
-    ctx->stats.window_fallback += win_fb[0];
-    ctx->stats.window_redo += win_fb[1];
-    ctx->stats.hazard -= std::min<uint64_t>(ctx->stats.hazard, win_fb[0]);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->stats.window_fallback += win_fb[0];
+        ctx->stats.window_redo += win_fb[1];
+        ctx->stats.hazard -= std::min<uint64_t>(ctx->stats.hazard, win_fb[0]);
+        ctx->last_dp_ms = std::max(ctx->last_dp_ms, dp_ms_total);
+    }
     dbg.lap("align: compaction+tail");
     d.cig_total = tail[2];
     d.timed_kernel = false;  // several fill launches: report their sum instead of one event pair
-    ctx->last_dp_ms = std::max(ctx->last_dp_ms, dp_ms_total);
     if (tail[0]) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: literal kernel disagreed with the fill score on %llu pairs", tail[0]);
     if (cig_ovf) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: CIGAR scratch overflow on %llu pairs", cig_ovf);
     return 0;
@@ -1398,6 +1420,21 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
     CU(ctx, cudaMemcpyAsync(&mism, ctr + 7, sizeof(mism), cudaMemcpyDeviceToHost, d.stream));
     CU(ctx, cudaStreamSynchronize(d.stream));
     if (mism) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: reverse pass disagreed with the forward score on %llu pairs", mism);
+    return 0;
+}
+
+// Drives every device of the context with `fn`.  The align and ranges pipelines synchronise with the host between
+// their stages, so with several devices in one process each device gets its own host thread (the streams alone
+// would serialise the devices); a single device runs inline.
+template <class Fn>
+int for_each_device(zoe_cuda_ctx *ctx, Fn fn) {
+    if (ctx->devs.size() == 1) return fn(ctx->devs[0]);
+    std::vector<int> rcs(ctx->devs.size(), 0);
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < ctx->devs.size(); ++k) th.emplace_back([&, k] { rcs[k] = fn(ctx->devs[k]); });
+    for (std::thread &t : th) t.join();
+    for (int rc : rcs)
+        if (rc) return rc;
     return 0;
 }
 
@@ -1645,11 +1682,9 @@ int zoe_cuda_run_align_staged(zoe_cuda_ctx *ctx) {
         CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
     }
     // generous device-side CIGAR capacity: 8 words per pair (typical CIGARs have <= 5 entries)
-    for (Device &d : ctx->devs) {
-        int rc = run_align_on_device(ctx, d, (uint64_t)d.n_count * ctx->n_prof * 8 + 1024);
-        if (rc) return rc;
-    }
-    int rc = sync_and_time(ctx);
+    int rc = for_each_device(ctx, [&](Device &d) { return run_align_on_device(ctx, d, (uint64_t)d.n_count * ctx->n_prof * 8 + 1024); });
+    if (rc) return rc;
+    rc = sync_and_time(ctx);
     if (rc) return rc;
     return gather_stats(ctx);
 }
@@ -1709,10 +1744,8 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
     int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
     if (rc) return rc;
     dbg.lap("align: stage");
-    for (Device &d : ctx->devs) {
-        rc = run_align_on_device(ctx, d, cigar_cap);
-        if (rc) return rc;
-    }
+    rc = for_each_device(ctx, [&](Device &d) { return run_align_on_device(ctx, d, cigar_cap); });
+    if (rc) return rc;
     dbg.lap("align: run_align_on_device");
     // CIGAR offsets: device-local running sums -> global offsets (devices own contiguous index ranges)
     uint64_t total = 0;
@@ -1764,10 +1797,8 @@ int zoe_cuda_sw_score_ranges_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_co
     begin_call(ctx);
     int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
     if (rc) return rc;
-    for (Device &d : ctx->devs) {
-        rc = run_ranges_on_device(ctx, d);
-        if (rc) return rc;
-    }
+    rc = for_each_device(ctx, [&](Device &d) { return run_ranges_on_device(ctx, d); });
+    if (rc) return rc;
     for (Device &d : ctx->devs) {
         if (d.n_count == 0) continue;
         CU(ctx, cudaSetDevice(d.id));
@@ -1797,11 +1828,9 @@ int zoe_cuda_run_ranges_staged(zoe_cuda_ctx *ctx) {
         CU(ctx, cudaSetDevice(d.id));
         CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
     }
-    for (Device &d : ctx->devs) {
-        int rc = run_ranges_on_device(ctx, d);
-        if (rc) return rc;
-    }
-    int rc = sync_and_time(ctx);
+    int rc = for_each_device(ctx, [&](Device &d) { return run_ranges_on_device(ctx, d); });
+    if (rc) return rc;
+    rc = sync_and_time(ctx);
     if (rc) return rc;
     return gather_stats(ctx);
 }
@@ -1810,7 +1839,7 @@ int zoe_cuda_last_timing(const zoe_cuda_ctx *ctx, float *total_ms, float *dp_ker
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     if (total_ms) *total_ms = ctx->last_total_ms;
     if (dp_kernel_ms) *dp_kernel_ms = ctx->last_dp_ms;
-    if (kernel_launches) *kernel_launches = ctx->last_launches;
+    if (kernel_launches) *kernel_launches = ctx->last_launches.load();
     return 0;
 }
 
