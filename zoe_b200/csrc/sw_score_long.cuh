@@ -29,6 +29,10 @@ struct LongParams {
     unsigned int *queue;     // dynamic task counter (zeroed before launch)
 };
 
+// Lane skew of this kernel.  Measured on cfg 4 (20k reads): skew 1 = 5.79 TCUPS, skew 2 = 5.57 -- unlike the two-stream
+// score kernel, the extra pending registers cost more here than the hidden shuffle latency gains.
+constexpr int kSkewLong = 1;
+
 template <int K, bool PACKED>
 __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp) {
     using O = Ops<PACKED>;
@@ -130,7 +134,10 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
                 uint32_t h_last = 0, e_out = 0, h_up_prev = 0;
                 uint2 cur = make_uint2(0, 0), nxt = make_uint2(0, 0);
                 if (has_top && lane < L) cur = __ldcg(bnd + lane);
-                const int nsteps = L + G - 1;
+                // lane skew of 2 (as in sw_score.cuh): what a lane needs from the lane above was produced two steps
+                // earlier and shuffled during the previous step, so consecutive steps are independent chains
+                uint32_t pend_h = 0, pend_e = 0;
+                const int nsteps = L + kSkewLong * (G - 1);
                 const uint32_t top_on = has_top ? 1u - nz : 0u;  // 1 on lane 0 of a chunk that has a chunk above it
 
                 // one column: FULLK = all K rows (a full chunk), else only the first k4_eff 4-row blocks
@@ -174,8 +181,15 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
                     }
                     const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1), e_sh = __shfl_up_sync(FULL, e_out, 1);
                     const uint32_t h_top = __shfl_sync(FULL, cur.x, step & 31), e_top = __shfl_sync(FULL, cur.y, step & 31);
-                    h_in = h_sh * nz + h_top * top_on;
-                    e_in = e_sh * nz + e_top * top_on;
+                    if (kSkewLong == 1) {
+                        h_in = h_sh * nz + h_top * top_on;
+                        e_in = e_sh * nz + e_top * top_on;
+                    } else {  // lane 0's boundary entry belongs to THIS step's column (lane 0: j == step)
+                        h_in = pend_h * nz + h_top * top_on;
+                        e_in = pend_e * nz + e_top * top_on;
+                        pend_h = h_sh;
+                        pend_e = e_sh;
+                    }
                     if ((step & 31) == 31) cur = nxt;
                 };
                 using P0 = std::integral_constant<int, 0>;
@@ -183,14 +197,14 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
                 auto generic_step = [&](auto parity, const int step) {
                     uint32_t h_in, e_in;
                     inputs(step, h_in, e_in);
-                    const int j = step - lane;
+                    const int j = step - kSkewLong * lane;
                     if (j >= 0 && j < L) column(parity, std::false_type{}, j, h_in, e_in, (uint32_t)cs[j]);
                     h_up_prev = h_in;
                 };
                 auto steady_step = [&](auto parity, auto fullk, const int step) {
                     uint32_t h_in, e_in;
                     inputs(step, h_in, e_in);
-                    const int j = step - lane;
+                    const int j = step - kSkewLong * lane;
                     column(parity, fullk, j, h_in, e_in, (uint32_t)scs[j]);
                     h_up_prev = h_in;
                 };
@@ -198,7 +212,7 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
                 // segments: ramp [0, G) generic; steady while step + 1 < L (every lane has a column); tail generic
                 const bool fast = p.cols_in_smem != 0;
                 const bool fullk = k4_eff == K4;
-                int seg_end[3] = {fast ? min(G, nsteps) : nsteps, L - 1, nsteps};
+                int seg_end[3] = {fast ? min(kSkewLong * G, nsteps) : nsteps, L - 1, nsteps};
                 int step = 0;
 #pragma unroll 1
                 for (int seg = 0; seg < 3; ++seg) {
