@@ -75,6 +75,8 @@ struct Device {
     size_t free_at_create = 0;  // cudaMemGetInfo is slow (tens of ms on a 180 GB part): asked once
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaStream_t stream2 = nullptr;  // the literal kernel overlaps the full-matrix redo stage on this one
+    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
     // scoring + profiled (replicated on every device)
     DevBuf ccodes, coff, wk, lut, corder;
     // batch state
@@ -1048,6 +1050,63 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         t.hazard_list = d.hazard_list.as<uint32_t>();
         t.all_exact = all_exact ? 1 : 0;
         t.tp = ctx->tp;
+        // ---- literal striped emulation for hazard / overflow / gap_open == 0 pairs: list[first, first + count) ----
+        auto launch_exact = [&](uint32_t first, uint32_t count, uint32_t total_hint, cudaStream_t stream) -> int {
+            const uint32_t slots = (std::min<uint32_t>(std::max(count, 1u), (uint32_t)d.sm_count * 16) + 3u) & ~3u;  // whole blocks
+            const uint64_t vcap = ((uint64_t)ctx->max_prof_len + 64 + 3) & ~3ull;  // multiple of 4: rows stay word-aligned
+            const uint64_t fcap = (uint64_t)std::max<uint32_t>(ctx->staged_max_len, 1) * vcap;
+            // scratch: two disjoint slot regions (always both reserved, so nothing is reallocated while a launch on
+            // the second stream is in flight); the CIGAR rows of every listed pair must survive until the gather
+            const uint32_t region = (uint32_t)d.sm_count * 16 + 4;
+            const uint32_t slot_base = first ? region : 0;
+            CU(ctx, d.ex_hbuf.reserve((size_t)2 * region * 4 * vcap * sizeof(int32_t)));
+            CU(ctx, d.ex_fbuf.reserve((size_t)2 * region * fcap));
+            CU(ctx, d.ex_cig.reserve((size_t)std::max(total_hint, first + count) * cig_cap * sizeof(uint32_t)));
+            ExactParams x{};
+            x.pair_ids = d.hazard_list.as<uint32_t>() + first;
+            x.n_pairs = count;
+            x.rseq = p.rseq;
+            x.roff = p.roff;
+            x.pbytes = d.pbytes.as<uint8_t>();
+            x.coff = p.coff;
+            x.n_cseq = n_prof;
+            x.weights = d.weights.as<int8_t>();
+            x.S = ctx->S;
+            x.lut = p.lut;
+            x.go = ctx->go;
+            x.ge = ctx->ge;
+            x.lanes8 = ctx->lanes[0];
+            x.lanes16 = ctx->lanes[1];
+            x.lanes32 = ctx->lanes[2];
+            x.invert = invert;
+            x.hbuf = d.ex_hbuf.as<int32_t>() + (size_t)slot_base * 4 * vcap;
+            x.fbuf = d.ex_fbuf.as<uint8_t>() + (size_t)slot_base * fcap;
+            x.vcap = vcap;
+            x.fcap = fcap;
+            x.score_in = t.score;
+            x.ref_start = t.ref_start;
+            x.ref_end = t.ref_end;
+            x.query_start = t.query_start;
+            x.query_end = t.query_end;
+            x.cig_scratch = d.ex_cig.as<uint32_t>() + (size_t)first * cig_cap;
+            x.cig_count = t.cig_count;
+            x.cig_cap = cig_cap;
+            x.counters = ctr;
+            x.tp = ctx->tp;
+            // four warps per block when their H/E rows fit in shared memory, else global scratch
+            // per warp: H/E rows + the current flag row + profiled symbol indices + the weight matrix (<= 64 x 64)
+            const size_t rows_bytes = (size_t)4 * vcap * sizeof(int32_t) + 2 * vcap + 4096;
+            x.rows_in_smem = rows_bytes * 4 <= 200 * 1024 ? 1 : 0;
+            const size_t ex_smem = x.rows_in_smem ? rows_bytes * 4 : 0;
+            if (ex_smem > 48 * 1024)
+                CU(ctx, cudaFuncSetAttribute(sw_align_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+            sw_align_exact_kernel<<<slots / 4, 128, ex_smem, stream>>>(x);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+            return 0;
+        };
+        uint32_t exact_done = 0;  // pairs already handed to the literal kernel on the second stream
+
         const uint32_t cpairs = cn * n_prof;
         if (!use_window) {
             sw_traceback_kernel<<<(cpairs + 127) / 128, 128, 0, d.stream>>>(t);
@@ -1139,9 +1198,21 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             CU(ctx, cudaGetLastError());
             ctx->last_launches += 7;
             // ---- sequences with an ambiguous end cell: the full-matrix pipeline on that (short) list ----
-            unsigned long long n_redo = 0;
+            unsigned long long n_redo = 0, early[4] = {0, 0, 0, 0};  // ctr[5] exact-list length .. ctr[8] packed overflows
             CU(ctx, cudaMemcpyAsync(&n_redo, ctr + 12, sizeof(n_redo), cudaMemcpyDeviceToHost, d.stream));
+            CU(ctx, cudaMemcpyAsync(early, ctr + 5, sizeof(early), cudaMemcpyDeviceToHost, d.stream));
             CU(ctx, cudaStreamSynchronize(d.stream));
+            if (n_redo && early[0] && early[3] == 0) {
+                // the hazards found so far run on the second stream while the redo stage occupies the first
+                // (the literal kernel is latency-bound: a handful of warps for milliseconds)
+                CU(ctx, cudaEventRecord(d.ev_x0, d.stream));
+                CU(ctx, cudaStreamWaitEvent(d.stream2, d.ev_x0, 0));
+                // every pair of a redone sequence may still join the list: reserve its CIGAR rows now
+                rc = launch_exact(0, (uint32_t)early[0], (uint32_t)std::min<uint64_t>(cpairs, early[0] + n_redo * n_prof), d.stream2);
+                if (rc) return rc;
+                CU(ctx, cudaEventRecord(d.ev_x1, d.stream2));
+                exact_done = (uint32_t)early[0];
+            }
             if (n_redo) {
                 LaunchPlan plan_f;
                 rc = plan_launch(ctx, *k, k->fill, &plan_f);
@@ -1158,7 +1229,10 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                     fa.s.cols_in_smem = plan_f.cols_in_smem;
                     fa.flags = d.redo_flags.as<uint32_t>();
                     const uint32_t gpb = plan_f.threads / k->G;
-                    const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_f.blocks_per_sm), (fa.s.n_tasks + gpb - 1) / gpb);
+                    // leave one SM to the literal kernel running on the second stream (its block needs > 100 KB of
+                    // shared memory and could not co-reside with a fill block)
+                    const int sms_for_fill = exact_done ? std::max(1, d.sm_count - 1) : d.sm_count;
+                    const uint32_t nb = std::min<uint32_t>((uint32_t)(sms_for_fill * plan_f.blocks_per_sm), (fa.s.n_tasks + gpb - 1) / gpb);
                     k->fill<<<nb, plan_f.threads, plan_f.smem, d.stream>>>(fa);
                     CU(ctx, cudaGetLastError());
                     TraceParams tr = t;
@@ -1205,59 +1279,14 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                 ctx->stats.rerun_wide += hc[4];
             }
         }
+        if (exact_done) CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_x1, 0));
+        if (n_exact > exact_done) {
+            rc = launch_exact(exact_done, n_exact - exact_done, n_exact, d.stream);
+            if (rc) return rc;
+        }
         if (n_exact > 0) {
-            // ---- literal striped emulation for hazard / overflow / gap_open == 0 pairs ----
-            const uint32_t slots = (std::min<uint32_t>(n_exact, (uint32_t)d.sm_count * 16) + 3u) & ~3u;  // whole blocks
-            const uint64_t vcap = ((uint64_t)ctx->max_prof_len + 64 + 3) & ~3ull;  // multiple of 4: rows stay word-aligned
-            const uint64_t fcap = (uint64_t)std::max<uint32_t>(ctx->staged_max_len, 1) * vcap;
-            CU(ctx, d.ex_hbuf.reserve((size_t)slots * 4 * vcap * sizeof(int32_t)));
-            CU(ctx, d.ex_fbuf.reserve((size_t)slots * fcap));
-            CU(ctx, d.ex_cig.reserve((size_t)n_exact * cig_cap * sizeof(uint32_t)));
-            ExactParams x{};
-            x.pair_ids = d.hazard_list.as<uint32_t>();
-            x.n_pairs = n_exact;
-            x.rseq = p.rseq;
-            x.roff = p.roff;
-            x.pbytes = d.pbytes.as<uint8_t>();
-            x.coff = p.coff;
-            x.n_cseq = n_prof;
-            x.weights = d.weights.as<int8_t>();
-            x.S = ctx->S;
-            x.lut = p.lut;
-            x.go = ctx->go;
-            x.ge = ctx->ge;
-            x.lanes8 = ctx->lanes[0];
-            x.lanes16 = ctx->lanes[1];
-            x.lanes32 = ctx->lanes[2];
-            x.invert = invert;
-            x.hbuf = d.ex_hbuf.as<int32_t>();
-            x.fbuf = d.ex_fbuf.as<uint8_t>();
-            x.vcap = vcap;
-            x.fcap = fcap;
-            x.score_in = t.score;
-            x.ref_start = t.ref_start;
-            x.ref_end = t.ref_end;
-            x.query_start = t.query_start;
-            x.query_end = t.query_end;
-            x.cig_scratch = d.ex_cig.as<uint32_t>();
-            x.cig_count = t.cig_count;
-            x.cig_cap = cig_cap;
-            x.counters = ctr;
-            x.tp = ctx->tp;
-            // four warps per block when their H/E rows fit in shared memory, else global scratch
-            // per warp: H/E rows + the current flag row + profiled symbol indices + the weight matrix (<= 64 x 64)
-            const size_t rows_bytes = (size_t)4 * vcap * sizeof(int32_t) + 2 * vcap + 4096;
-            x.rows_in_smem = rows_bytes * 4 <= 200 * 1024 ? 1 : 0;
-            const size_t ex_smem = x.rows_in_smem ? rows_bytes * 4 : 0;
-            if (ex_smem > 48 * 1024)
-                CU(ctx, cudaFuncSetAttribute(sw_align_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-            sw_align_exact_kernel<<<slots / 4, 128, ex_smem, d.stream>>>(x);
-            CU(ctx, cudaGetLastError());
-            ctx->last_launches++;
-            {
-                std::lock_guard<std::mutex> lk(ctx->mu);
-                ctx->stats.hazard += n_exact - hc[4];
-            }
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            ctx->stats.hazard += n_exact - hc[4];
         }
         // ---- CIGAR compaction, chained through the device-side running base ctr[9] ----
         cigar_scan_kernel<<<1, 1024, 0, d.stream>>>(t.cig_count, (uint64_t)c0 * n_prof, cpairs, d.cig_off.as<uint64_t>(),
@@ -1506,7 +1535,10 @@ int zoe_cuda_create(zoe_cuda_ctx **out, const int *device_ids, int n_devices) {
             [&] { size_t tot = 0; return cudaMemGetInfo(&d.free_at_create, &tot); }() != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&d.ev_begin) != cudaSuccess || cudaEventCreate(&d.ev_end) != cudaSuccess ||
-            cudaEventCreate(&d.ev_k0) != cudaSuccess || cudaEventCreate(&d.ev_k1) != cudaSuccess) {
+            cudaEventCreate(&d.ev_k0) != cudaSuccess || cudaEventCreate(&d.ev_k1) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.ev_x0, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&d.ev_x1, cudaEventDisableTiming) != cudaSuccess) {
             delete ctx;
             return ZOE_CUDA_E_CUDA;
         }
@@ -1531,6 +1563,9 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.ev_k0) cudaEventDestroy(d.ev_k0);
         if (d.ev_k1) cudaEventDestroy(d.ev_k1);
+        if (d.ev_x0) cudaEventDestroy(d.ev_x0);
+        if (d.ev_x1) cudaEventDestroy(d.ev_x1);
+        if (d.stream2) cudaStreamDestroy(d.stream2);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
