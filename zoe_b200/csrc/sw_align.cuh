@@ -782,6 +782,88 @@ __global__ void cigar_scan_kernel(const uint32_t *count, uint64_t first, uint64_
     }
 }
 
+// Multi-block version of the same scan (large chunks): per-block sums -> scan of the sums (one block) -> per-block
+// exclusive scan seeded with its base.  out_off / running_base semantics are those of cigar_scan_kernel.
+__global__ void cigar_block_sum_kernel(const uint32_t *count, uint64_t first, uint64_t n, unsigned long long *block_sum) {
+    __shared__ unsigned long long s_warp[32];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = (i < n) ? count[first + i] : 0ULL;
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long w = (threadIdx.x < (blockDim.x >> 5)) ? s_warp[threadIdx.x] : 0ULL;
+        for (int d = 16; d >= 1; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
+        if (threadIdx.x == 0) block_sum[blockIdx.x] = w;
+    }
+}
+
+// exclusive scan of the block sums in place (single block), seeded with and updating the running base
+__global__ void cigar_scan_sums_kernel(unsigned long long *block_sum, uint32_t n_blocks, unsigned long long *running_base,
+                                       uint64_t *out_off_last) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = *running_base;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_blocks; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = (i < n_blocks) ? block_sum[i] : 0ULL;
+        unsigned long long incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0ULL;
+            unsigned long long wi = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const unsigned long long excl = s_carry + s_warp[wid] + incl - v;
+        if (i < n_blocks) block_sum[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *running_base = s_carry;
+        *out_off_last = s_carry;
+    }
+}
+
+__global__ void cigar_block_scan_kernel(const uint32_t *count, uint64_t first, uint64_t n, const unsigned long long *block_base,
+                                        uint64_t *out_off) {
+    __shared__ unsigned long long s_warp[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long v = (i < n) ? count[first + i] : 0ULL;
+    unsigned long long incl = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long w = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0ULL;
+        unsigned long long wi = w;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    if (i < n) out_off[first + i] = block_base[blockIdx.x] + s_warp[wid] + incl - v;
+}
+
 __global__ void cigar_gather_kernel(const uint32_t *scratch, uint32_t cig_cap, const uint32_t *pair_of_slot,
                                     uint32_t n_slots, uint32_t slot_first_pair, const uint32_t *count,
                                     const uint64_t *out_off, uint32_t *out, uint64_t out_cap,

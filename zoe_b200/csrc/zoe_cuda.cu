@@ -87,6 +87,7 @@ struct Device {
     // windowed align path (sw_align_win.cuh)
     DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems, redo_flag, redo_ids, redo_flags;
     DevBuf starts;  // ranges: reverse-pass results
+    DevBuf cig_bsum;  // CIGAR scan: per-block sums
     uint64_t cig_total = 0;
     // long-row score path
     DevBuf long_ids, long_bnd, long_queue;
@@ -1289,9 +1290,24 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             ctx->stats.hazard += n_exact - hc[4];
         }
         // ---- CIGAR compaction, chained through the device-side running base ctr[9] ----
-        cigar_scan_kernel<<<1, 1024, 0, d.stream>>>(t.cig_count, (uint64_t)c0 * n_prof, cpairs, d.cig_off.as<uint64_t>(),
-                                                    ctr + 9);
-        CU(ctx, cudaGetLastError());
+        if (cpairs >= (1u << 16)) {  // three short launches instead of one block walking a million counts
+            const uint32_t nbk = (cpairs + 1023) / 1024;
+            CU(ctx, d.cig_bsum.reserve((size_t)nbk * sizeof(unsigned long long)));
+            cigar_block_sum_kernel<<<nbk, 1024, 0, d.stream>>>(t.cig_count, (uint64_t)c0 * n_prof, cpairs,
+                                                               d.cig_bsum.as<unsigned long long>());
+            CU(ctx, cudaGetLastError());
+            cigar_scan_sums_kernel<<<1, 1024, 0, d.stream>>>(d.cig_bsum.as<unsigned long long>(), nbk, ctr + 9,
+                                                             d.cig_off.as<uint64_t>() + (uint64_t)c0 * n_prof + cpairs);
+            CU(ctx, cudaGetLastError());
+            cigar_block_scan_kernel<<<nbk, 1024, 0, d.stream>>>(t.cig_count, (uint64_t)c0 * n_prof, cpairs,
+                                                                d.cig_bsum.as<unsigned long long>(), d.cig_off.as<uint64_t>());
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches += 2;
+        } else {
+            cigar_scan_kernel<<<1, 1024, 0, d.stream>>>(t.cig_count, (uint64_t)c0 * n_prof, cpairs, d.cig_off.as<uint64_t>(),
+                                                        ctr + 9);
+            CU(ctx, cudaGetLastError());
+        }
         cigar_gather_kernel<<<cpairs, 32, 0, d.stream>>>(t.cig_scratch, cig_cap, nullptr, cpairs, (uint32_t)(c0 * n_prof),
                                                          t.cig_count, d.cig_off.as<uint64_t>(), d.cig_out.as<uint32_t>(),
                                                          cigar_cap_words, t.hazard);
@@ -1557,7 +1573,7 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.long_ids, &d.long_bnd,
                           &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.redo_flag,
-                          &d.redo_ids, &d.redo_flags, &d.starts})
+                          &d.redo_ids, &d.redo_flags, &d.starts, &d.cig_bsum})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
