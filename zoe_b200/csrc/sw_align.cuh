@@ -69,16 +69,9 @@ __global__ void __launch_bounds__(512) sw_align_fill_kernel(const AlignParams ap
     const int group_in_block = tid / G;
     const int groups_per_block = blockDim.x / G;
 
-    const int tab_bytes = p.n_csym * K4 * G * 16;
-    uint4 *tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * tab_bytes);
-    uint8_t *s_lut = smem + (size_t)groups_per_block * tab_bytes;
-    int8_t *s_wk = reinterpret_cast<int8_t *>(s_lut + 256);
-    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
-    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
-    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
-    if (p.cols_in_smem) stage_with_tma(s_cc, p.ccodes, p.ccodes_bytes);  // one TMA bulk copy per CTA
-    __syncthreads();
-    const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
+    const TaskSmem sm = carve_and_stage<G, K4>(smem, p, p.cols_in_smem != 0);
+    uint4 *const tab = sm.tab;
+    const uint8_t *cc = p.cols_in_smem ? sm.s_cc : p.ccodes;
 
     const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge), one_s = O::splat(1), c21 = O::splat(21);
 
@@ -115,26 +108,7 @@ __global__ void __launch_bounds__(512) sw_align_fill_kernel(const AlignParams ap
             len_hi = (int)(p.roff[id_hi + 1] - off_hi);
         }
 
-        __syncwarp();
-        for (int s = 0; s < p.n_csym; ++s) {
-            const int8_t *wrow = s_wk + s * p.S;
-#pragma unroll
-            for (int i4 = 0; i4 < K4; ++i4) {
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    int i = i4 * 4 + q, r = lig * K + i;
-                    int wl = kPadWeight, wh = kPadWeight;
-                    if (i < K) {
-                        if (r < len_lo) wl = wrow[s_lut[p.rseq[off_lo + r]]];
-                        if (PACKED && r < len_hi) wh = wrow[s_lut[p.rseq[off_hi + r]]];
-                    }
-                    w[q] = PACKED ? ((uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16)) : (uint32_t)wl;
-                }
-                tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-        __syncwarp();
+        build_task_table<G, K, PACKED>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
 
         uint32_t *task_flags = ap.flags + (size_t)task * ap.task_stride;
 

@@ -107,18 +107,11 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
     const int group_in_block = tid / G;
     const int groups_per_block = blockDim.x / G;
 
-    const int tab_bytes = p.n_csym * K4 * G * 16;
-    uint4 *tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * tab_bytes);
-    uint8_t *s_lut = smem + (size_t)groups_per_block * tab_bytes;
-    int8_t *s_wk = reinterpret_cast<int8_t *>(s_lut + 256);
-    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
-    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
-    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
     // the profiled sequences are always staged in shared memory here (the host only picks this pipeline when
     // they fit), so the per-step column-code load is an LDS with a 32-bit address
-    stage_with_tma(s_cc, p.ccodes, p.ccodes_bytes);  // one TMA bulk copy per CTA
-    __syncthreads();
-    const uint8_t *cc = s_cc;
+    const TaskSmem sm = carve_and_stage<G, K4>(smem, p, true);
+    const int tab_bytes = sm.tab_bytes;
+    const uint8_t *cc = sm.s_cc;
 
     uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
     const uint32_t cb_mask = (1u << wp.cb_log2) - 1u;
@@ -153,28 +146,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
             len_hi = (int)(p.roff[id_hi + 1] - off_hi);
         }
 
-        __syncwarp();
-        for (int i4 = 0; i4 < K4; ++i4) {
-            int sym_lo[4], sym_hi[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i4 * 4 + q, r = lig * K + i;
-                sym_lo[q] = (i < K && r < len_lo) ? (int)s_lut[p.rseq[off_lo + r]] : -1;
-                sym_hi[q] = (i < K && r < len_hi) ? (int)s_lut[p.rseq[off_hi + r]] : -1;
-            }
-            for (int s = 0; s < p.n_csym; ++s) {
-                const int8_t *wrow = s_wk + s * p.S;
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int wl = sym_lo[q] >= 0 ? (int)wrow[sym_lo[q]] : kPadWeight;
-                    const int wh = sym_hi[q] >= 0 ? (int)wrow[sym_hi[q]] : kPadWeight;
-                    w[q] = (uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16);
-                }
-                tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-        __syncwarp();
+        build_task_table<G, K, true>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
 
         uint32_t *ck_task = wp.ckpt + (size_t)task * wp.ckpt_task_stride;
 
@@ -497,16 +469,9 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
     const int group_in_block = tid / G;
     const int groups_per_block = blockDim.x / G;
 
-    const int tab_bytes = p.n_csym * K4 * G * 16;
-    uint4 *tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * tab_bytes);
-    uint8_t *s_lut = smem + (size_t)groups_per_block * tab_bytes;
-    int8_t *s_wk = reinterpret_cast<int8_t *>(s_lut + 256);
-    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
-    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
-    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
-    if (p.cols_in_smem) stage_with_tma(s_cc, p.ccodes, p.ccodes_bytes);  // one TMA bulk copy per CTA
-    __syncthreads();
-    const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
+    const TaskSmem sm = carve_and_stage<G, K4>(smem, p, p.cols_in_smem != 0);
+    uint4 *const tab = sm.tab;
+    const uint8_t *cc = p.cols_in_smem ? sm.s_cc : p.ccodes;
 
     const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge), one_s = O::splat(1), c21 = O::splat(21);
 
@@ -562,28 +527,7 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
         }
         int bi_lo = K, bi_hi = K, bj_lo = 0, bj_hi = 0;  // best cell inside the pointed-at column pair
 
-        __syncwarp();
-        for (int i4 = 0; i4 < K4; ++i4) {
-            int sym_lo[4], sym_hi[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i4 * 4 + q, r = lig * K + i;
-                sym_lo[q] = (i < K && r < len_lo) ? (int)s_lut[p.rseq[off_lo + r]] : -1;
-                sym_hi[q] = (i < K && r < len_hi) ? (int)s_lut[p.rseq[off_hi + r]] : -1;
-            }
-            for (int s = 0; s < p.n_csym; ++s) {
-                const int8_t *wrow = s_wk + s * p.S;
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int wl = sym_lo[q] >= 0 ? (int)wrow[sym_lo[q]] : kPadWeight;
-                    const int wh = sym_hi[q] >= 0 ? (int)wrow[sym_hi[q]] : kPadWeight;
-                    w[q] = (uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16);
-                }
-                tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-        __syncwarp();
+        build_task_table<G, K, true>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
 
         // ---- restore the systolic state before step ws (sw_align_scan_kernel's checkpoint layout) ----
         uint32_t Hrow[K], Frow[K];

@@ -47,16 +47,9 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_ends_kernel(const EndsP
     const int group_in_block = tid / G;
     const int groups_per_block = blockDim.x / G;
 
-    const int tab_bytes = p.n_csym * K4 * G * 16;
-    uint4 *tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * tab_bytes);
-    uint8_t *s_lut = smem + (size_t)groups_per_block * tab_bytes;
-    int8_t *s_wk = reinterpret_cast<int8_t *>(s_lut + 256);
-    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
-    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
-    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
-    if (p.cols_in_smem) stage_with_tma(s_cc, p.ccodes, p.ccodes_bytes);  // one TMA bulk copy per CTA
-    __syncthreads();
-    const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
+    const TaskSmem sm = carve_and_stage<G, K4>(smem, p, p.cols_in_smem != 0);
+    uint4 *const tab = sm.tab;
+    const uint8_t *cc = p.cols_in_smem ? sm.s_cc : p.ccodes;
 
     const uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
     const bool reverse = ep.items != nullptr;
@@ -116,27 +109,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_ends_kernel(const EndsP
             }
         }
 
-        // ---- score table of the task ----
-        __syncwarp();
-        for (int s = 0; s < p.n_csym; ++s) {
-            const int8_t *wrow = s_wk + s * p.S;
-#pragma unroll
-            for (int i4 = 0; i4 < K4; ++i4) {
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = i4 * 4 + q, r = lig * K + i;
-                    int wl = kPadWeight, wh = kPadWeight;
-                    if (i < K) {
-                        if (r < len_lo) wl = wrow[s_lut[p.rseq[base_lo + (int64_t)dir * r]]];
-                        if (PACKED && r < len_hi) wh = wrow[s_lut[p.rseq[base_hi + (int64_t)dir * r]]];
-                    }
-                    w[q] = PACKED ? ((uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16)) : (uint32_t)wl;
-                }
-                tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-        __syncwarp();
+        build_task_table<G, K, PACKED>(sm, p, lig, base_lo, len_lo, base_hi, len_hi, dir);
 
         // the groups of a warp may sweep different numbers of profiled sequences / columns: keep the loops uniform
         const uint32_t n_sweeps = __reduce_max_sync(FULL, cj_last - cj_first);

@@ -140,6 +140,67 @@ __device__ __forceinline__ uint32_t half2_max_bits(uint32_t a, uint32_t b) {
 // Shared-memory footprint helpers (host + device).
 __host__ __device__ inline int score_tab_bytes(int n_csym, int G, int K) { return n_csym * ((K + 3) / 4) * G * 16; }
 
+
+// Shared-memory carve-up common to the kernels that keep a score table per task:
+//   [one table per group][byte -> symbol LUT, 256][weights n_csym x S][profiled symbol codes]
+struct TaskSmem {
+    uint4 *tab;      // this group's table
+    uint8_t *s_lut;
+    int8_t *s_wk;
+    uint8_t *s_cc;
+    int tab_bytes;
+};
+
+// Carves the dynamic shared memory, loads the LUT and the weights, stages the profiled symbol codes (one TMA bulk
+// copy per CTA) when `stage_cols`, and synchronises the CTA.  Must be called by every thread of the CTA.
+template <int G, int K4>
+__device__ __forceinline__ TaskSmem carve_and_stage(uint8_t *smem, const ScoreParams &p, bool stage_cols) {
+    const int tid = threadIdx.x;
+    const int group_in_block = tid / G, groups_per_block = blockDim.x / G;
+    TaskSmem m;
+    m.tab_bytes = p.n_csym * K4 * G * 16;
+    m.tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * m.tab_bytes);
+    m.s_lut = smem + (size_t)groups_per_block * m.tab_bytes;
+    m.s_wk = reinterpret_cast<int8_t *>(m.s_lut + 256);
+    m.s_cc = reinterpret_cast<uint8_t *>(m.s_wk) + ((p.n_csym * p.S + 15) & ~15);
+    for (int i = tid; i < 256; i += blockDim.x) m.s_lut[i] = p.lut[i];
+    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) m.s_wk[i] = p.wk[i];
+    if (stage_cols) stage_with_tma(m.s_cc, p.ccodes, p.ccodes_bytes);
+    __syncthreads();
+    return m;
+}
+
+// Builds a task's score table: lane `lig` fills its own K rows for every column symbol.  Row r of the low / high
+// half reads rseq[base + dir * r] for r < len (dir = -1: a reversed prefix), else the padding weight.
+// tab[(s * K4 + i4) * G + lig] = the four packed weights of rows lig*K + 4*i4 .. +3 against column symbol s.
+template <int G, int K, bool PACKED>
+__device__ __forceinline__ void build_task_table(const TaskSmem &m, const ScoreParams &p, int lig, int64_t base_lo, int len_lo,
+                                                 int64_t base_hi, int len_hi, int dir = 1) {
+    constexpr int K4 = (K + 3) / 4;
+    __syncwarp();
+    for (int i4 = 0; i4 < K4; ++i4) {
+        int sym_lo[4], sym_hi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i4 * 4 + q, r = lig * K + i;
+            sym_lo[q] = (i < K && r < len_lo) ? (int)m.s_lut[p.rseq[base_lo + (int64_t)dir * r]] : -1;
+            sym_hi[q] = (PACKED && i < K && r < len_hi) ? (int)m.s_lut[p.rseq[base_hi + (int64_t)dir * r]] : -1;
+        }
+        for (int s = 0; s < p.n_csym; ++s) {
+            const int8_t *wrow = m.s_wk + s * p.S;
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int wl = sym_lo[q] >= 0 ? (int)wrow[sym_lo[q]] : kPadWeight;
+                const int wh = sym_hi[q] >= 0 ? (int)wrow[sym_hi[q]] : kPadWeight;
+                w[q] = PACKED ? ((uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16)) : (uint32_t)wl;
+            }
+            m.tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncwarp();
+}
+
 // One column step of one systolic stream: K rows, fully unrolled.  `tp` points at this lane's uint4 of the
 // column symbol's table row; (diag, E) enter from the lane above.
 // H is kept in two register sets (P = step parity): column j-1 is read from set P, column j is written to
@@ -181,17 +242,10 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
     const int group_in_block = tid / G;
     const int groups_per_block = blockDim.x / G;
 
-    // ---- shared memory carve-up: [tables][lut 256][wk][ccodes] ----
-    const int tab_bytes = p.n_csym * K4 * G * 16;
-    uint4 *tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * tab_bytes);
-    uint8_t *s_lut = smem + (size_t)groups_per_block * tab_bytes;
-    int8_t *s_wk = reinterpret_cast<int8_t *>(s_lut + 256);
-    uint8_t *s_cc = reinterpret_cast<uint8_t *>(s_wk) + ((p.n_csym * p.S + 15) & ~15);
-
-    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = p.lut[i];
-    for (int i = tid; i < p.n_csym * p.S; i += blockDim.x) s_wk[i] = p.wk[i];
-    if (p.cols_in_smem) stage_with_tma(s_cc, p.ccodes, p.ccodes_bytes);  // one TMA bulk copy per CTA
-    __syncthreads();
+    const TaskSmem sm = carve_and_stage<G, K4>(smem, p, p.cols_in_smem != 0);
+    uint4 *const tab = sm.tab;
+    uint8_t *const s_cc = sm.s_cc;
+    const int tab_bytes = sm.tab_bytes;
     const uint8_t *cc = p.cols_in_smem ? s_cc : p.ccodes;
 
     uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
@@ -241,29 +295,7 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
             len_hi = (int)(p.roff[id_hi + 1] - off_hi);
         }
 
-        // ---- build this task's score table: lane l fills its own K rows for every column symbol ----
-        __syncwarp();
-        for (int i4 = 0; i4 < K4; ++i4) {
-            int sym_lo[4], sym_hi[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i4 * 4 + q, r = lig * K + i;
-                sym_lo[q] = (i < K && r < len_lo) ? (int)s_lut[p.rseq[off_lo + r]] : -1;
-                sym_hi[q] = (PACKED && i < K && r < len_hi) ? (int)s_lut[p.rseq[off_hi + r]] : -1;
-            }
-            for (int s = 0; s < p.n_csym; ++s) {
-                const int8_t *wrow = s_wk + s * p.S;
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int wl = sym_lo[q] >= 0 ? (int)wrow[sym_lo[q]] : kPadWeight;
-                    const int wh = sym_hi[q] >= 0 ? (int)wrow[sym_hi[q]] : kPadWeight;
-                    w[q] = PACKED ? ((uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16)) : (uint32_t)wl;
-                }
-                tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-        __syncwarp();
+        build_task_table<G, K, PACKED>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
 
         // ---- sweep the column sequences, NS at a time ----
         for (uint32_t ci = 0; ci < p.n_cseq; ci += NS) {
