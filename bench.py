@@ -138,6 +138,17 @@ def cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads, width_bi
     return cells / dt / 1e9, dt, res
 
 
+def run_threaded(check_range, n_items):
+    """Runs ``check_range(lo, hi) -> mismatches`` over [0, n_items) on all host threads (the oracle is called through
+    ctypes, which releases the GIL).  Returns (total mismatches, threads used)."""
+    from concurrent.futures import ThreadPoolExecutor
+    threads = max(1, min(os.cpu_count() or 1, 64))
+    step = max(1, (n_items + 8 * threads - 1) // (8 * threads))
+    spans = [(lo, min(lo + step, n_items)) for lo in range(0, n_items, step)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return sum(ex.map(lambda sp: check_range(*sp), spans)), threads
+
+
 def run_reference(args):
     """`--impl reference`: the CPU restatement on all host threads, rank 0 only."""
     rank = env_int("RANK", 0)
@@ -432,21 +443,26 @@ def main():
     if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "ranges":
         from oracle import oracle as O
         sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
-        n_sample = min(n, 600)
+        n_sample = min(n, 20000)
         t0 = time.perf_counter()
-        mism = 0
-        for i in range(n_sample):
-            s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
-            for j, tg in enumerate(targets):
-                rc, score, rr, qr, _ = O.sw_score_ranges_from(bytes(tg), s_i, sc, streamed_is_query=True)
-                k = i * n_prof + j
-                ok = int(outs["status"][k]) == rc
-                if ok and rc == 0:
-                    ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
-                          int(outs["query_start"][k]), int(outs["query_end"][k])) == (score, rr[0], rr[1], qr[0], qr[1])
-                mism += 0 if ok else 1
+
+        def check_range(lo, hi):
+            bad = 0
+            for i in range(lo, hi):
+                s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
+                for j, tg in enumerate(targets):
+                    rc, score, rr, qr, _ = O.sw_score_ranges_from(bytes(tg), s_i, sc, streamed_is_query=True)
+                    k = i * n_prof + j
+                    ok = int(outs["status"][k]) == rc
+                    if ok and rc == 0:
+                        ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
+                              int(outs["query_start"][k]), int(outs["query_end"][k])) == (score, rr[0], rr[1], qr[0], qr[1])
+                    bad += 0 if ok else 1
+            return bad
+
+        mism, oracle_threads = run_threaded(check_range, n_sample)
         dt = time.perf_counter() - t0
-        cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+        cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": oracle_threads, "kind": "port",
                "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of sw_simd_score_ranges + escalation ({dt:.1f} s); "
                          "not vectorised -- a checker, not a tuned baseline"}
         parity = {"checked_pairs": n_sample * n_prof, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c (score, ranges)"}
@@ -454,24 +470,29 @@ def main():
     if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "align":
         from oracle import oracle as O
         sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
-        n_sample = min(n, 600)
+        n_sample = min(n, 20000)
         t0 = time.perf_counter()
-        mism = 0
-        for i in range(n_sample):
-            s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
-            for j, tg in enumerate(targets):
-                rc, want, _ = O.sw_align_from(bytes(tg), s_i, sc, streamed_is_query=True)
-                k = i * n_prof + j
-                ok = int(outs["status"][k]) == rc
-                if ok and rc == 0:
-                    lo, hi = int(outs["cigar_off"][k]), int(outs["cigar_off"][k + 1])
-                    cig = "".join(f"{int(w) >> 4}{'MID?S'[int(w) & 15]}" for w in outs["cigar"][lo:hi])
-                    ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
-                          int(outs["query_start"][k]), int(outs["query_end"][k]), cig) == \
-                         (want.score, want.ref_range[0], want.ref_range[1], want.query_range[0], want.query_range[1], want.cigar)
-                mism += 0 if ok else 1
+
+        def check_range(lo, hi):
+            bad = 0
+            for i in range(lo, hi):
+                s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
+                for j, tg in enumerate(targets):
+                    rc, want, _ = O.sw_align_from(bytes(tg), s_i, sc, streamed_is_query=True)
+                    k = i * n_prof + j
+                    ok = int(outs["status"][k]) == rc
+                    if ok and rc == 0:
+                        lo_w, hi_w = int(outs["cigar_off"][k]), int(outs["cigar_off"][k + 1])
+                        cig = "".join(f"{int(w) >> 4}{'MID?S'[int(w) & 15]}" for w in outs["cigar"][lo_w:hi_w])
+                        ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
+                              int(outs["query_start"][k]), int(outs["query_end"][k]), cig) == \
+                             (want.score, want.ref_range[0], want.ref_range[1], want.query_range[0], want.query_range[1], want.cigar)
+                    bad += 0 if ok else 1
+            return bad
+
+        mism, oracle_threads = run_threaded(check_range, n_sample)
         dt = time.perf_counter() - t0
-        cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+        cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": oracle_threads, "kind": "port",
                "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of sw_simd_align + escalation ({dt:.1f} s); "
                          "not vectorised -- a checker, not a tuned baseline"}
         parity = {"checked_pairs": n_sample * n_prof, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c (score, ranges, CIGAR)"}
