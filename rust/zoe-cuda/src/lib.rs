@@ -4,7 +4,7 @@
 use std::ffi::CStr;
 
 use zoe::{
-    alignment::{Alignment, AlignmentStates, MaybeAligned, ProfileError, SeqSrc},
+    alignment::{Alignment, AlignmentStates, MaybeAligned, ProfileError, ScoreAndRanges, SeqSrc},
     data::{cigar::Ciglet, matrices::WeightMatrix},
 };
 use zoe_cuda_sys as sys;
@@ -134,6 +134,42 @@ impl CudaProfiles {
             }
         }
         Ok(out)
+    }
+
+    /// `out[i * n_profiled + j] == profiles[j].sw_score_ranges_from_i8(seq_src(seqs[i]))`
+    /// (profile_set.rs:313-322): score plus 0-based half-open ranges, no traceback matrix.
+    pub fn sw_score_ranges_batch(&self, seqs: &[&[u8]]) -> Result<Vec<MaybeAligned<ScoreAndRanges<u32>>>, CudaError> {
+        let (concat, offsets) = pack(seqs);
+        let pairs = seqs.len() * self.profiled_lens.len();
+        let mut score = vec![0u32; pairs];
+        let (mut status, mut tier) = (vec![0u8; pairs], vec![0u8; pairs]);
+        let (mut rs, mut re, mut qs, mut qe) = (vec![0u32; pairs], vec![0u32; pairs], vec![0u32; pairs], vec![0u32; pairs]);
+        self.check(unsafe {
+            sys::zoe_cuda_sw_score_ranges_batch(self.ctx, concat.as_ptr(), offsets.as_ptr(), seqs.len() as u64,
+                score.as_mut_ptr(), status.as_mut_ptr(), tier.as_mut_ptr(), rs.as_mut_ptr(), re.as_mut_ptr(),
+                qs.as_mut_ptr(), qe.as_mut_ptr())
+        }, 0, 0)?;
+        Ok((0..pairs).map(|k| match status[k] {
+            sys::ZOE_CUDA_SOME => MaybeAligned::Some(ScoreAndRanges {
+                score: score[k],
+                ref_range: rs[k] as usize..re[k] as usize,
+                query_range: qs[k] as usize..qe[k] as usize,
+            }),
+            sys::ZOE_CUDA_OVERFLOWED => MaybeAligned::Overflowed,
+            _ => MaybeAligned::Unmapped,
+        }).collect())
+    }
+
+    /// Which integer types may answer: `(8, 32, false)` = `sw_*_from_i8` (default), `(16, 32, false)` =
+    /// `..._from_i16`, `(32, 32, false)` = `..._from_i32` (profile_set.rs:71-179); `first == last` = a standalone
+    /// `StripedProfile<T, N, S>`; `unsigned` = the u8/u16/u32 profiles over `to_biased_matrix()`.
+    pub fn set_width_policy(&self, first_bits: i32, last_bits: i32, unsigned: bool) -> Result<(), CudaError> {
+        self.check(unsafe { sys::zoe_cuda_set_width_policy(self.ctx, first_bits, last_bits, unsigned as i32) }, 0, 0)
+    }
+
+    /// Tuning of the align pipeline (never changes results): 0 auto, 1 full-matrix flags, 2 checkpointed window.
+    pub fn set_align_options(&self, mode: i32, checkpoint_log2: i32, slack: i32) -> Result<(), CudaError> {
+        self.check(unsafe { sys::zoe_cuda_set_align_options(self.ctx, mode, checkpoint_log2, slack) }, 0, 0)
     }
 
     /// The SeqSrc this context's batches correspond to (alignment/mod.rs:157-162).
