@@ -167,7 +167,7 @@ typedef struct {
     uint64_t tier8, tier16, tier32, overflowed, unmapped;
     uint64_t rerun_wide, hazard;
     uint64_t window_fallback; /* pairs whose walk left its checkpoint window (re-done by the literal kernel) */
-    uint64_t window_redo;     /* pairs whose best cell recurs in a later column (re-done with full-matrix flags) */
+    uint64_t window_pinned;   /* pairs whose maximum recurs in the winning lane: best cell found by a pin sweep */
 } zoe_cuda_stats;
 int zoe_cuda_last_stats(const zoe_cuda_ctx *ctx, zoe_cuda_stats *out);
 

@@ -34,7 +34,7 @@ pub struct zoe_cuda_stats {
     pub rerun_wide: u64,
     pub hazard: u64,
     pub window_fallback: u64,
-    pub window_redo: u64,
+    pub window_pinned: u64,
 }
 
 unsafe extern "C" {

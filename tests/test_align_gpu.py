@@ -244,3 +244,28 @@ def test_window_pipeline_protein_and_overflow():
     stats = check_align([b"A" * 600], [b"A" * 600, b"A" * 300, b"A" * 100 + b"C" + b"A" * 100], w,
                         align_options=(WINDOW, 6, 8))
     assert stats["tier32"] == 1 and stats["rerun_wide"] >= 1
+
+
+def test_window_pipeline_with_profiled_set_larger_than_shared_memory():
+    """> 96 KB of profiled sequences: pass A reads the symbol codes from global memory (sw_align_scan_kernel<.., false>)."""
+    rng = np.random.default_rng(211)
+    targets = [synth.random_dna(rng, int(L)) for L in rng.integers(2300, 2900, 40)]
+    assert sum(len(t) for t in targets) > 96 * 1024
+    seqs = _related_seqs(rng, targets, 40, lo=60, hi=150)
+    stats = check_align(targets, seqs, W25, align_options=(CudaProfiles.ALIGN_AUTO, 6, 16))
+    assert stats["tier16"] + stats["tier8"] > 0
+    # and the two pipelines agree on every array for a larger batch
+    reads = _related_seqs(rng, targets, 600, lo=100, hi=150)
+    buf, offs = synth.pack(reads)
+    outs = []
+    for mode in (CudaProfiles.ALIGN_WINDOW, CudaProfiles.ALIGN_FULL):
+        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], W25, -10, -1)
+        prof.set_align_options(mode, 6, 16)
+        outs.append(prof.align_arrays(buf, offs))
+        prof.close()
+    a, b = outs
+    n_words = int(a["cigar_off"][-1])
+    assert n_words == int(b["cigar_off"][-1])
+    for k in ("score", "status", "tier", "ref_start", "ref_end", "query_start", "query_end", "cigar_off"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["cigar"][:n_words], b["cigar"][:n_words])

@@ -25,7 +25,7 @@ SYMBOLS = [
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("pairs", "cells", "tier8", "tier16", "tier32", "overflowed", "unmapped", "rerun_wide", "hazard",
-                 "window_fallback", "window_redo")]
+                 "window_fallback", "window_pinned")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -39,9 +39,9 @@ struct AlignEnd {      // per pair, written by the fill kernel
     int32_t best;      // exact best score; -1 = needs the 32-bit kernel
     uint32_t r_end;    // 0-based row (streamed index) of the best cell
     uint32_t c_end;    // 0-based column (profiled index) of the best cell
-    uint32_t aux;      // windowed pipeline only (sw_align_win.cuh): window start, or kAmbiguousEnd
+    uint32_t aux;      // windowed pipeline only (sw_align_win.cuh): last pair holding the maximum, then the window start
 };
-constexpr uint32_t kAmbiguousEnd = 0xffffffffu;
+constexpr uint32_t kNotBucketed = 0xffffffffu;  // aux of a pair that takes no part in the windowed pipeline
 
 struct AlignParams {
     ScoreParams s;               // sequences, tables, scoring (s.best unused)
@@ -281,7 +281,6 @@ struct TraceParams {
     unsigned long long *counters;  // [5] exact-list length, [6] cigar overflow count, [8] packed overflows
     uint32_t *hazard_list;      // global pair ids that need the exact kernel
     int all_exact;              // gap_open == 0: every Some pair goes to the exact kernel
-    int only_ambiguous;         // seq_ids mode: redo only the pairs the windowed pipeline marked kAmbiguousEnd
     TierPolicy tp;
 };
 
@@ -333,7 +332,6 @@ __global__ void sw_traceback_kernel(const TraceParams t) {
     const uint32_t seq = t.seq_ids ? t.seq_ids[seq_local] : t.chunk_first + seq_local;
     const size_t gid = (size_t)seq * t.n_cseq + cj;
     const AlignEnd e = t.ends[gid];
-    if (t.only_ambiguous && e.aux != kAmbiguousEnd) return;
     const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
     const uint32_t m = t.coff[cj + 1] - t.coff[cj];
     t.hazard[gid] = 0;

@@ -25,9 +25,10 @@
 //
 // Which cell is "the" best cell?  zoe takes the smallest row, then the smallest column among the cells holding the
 // maximum.  Lanes own disjoint ascending row ranges, so the winner lies in the lowest lane that reaches the
-// maximum; inside that lane pass A knows the first column pair holding it.  If the same lane reaches the maximum
-// again in a later column pair (first != last) a smaller row could hide there: such pairs are marked
-// kAmbiguousEnd and redone by the full-matrix pipeline (sw_align.cuh).  [cfg 3: a fraction of the 5 % random reads]
+// maximum; inside that lane pass A knows the first and the last column pair holding it.  If they differ (typical
+// for unrelated pairs, whose small maximum recurs) a smaller row could hide in a later column: a PIN sweep
+// (sw_align_winfill_kernel<.., FLAGS=false> in pin mode) restarts at the checkpoint before the first occurrence,
+// runs the plain recurrence up to the last one and finds the cell exactly; the pair then joins the others.
 //
 // Checkpoint layout per pass-A task and profiled sequence: ckpt[kb-1][w][lane] = one 32-bit word of the lane's
 // vector (H[0..K), F[0..K), E leaving the last row, diagonal for the next column); kb = 1 .. (L-1)/CB
@@ -64,6 +65,7 @@ struct WinParams {
     uint64_t win_task_stride;    // words per pass-B task = Wmax * G * NW
     uint32_t wmax;               // window capacity in columns
     unsigned long long *counters; // [7] internal consistency failures
+    int pin_mode;                // 1: pin sweep over the ambiguous pairs (no flags), 0: window fill
 };
 
 // Pass A leaves (winning lane, even step of the first column pair); the best cell is one of that lane's K rows in
@@ -93,7 +95,10 @@ __device__ __forceinline__ uint32_t win_start(uint32_t r_end, uint32_t c_end, ui
 //     test is a uniform-datapath compare.
 // State parked before step s0 = kb*CB (s0 even, s0 >= G): lane l holds column s0-1-l in H[0], its along-row gap
 // state F, the E leaving its last row and the diagonal it received at step s0-1.
-template <int G, int K>
+// CSM = the profiled symbol codes are staged in shared memory (LDS with a 32-bit address in the hot loop); false = a
+// profiled set too large for that (> 96 KB): the codes are read from global memory (L1-resident: every warp of the
+// SM walks the same sequences).
+template <int G, int K, bool CSM = true>
 __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const WinParams wp) {
     using O = Ops<true>;
     const ScoreParams &p = wp.s;
@@ -107,11 +112,9 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
     const int group_in_block = tid / G;
     const int groups_per_block = blockDim.x / G;
 
-    // the profiled sequences are always staged in shared memory here (the host only picks this pipeline when
-    // they fit), so the per-step column-code load is an LDS with a 32-bit address
-    const TaskSmem sm = carve_and_stage<G, K4>(smem, p, true);
+    const TaskSmem sm = carve_and_stage<G, K4>(smem, p, CSM);
     const int tab_bytes = sm.tab_bytes;
-    const uint8_t *cc = sm.s_cc;
+    const uint8_t *cc = CSM ? sm.s_cc : p.ccodes;
 
     uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
     const uint32_t cb_mask = (1u << wp.cb_log2) - 1u;
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
                     e.best = (b >= p.ovf_thresh) ? -1 : b;
                     e.r_end = (uint32_t)wl_lo;   // winning lane, refined to a row by pass B
                     e.c_end = 2u * f_lo;         // even step of the pair: columns (s - lane, s + 1 - lane)
-                    e.aux = (f_lo != l_lo) ? kAmbiguousEnd : 0u;
+                    e.aux = 2u * l_lo;           // last pair holding the maximum in that lane (== c_end: unambiguous)
                     wp.ends[(size_t)id_lo * p.n_cseq + cj] = e;
                 }
                 if (id_hi != 0xffffffffu) {
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
                     e.best = (b >= p.ovf_thresh) ? -1 : b;
                     e.r_end = (uint32_t)wl_hi;
                     e.c_end = 2u * f_hi;
-                    e.aux = (f_hi != l_hi) ? kAmbiguousEnd : 0u;
+                    e.aux = 2u * l_hi;
                     wp.ends[(size_t)id_hi * p.n_cseq + cj] = e;
                 }
             }
@@ -315,15 +318,27 @@ struct ClassifyParams {
     uint32_t slack, nblk;
     int all_exact;
     uint32_t *hist;
-    uint8_t *redo_flag;            // [n_slots] 1 = the sequence has an ambiguous pair: full-matrix pipeline
+    int pin_stage;                 // 1: select the ambiguous pairs for the pin sweep; 0: the classification proper
     int32_t *best_arr;
     uint32_t *score;
     uint8_t *status, *tier, *hazard;
     uint32_t *ref_start, *ref_end, *query_start, *query_end, *cig_count;
-    unsigned long long *counters;  // [5] exact-list length, [8] packed overflows, [11] ambiguous pairs
+    unsigned long long *counters;  // [5] exact-list length, [8] packed overflows, [11] pinned (ambiguous) pairs
     uint32_t *hazard_list;
     TierPolicy tp;
 };
+
+// Restart step of a pin sweep: the checkpoint at or before the first occurrence (0 = from scratch).  Pass A parks
+// its state only at steps < L (a step index can exceed L-1 by the lane skew), hence the clamp.
+__device__ __forceinline__ uint32_t pin_start(uint32_t first_s, uint32_t L, int cb_log2) {
+    return (min(first_s, L - 1u) >> cb_log2) << cb_log2;
+}
+
+// Does this pair take part in the windowed pipeline at all (mapped, inside the packed range, inside the widest
+// allowed integer type, not literal-only)?
+__device__ __forceinline__ bool win_eligible(const AlignEnd &e, uint32_t n, const TierPolicy &tp, int all_exact) {
+    return e.best > 0 && n != 0 && !all_exact && tier_for(tp, (uint32_t)e.best) != 0;
+}
 
 __global__ void win_classify_kernel(const ClassifyParams t) {
     const uint32_t pairs = t.n_slots * t.n_cseq;
@@ -334,6 +349,13 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
     const size_t gid = (size_t)seq * t.n_cseq + cj;
     const AlignEnd e = t.ends[gid];
     const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
+    if (t.pin_stage) {  // ambiguous end cells only: bucket them by (profiled sequence, checkpoint block)
+        if (win_eligible(e, n, t.tp, t.all_exact) && e.aux != e.c_end) {
+            atomicAdd(&t.hist[cj * t.nblk + (pin_start(e.c_end, t.coff[cj + 1] - t.coff[cj], t.cb_log2) >> t.cb_log2)], 1u);
+            atomicAdd(&t.counters[11], 1ULL);
+        }
+        return;
+    }
     t.hazard[gid] = 0;
     t.cig_count[gid] = 0;
     t.best_arr[gid] = e.best;
@@ -343,7 +365,7 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         atomicAdd(&t.counters[8], 1ULL);
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
         t.hazard_list[slot] = (uint32_t)gid;
-        t.ends[gid].aux = kAmbiguousEnd - 1u;  // not bucketed
+        t.ends[gid].aux = kNotBucketed;
         return;
     }
     if (e.best == 0 || n == 0) {
@@ -351,7 +373,7 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         t.status[gid] = 2;  // Unmapped
         t.tier[gid] = 8;
         t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
-        t.ends[gid].aux = kAmbiguousEnd - 1u;
+        t.ends[gid].aux = kNotBucketed;
         return;
     }
     const uint8_t tier = tier_for(t.tp, (uint32_t)e.best);
@@ -360,7 +382,7 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         t.status[gid] = 1;
         t.tier[gid] = t.tp.last;
         t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
-        t.ends[gid].aux = kAmbiguousEnd - 1u;
+        t.ends[gid].aux = kNotBucketed;
         return;
     }
     t.score[gid] = (uint32_t)e.best;
@@ -370,12 +392,7 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
         t.hazard_list[slot] = (uint32_t)gid;
         t.hazard[gid] = 1;
-        t.ends[gid].aux = kAmbiguousEnd - 1u;
-        return;
-    }
-    if (e.aux == kAmbiguousEnd) {  // the maximum recurs later in the winning lane: redo with the full matrix
-        t.redo_flag[seq_local] = 1;
-        atomicAdd(&t.counters[11], 1ULL);
+        t.ends[gid].aux = kNotBucketed;
         return;
     }
     uint32_t r_hi, c_hi;
@@ -383,15 +400,6 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
     const uint32_t ws = win_start(r_hi, c_hi, t.slack, t.cb_log2);
     t.ends[gid].aux = ws;
     atomicAdd(&t.hist[cj * t.nblk + (ws >> t.cb_log2)], 1u);
-}
-
-// Sequences flagged by win_classify_kernel -> list (chunk order is not preserved; results do not depend on it).
-__global__ void win_collect_redo_kernel(const uint8_t *redo_flag, uint32_t chunk_first, uint32_t n_slots, uint32_t *ids,
-                                        unsigned long long *counters) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_slots || !redo_flag[i]) return;
-    const unsigned long long slot = atomicAdd(&counters[12], 1ULL);
-    ids[slot] = chunk_first + i;
 }
 
 // Single-block exclusive scan of the bucket sizes rounded up to even (a pass-B task holds two pairs of ONE
@@ -444,17 +452,27 @@ __global__ void win_scatter_kernel(const ClassifyParams t, const uint32_t *bucke
     if (k >= pairs) return;
     const uint32_t seq = t.chunk_first + k / t.n_cseq, cj = k % t.n_cseq;
     const size_t gid = (size_t)seq * t.n_cseq + cj;
-    const uint32_t ws = t.ends[gid].aux;
-    if (ws >= kAmbiguousEnd - 1u) return;  // unmapped / overflowed / literal-only / ambiguous
-    const uint32_t key = cj * t.nblk + (ws >> t.cb_log2);
+    const AlignEnd e = t.ends[gid];
+    uint32_t key;
+    if (t.pin_stage) {
+        const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
+        if (!(win_eligible(e, n, t.tp, t.all_exact) && e.aux != e.c_end)) return;
+        key = cj * t.nblk + (pin_start(e.c_end, t.coff[cj + 1] - t.coff[cj], t.cb_log2) >> t.cb_log2);
+    } else {
+        if (e.aux == kNotBucketed) return;  // unmapped / overflowed / literal-only
+        key = cj * t.nblk + (e.aux >> t.cb_log2);
+    }
     const uint32_t slot = bucket_start[key] + atomicAdd(&t.hist[key], 1u);
     items[slot] = (uint32_t)gid;
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass B: direction bits for the window [ws, c_end] of every mapped pair
+// pass B: direction bits for the window [ws, c_end] of every mapped pair            (FLAGS = true,  wp.pin_mode = 0)
+// pin   : exact best cell of the pairs whose maximum recurs in the winning lane      (FLAGS = false, wp.pin_mode = 1)
+// Both resume the systolic sweep from a checkpoint of pass A and search the winning lane for the best cell (smallest
+// row, then smallest column -- striped.rs:555-583) inside a range of steps; only pass B emits direction bits.
 // ---------------------------------------------------------------------------------------------
-template <int G, int K>
+template <int G, int K, bool FLAGS = true>
 __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams wp) {
     using O = Ops<true>;
     const ScoreParams &p = wp.s;
@@ -488,9 +506,11 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
             g_lo = wp.items[2 * task];
             g_hi = wp.items[2 * task + 1];
         }
-        // the two pairs share (profiled sequence, window start); a bucket of odd size leaves g_hi empty
+        // the two pairs share (profiled sequence, restart step); a bucket of odd size leaves g_hi empty
         uint32_t cj = 0, ws = 0;
-        int we = -1;  // last column of the window
+        int we = -1;       // last column computed
+        int s_last = -1;   // last step of the sweep (absolute)
+        uint32_t se_lo = 0, se_hi = 0;  // last step searched for the best cell (the first one is fs_*)
         uint64_t off_lo = 0, off_hi = 0;
         int len_lo = 0, len_hi = 0;
         uint32_t seqA_lo = 0, seqA_hi = 0;  // chunk-relative sequence index (locates the checkpoint)
@@ -503,10 +523,20 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
             const AlignEnd e = wp.ends[g_lo];
             off_lo = p.roff[seq];
             len_lo = (int)(p.roff[seq + 1] - off_lo);
-            uint32_t r_hi, c_hi;
-            end_bounds(e.r_end, e.c_end, K, (uint32_t)len_lo, p.coff[cj + 1] - p.coff[cj], r_hi, c_hi);
-            ws = e.aux;
-            we = (int)c_hi;
+            const uint32_t Lc = p.coff[cj + 1] - p.coff[cj];
+            if (wp.pin_mode) {  // from the checkpoint before the first occurrence to the last one, all columns
+                ws = pin_start(e.c_end, Lc, wp.cb_log2);
+                we = (int)Lc - 1;
+                se_lo = e.aux + 1;
+                s_last = (int)se_lo;
+            } else {
+                uint32_t r_hi, c_hi;
+                end_bounds(e.r_end, e.c_end, K, (uint32_t)len_lo, Lc, r_hi, c_hi);
+                ws = e.aux;
+                we = (int)c_hi;
+                se_lo = e.c_end + 1;
+                s_last = we + G - 1;
+            }
             ls_lo = e.r_end;
             fs_lo = e.c_end;
             best_lo = e.best;
@@ -517,9 +547,17 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
             const AlignEnd e = wp.ends[g_hi];
             off_hi = p.roff[seq];
             len_hi = (int)(p.roff[seq + 1] - off_hi);
-            uint32_t r_hi, c_hi;
-            end_bounds(e.r_end, e.c_end, K, (uint32_t)len_hi, p.coff[cj + 1] - p.coff[cj], r_hi, c_hi);
-            we = max(we, (int)c_hi);
+            const uint32_t Lc = p.coff[cj + 1] - p.coff[cj];
+            if (wp.pin_mode) {
+                se_hi = e.aux + 1;
+                s_last = max(s_last, (int)se_hi);
+            } else {
+                uint32_t r_hi, c_hi;
+                end_bounds(e.r_end, e.c_end, K, (uint32_t)len_hi, Lc, r_hi, c_hi);
+                we = max(we, (int)c_hi);
+                se_hi = e.c_end + 1;
+                s_last = max(s_last, (int)c_hi + G - 1);
+            }
             ls_hi = e.r_end;
             fs_hi = e.c_end;
             best_hi = e.best;
@@ -569,7 +607,7 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
         const int origin = (int)ws - (G - 1);
         uint32_t h_last = Hrow[K - 1];
         // the groups of a warp hold different windows: the trip count must be warp-uniform for the shuffles
-        const int nsteps = __reduce_max_sync(FULL, we >= (int)ws ? we - (int)ws + G : 0);
+        const int nsteps = __reduce_max_sync(FULL, s_last >= (int)ws ? s_last - (int)ws + 1 : 0);
 
         for (int step = 0; step < nsteps; ++step) {
             uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G);
@@ -584,9 +622,11 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                 const uint4 *tp = tab + (size_t)cs[j] * (K4 * G) + lig;
                 uint32_t diag = h_up_prev;
                 uint32_t E = e_in;
-                uint32_t words[NW];
+                uint32_t words[FLAGS ? NW : 1];
+                if (FLAGS) {
 #pragma unroll
-                for (int w = 0; w < NW; ++w) words[w] = 0;
+                    for (int w = 0; w < NW; ++w) words[w] = 0;
+                }
 #pragma unroll
                 for (int i4 = 0; i4 < K4; ++i4) {
                     const uint4 w4 = tp[i4 * G];
@@ -599,16 +639,18 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                             uint32_t x = O::max3(E, Fi, go_s) - go_s;
                             uint32_t H = O::addmax(diag, wv[q], x);
                             diag = Hrow[i];
-                            uint32_t Hg = H + go_s;
-                            uint32_t nve = O::min2(Hg - E, one_s);    // 0 where E == H   (UP)
-                            uint32_t nhe = O::min2(Hg - Fi, one_s);   // 0 where F == H   (LEFT)
                             uint32_t E2 = O::addmax(E, neg_ge, H);
                             uint32_t F2 = O::addmax(Fi, neg_ge, H);
-                            uint32_t xv = O::min2(E2 - H, one_s);     // 1 where next-row E extends (UP_EXT)
-                            uint32_t xh = O::min2(F2 - H, one_s);     // 1 where next-col F extends (LEFT_EXT)
-                            uint32_t ns = O::min2(H, one_s);          // 0 where H == 0   (STOP)
-                            uint32_t code = c21 + 2u * xv + 8u * xh - nve - 4u * nhe - 16u * ns;
-                            words[i / 3] += code << (5 * (i % 3));
+                            if (FLAGS) {
+                                uint32_t Hg = H + go_s;
+                                uint32_t nve = O::min2(Hg - E, one_s);    // 0 where E == H   (UP)
+                                uint32_t nhe = O::min2(Hg - Fi, one_s);   // 0 where F == H   (LEFT)
+                                uint32_t xv = O::min2(E2 - H, one_s);     // 1 where next-row E extends (UP_EXT)
+                                uint32_t xh = O::min2(F2 - H, one_s);     // 1 where next-col F extends (LEFT_EXT)
+                                uint32_t ns = O::min2(H, one_s);          // 0 where H == 0   (STOP)
+                                uint32_t code = c21 + 2u * xv + 8u * xh - nve - 4u * nhe - 16u * ns;
+                                words[i / 3] += code << (5 * (i % 3));
+                            }
                             E = E2;
                             Frow[i] = F2;
                             Hrow[i] = H;
@@ -619,7 +661,7 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                 e_out = E;
                 // ---- pin the best cell down: smallest row, then smallest column (striped.rs:555-583) ----
                 const uint32_t s_abs = ws + (uint32_t)step;
-                if ((uint32_t)lig == ls_lo && s_abs - fs_lo <= 1u) {
+                if ((uint32_t)lig == ls_lo && s_abs >= fs_lo && s_abs <= se_lo) {
                     int irow = K;
 #pragma unroll
                     for (int i = K - 1; i >= 0; --i)
@@ -629,7 +671,7 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                         bj_lo = j;
                     }
                 }
-                if ((uint32_t)lig == ls_hi && s_abs - fs_hi <= 1u) {
+                if ((uint32_t)lig == ls_hi && s_abs >= fs_hi && s_abs <= se_hi) {
                     int irow = K;
 #pragma unroll
                     for (int i = K - 1; i >= 0; --i)
@@ -639,7 +681,7 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                         bj_hi = j;
                     }
                 }
-                if (valid) {
+                if (FLAGS && valid) {
 #pragma unroll
                     for (int w = 0; w < NW; w += 4)
                         *reinterpret_cast<uint4 *>(fl + (size_t)jw * (G * NW) + w) =
@@ -649,18 +691,30 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
             h_up_prev = h_in;
         }
         // the winning lane publishes the exact end cell (the walk starts there)
+        // (pin mode: the cell goes back into pass A's representation -- winning lane, even step of the column
+        //  pair -- now unambiguous, so the pair joins the regular classification)
         if ((uint32_t)lig == ls_lo) {
             if (bi_lo < K) {
-                wp.ends[g_lo].r_end = ls_lo * K + (uint32_t)bi_lo;
-                wp.ends[g_lo].c_end = (uint32_t)bj_lo;
+                if (wp.pin_mode) {
+                    wp.ends[g_lo].c_end = ((uint32_t)bj_lo + ls_lo) & ~1u;
+                    wp.ends[g_lo].aux = ((uint32_t)bj_lo + ls_lo) & ~1u;
+                } else {
+                    wp.ends[g_lo].r_end = ls_lo * K + (uint32_t)bi_lo;
+                    wp.ends[g_lo].c_end = (uint32_t)bj_lo;
+                }
             } else {
                 atomicAdd(&wp.counters[7], 1ULL);  // pass A and pass B disagree: reported as an internal error
             }
         }
         if ((uint32_t)lig == ls_hi) {
             if (bi_hi < K) {
-                wp.ends[g_hi].r_end = ls_hi * K + (uint32_t)bi_hi;
-                wp.ends[g_hi].c_end = (uint32_t)bj_hi;
+                if (wp.pin_mode) {
+                    wp.ends[g_hi].c_end = ((uint32_t)bj_hi + ls_hi) & ~1u;
+                    wp.ends[g_hi].aux = ((uint32_t)bj_hi + ls_hi) & ~1u;
+                } else {
+                    wp.ends[g_hi].r_end = ls_hi * K + (uint32_t)bi_hi;
+                    wp.ends[g_hi].c_end = (uint32_t)bj_hi;
+                }
             } else {
                 atomicAdd(&wp.counters[7], 1ULL);
             }

@@ -75,8 +75,6 @@ struct Device {
     size_t free_at_create = 0;  // cudaMemGetInfo is slow (tens of ms on a 180 GB part): asked once
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
-    cudaStream_t stream2 = nullptr;  // the literal kernel overlaps the full-matrix redo stage on this one
-    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
     // scoring + profiled (replicated on every device)
     DevBuf ccodes, coff, wk, lut, corder;
     // batch state
@@ -85,7 +83,7 @@ struct Device {
     DevBuf pbytes, ends, flags, flag_base, ref_start, ref_end, query_start, query_end, hazard, hazard_list;
     DevBuf cig_scratch, cig_count, cig_off, cig_out, ex_hbuf, ex_fbuf, ex_cig, weights;
     // windowed align path (sw_align_win.cuh)
-    DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems, redo_flag, redo_ids, redo_flags;
+    DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems;
     DevBuf starts;  // ranges: reverse-pass results
     DevBuf cig_bsum;  // CIGAR scan: per-block sums
     uint64_t cig_total = 0;
@@ -106,13 +104,16 @@ struct KernelEntry {
     void (*winfill)(const WinParams);    // windowed align, pass B
     void (*ends)(const EndsParams);      // score + end cell (ranges), packed
     void (*ends_wide)(const EndsParams); // ... 32-bit
+    void (*scan_g)(const WinParams);     // pass A with the profiled symbol codes read from global memory (sets > 96 KB)
+    void (*pin)(const WinParams);        // windowed align: exact best cell of the pairs whose maximum recurs
 };
 
 #define ZK(G, K) \
     KernelEntry {                                                                                          \
         G, K, sw_score_kernel<G, K, true, 1>, sw_score_kernel<G, K, false, 1>, sw_align_fill_kernel<G, K, true>, \
             sw_score_kernel<G, K, true, 2>, sw_align_scan_kernel<G, K>, sw_align_winfill_kernel<G, K>,     \
-            sw_ends_kernel<G, K, true>, sw_ends_kernel<G, K, false>                                         \
+            sw_ends_kernel<G, K, true>, sw_ends_kernel<G, K, false>, sw_align_scan_kernel<G, K, false>,     \
+            sw_align_winfill_kernel<G, K, false>                                                            \
     }
 
 // Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
@@ -883,8 +884,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     const uint32_t CB = 1u << cb_log2;
     // window capacity in columns: the walk's reach + the distance to the previous checkpoint + the lane skew
     const uint32_t wmax = std::min<uint32_t>(ctx->max_prof_len, std::max<uint32_t>(ctx->staged_max_len, 1) + ctx->win_slack + CB) + k->G;
-    // (the scan kernel stages the profiled sequences in shared memory: they must fit)
-    const bool window_ok = ctx->go != 0 && ctx->ccodes.size() <= 96 * 1024;
+    const bool window_ok = ctx->go != 0;
     bool use_window = window_ok && (uint64_t)ctx->max_prof_len >= 2ull * wmax;
     if (ctx->align_mode == 1) use_window = false;
     if (ctx->align_mode == 2) use_window = window_ok;
@@ -937,8 +937,6 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         CU(ctx, d.win_bucket.reserve((n_keys + 1) * sizeof(uint32_t)));
         CU(ctx, d.win_items.reserve(max_items * sizeof(uint32_t)));
         CU(ctx, d.win_nitems.reserve(sizeof(uint32_t)));
-        CU(ctx, d.redo_flag.reserve(chunk_seqs));
-        CU(ctx, d.redo_ids.reserve((chunk_seqs + 1) * sizeof(uint32_t)));
     } else {
         CU(ctx, d.flags.reserve(((chunk_seqs + 1) / 2) * task_stride * 4));
     }
@@ -960,14 +958,24 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
 
     DebugTimer dbg;
     LaunchPlan plan, plan_b;
+    // pass A comes in two instantiations: profiled symbol codes staged in shared memory, or (sets > 96 KB) read from
+    // global memory; plan_launch tells which one fits
     int rc = use_window ? plan_launch(ctx, *k, k->scan, &plan) : plan_launch(ctx, *k, k->fill, &plan);
     if (rc) return rc;
-    if (use_window && !plan.cols_in_smem)
-        return fail(ctx, ZOE_CUDA_E_STATE, "internal error: window pipeline planned without staged columns");
+    void (*scan_fn)(const WinParams) = k->scan;
+    if (use_window && !plan.cols_in_smem) {
+        scan_fn = k->scan_g;
+        rc = plan_launch(ctx, *k, scan_fn, &plan);
+        if (rc) return rc;
+    }
+    LaunchPlan plan_p;
     if (use_window) {
         rc = plan_launch(ctx, *k, k->winfill, &plan_b);
         if (rc) return rc;
-        CU(ctx, cudaFuncSetAttribute(k->scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        rc = plan_launch(ctx, *k, k->pin, &plan_p);
+        if (rc) return rc;
+        CU(ctx, cudaFuncSetAttribute(k->pin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_p.smem));
+        CU(ctx, cudaFuncSetAttribute(scan_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
         CU(ctx, cudaFuncSetAttribute(k->winfill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_b.smem));
     } else {
         CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
@@ -1106,8 +1114,6 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             ctx->last_launches++;
             return 0;
         };
-        uint32_t exact_done = 0;  // pairs already handed to the literal kernel on the second stream
-
         const uint32_t cpairs = cn * n_prof;
         if (!use_window) {
             sw_traceback_kernel<<<(cpairs + 127) / 128, 128, 0, d.stream>>>(t);
@@ -1134,12 +1140,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             wp.wmax = wmax;
             wp.counters = ctr;
             const uint64_t max_items = (uint64_t)cpairs + n_keys + 2;
-            CU(ctx, cudaMemsetAsync(d.win_hist.p, 0, n_keys * sizeof(uint32_t), d.stream));
-            CU(ctx, cudaMemsetAsync(d.win_items.p, 0xff, max_items * sizeof(uint32_t), d.stream));
-            CU(ctx, cudaMemsetAsync(d.redo_flag.p, 0, cn, d.stream));
-            CU(ctx, cudaMemsetAsync(ctr + 12, 0, sizeof(unsigned long long), d.stream));  // [12] redo list length
             CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
-            k->scan<<<blocks, plan.threads, plan.smem, d.stream>>>(wp);
+            scan_fn<<<blocks, plan.threads, plan.smem, d.stream>>>(wp);
             CU(ctx, cudaGetLastError());
             ClassifyParams cp{};
             cp.ends = ap.ends;
@@ -1149,7 +1151,6 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             cp.chunk_first = (uint32_t)c0;
             cp.n_slots = cn;
             cp.K = k->K;
-            cp.redo_flag = d.redo_flag.as<uint8_t>();
             cp.cb_log2 = cb_log2;
             cp.slack = ctx->win_slack;
             cp.nblk = nblk;
@@ -1168,14 +1169,39 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             cp.cig_count = t.cig_count;
             cp.counters = ctr;
             cp.hazard_list = t.hazard_list;
-            win_classify_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp);
-            CU(ctx, cudaGetLastError());
-            win_bucket_scan_kernel<<<1, 1024, 0, d.stream>>>(wp.hist, n_keys, wp.bucket_start, wp.n_items);
-            CU(ctx, cudaGetLastError());
-            win_scatter_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp, wp.bucket_start, wp.items);
-            CU(ctx, cudaGetLastError());
+            // counting sort of the selected pairs by (profiled sequence, checkpoint block) into wp.items
+            auto bucket = [&](int pin_stage) -> int {
+                cp.pin_stage = pin_stage;
+                CU(ctx, cudaMemsetAsync(d.win_hist.p, 0, n_keys * sizeof(uint32_t), d.stream));
+                CU(ctx, cudaMemsetAsync(d.win_items.p, 0xff, max_items * sizeof(uint32_t), d.stream));
+                win_classify_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp);
+                CU(ctx, cudaGetLastError());
+                win_bucket_scan_kernel<<<1, 1024, 0, d.stream>>>(wp.hist, n_keys, wp.bucket_start, wp.n_items);
+                CU(ctx, cudaGetLastError());
+                win_scatter_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp, wp.bucket_start, wp.items);
+                CU(ctx, cudaGetLastError());
+                ctx->last_launches += 3;
+                return 0;
+            };
+            // ---- pin stage: pairs whose maximum recurs in the winning lane get their exact best cell ----
+            rc = bucket(1);
+            if (rc) return rc;
+            {
+                WinParams wq = wp;
+                wq.pin_mode = 1;
+                wq.s.cols_in_smem = plan_p.cols_in_smem;
+                const uint32_t gpb = plan_p.threads / k->G;
+                const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_p.blocks_per_sm),
+                                                       (uint32_t)((max_items / 2 + gpb - 1) / gpb));
+                k->pin<<<nb, plan_p.threads, plan_p.smem, d.stream>>>(wq);
+                CU(ctx, cudaGetLastError());
+            }
+            // ---- classification proper, window fill, walk ----
+            rc = bucket(0);
+            if (rc) return rc;
             {
                 WinParams wb = wp;
+                wb.pin_mode = 0;
                 wb.s.cols_in_smem = plan_b.cols_in_smem;
                 const uint32_t gpb = plan_b.threads / k->G;
                 const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_b.blocks_per_sm),
@@ -1194,58 +1220,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             tw.slack = ctx->win_slack;
             sw_traceback_win_kernel<<<(uint32_t)((max_items + 127) / 128), 128, 0, d.stream>>>(tw);
             CU(ctx, cudaGetLastError());
-            win_collect_redo_kernel<<<(cn + 255) / 256, 256, 0, d.stream>>>(cp.redo_flag, (uint32_t)c0, cn,
-                                                                            d.redo_ids.as<uint32_t>(), ctr);
-            CU(ctx, cudaGetLastError());
-            ctx->last_launches += 7;
-            // ---- sequences with an ambiguous end cell: the full-matrix pipeline on that (short) list ----
-            unsigned long long n_redo = 0, early[4] = {0, 0, 0, 0};  // ctr[5] exact-list length .. ctr[8] packed overflows
-            CU(ctx, cudaMemcpyAsync(&n_redo, ctr + 12, sizeof(n_redo), cudaMemcpyDeviceToHost, d.stream));
-            CU(ctx, cudaMemcpyAsync(early, ctr + 5, sizeof(early), cudaMemcpyDeviceToHost, d.stream));
-            CU(ctx, cudaStreamSynchronize(d.stream));
-            if (n_redo && early[0] && early[3] == 0) {
-                // the hazards found so far run on the second stream while the redo stage occupies the first
-                // (the literal kernel is latency-bound: a handful of warps for milliseconds)
-                CU(ctx, cudaEventRecord(d.ev_x0, d.stream));
-                CU(ctx, cudaStreamWaitEvent(d.stream2, d.ev_x0, 0));
-                // every pair of a redone sequence may still join the list: reserve its CIGAR rows now
-                rc = launch_exact(0, (uint32_t)early[0], (uint32_t)std::min<uint64_t>(cpairs, early[0] + n_redo * n_prof), d.stream2);
-                if (rc) return rc;
-                CU(ctx, cudaEventRecord(d.ev_x1, d.stream2));
-                exact_done = (uint32_t)early[0];
-            }
-            if (n_redo) {
-                LaunchPlan plan_f;
-                rc = plan_launch(ctx, *k, k->fill, &plan_f);
-                if (rc) return rc;
-                CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_f.smem));
-                const uint64_t sub_cap = std::max<uint64_t>(2, (((uint64_t)8 << 30) / (task_stride * 4)) * 2);  // <= 8 GB of flags
-                CU(ctx, d.redo_flags.reserve(((std::min<uint64_t>(n_redo, sub_cap) + 1) / 2) * task_stride * 4));
-                for (uint64_t r0 = 0; r0 < n_redo; r0 += sub_cap) {
-                    const uint32_t rn = (uint32_t)std::min<uint64_t>(sub_cap, n_redo - r0);
-                    AlignParams fa = ap;
-                    fa.s.task_ids = d.redo_ids.as<uint32_t>() + r0;
-                    fa.s.n_rseq = rn;
-                    fa.s.n_tasks = (rn + 1) / 2;
-                    fa.s.cols_in_smem = plan_f.cols_in_smem;
-                    fa.flags = d.redo_flags.as<uint32_t>();
-                    const uint32_t gpb = plan_f.threads / k->G;
-                    // leave one SM to the literal kernel running on the second stream (its block needs > 100 KB of
-                    // shared memory and could not co-reside with a fill block)
-                    const int sms_for_fill = exact_done ? std::max(1, d.sm_count - 1) : d.sm_count;
-                    const uint32_t nb = std::min<uint32_t>((uint32_t)(sms_for_fill * plan_f.blocks_per_sm), (fa.s.n_tasks + gpb - 1) / gpb);
-                    k->fill<<<nb, plan_f.threads, plan_f.smem, d.stream>>>(fa);
-                    CU(ctx, cudaGetLastError());
-                    TraceParams tr = t;
-                    tr.flags = fa.flags;
-                    tr.seq_ids = fa.s.task_ids;
-                    tr.n_slots = rn;
-                    tr.only_ambiguous = 1;
-                    sw_traceback_kernel<<<(rn * n_prof + 127) / 128, 128, 0, d.stream>>>(tr);
-                    CU(ctx, cudaGetLastError());
-                    ctx->last_launches += 2;
-                }
-            }
+            ctx->last_launches += 4;
         }
 
         unsigned long long hc[5] = {0, 0, 0, 0, 0};  // ctr[4..8]
@@ -1280,9 +1255,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                 ctx->stats.rerun_wide += hc[4];
             }
         }
-        if (exact_done) CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_x1, 0));
-        if (n_exact > exact_done) {
-            rc = launch_exact(exact_done, n_exact - exact_done, n_exact, d.stream);
+        if (n_exact > 0) {
+            rc = launch_exact(0, n_exact, n_exact, d.stream);
             if (rc) return rc;
         }
         if (n_exact > 0) {
@@ -1336,7 +1310,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->stats.window_fallback += win_fb[0];
-        ctx->stats.window_redo += win_fb[1];
+        ctx->stats.window_pinned += win_fb[1];
         ctx->stats.hazard -= std::min<uint64_t>(ctx->stats.hazard, win_fb[0]);
         ctx->last_dp_ms = std::max(ctx->last_dp_ms, dp_ms_total);
     }
@@ -1551,10 +1525,7 @@ int zoe_cuda_create(zoe_cuda_ctx **out, const int *device_ids, int n_devices) {
             [&] { size_t tot = 0; return cudaMemGetInfo(&d.free_at_create, &tot); }() != cudaSuccess ||
             cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreate(&d.ev_begin) != cudaSuccess || cudaEventCreate(&d.ev_end) != cudaSuccess ||
-            cudaEventCreate(&d.ev_k0) != cudaSuccess || cudaEventCreate(&d.ev_k1) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&d.ev_x0, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&d.ev_x1, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreate(&d.ev_k0) != cudaSuccess || cudaEventCreate(&d.ev_k1) != cudaSuccess) {
             delete ctx;
             return ZOE_CUDA_E_CUDA;
         }
@@ -1572,16 +1543,12 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.long_ids, &d.long_bnd,
-                          &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.redo_flag,
-                          &d.redo_ids, &d.redo_flags, &d.starts, &d.cig_bsum})
+                          &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.starts, &d.cig_bsum})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.ev_k0) cudaEventDestroy(d.ev_k0);
         if (d.ev_k1) cudaEventDestroy(d.ev_k1);
-        if (d.ev_x0) cudaEventDestroy(d.ev_x0);
-        if (d.ev_x1) cudaEventDestroy(d.ev_x1);
-        if (d.stream2) cudaStreamDestroy(d.stream2);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
