@@ -65,7 +65,8 @@ struct WinParams {
     uint64_t win_task_stride;    // words per pass-B task = Wmax * G * NW
     uint32_t wmax;               // window capacity in columns
     unsigned long long *counters; // [7] internal consistency failures
-    int pin_mode;                // 1: pin sweep over the ambiguous pairs (no flags), 0: window fill
+    int pin_mode;                // 0: window fill; 1: pin sweep, result back in pass A's representation;
+                                 // 2: pin sweep, exact (row, column) published (ranges)
 };
 
 // Pass A leaves (winning lane, even step of the first column pair); the best cell is one of that lane's K rows in
@@ -318,7 +319,8 @@ struct ClassifyParams {
     uint32_t slack, nblk;
     int all_exact;
     uint32_t *hist;
-    int pin_stage;                 // 1: select the ambiguous pairs for the pin sweep; 0: the classification proper
+    int pin_stage;                 // 1: select the ambiguous pairs for the pin sweep; 2: every mapped pair (ranges);
+                                   // 0: the classification proper
     int32_t *best_arr;
     uint32_t *score;
     uint8_t *status, *tier, *hazard;
@@ -350,9 +352,9 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
     const AlignEnd e = t.ends[gid];
     const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
     if (t.pin_stage) {  // ambiguous end cells only: bucket them by (profiled sequence, checkpoint block)
-        if (win_eligible(e, n, t.tp, t.all_exact) && e.aux != e.c_end) {
+        if (win_eligible(e, n, t.tp, t.all_exact) && (t.pin_stage == 2 || e.aux != e.c_end)) {
             atomicAdd(&t.hist[cj * t.nblk + (pin_start(e.c_end, t.coff[cj + 1] - t.coff[cj], t.cb_log2) >> t.cb_log2)], 1u);
-            atomicAdd(&t.counters[11], 1ULL);
+            if (e.aux != e.c_end) atomicAdd(&t.counters[11], 1ULL);
         }
         return;
     }
@@ -456,7 +458,7 @@ __global__ void win_scatter_kernel(const ClassifyParams t, const uint32_t *bucke
     uint32_t key;
     if (t.pin_stage) {
         const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
-        if (!(win_eligible(e, n, t.tp, t.all_exact) && e.aux != e.c_end)) return;
+        if (!(win_eligible(e, n, t.tp, t.all_exact) && (t.pin_stage == 2 || e.aux != e.c_end))) return;
         key = cj * t.nblk + (pin_start(e.c_end, t.coff[cj + 1] - t.coff[cj], t.cb_log2) >> t.cb_log2);
     } else {
         if (e.aux == kNotBucketed) return;  // unmapped / overflowed / literal-only
@@ -695,7 +697,7 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
         //  pair -- now unambiguous, so the pair joins the regular classification)
         if ((uint32_t)lig == ls_lo) {
             if (bi_lo < K) {
-                if (wp.pin_mode) {
+                if (wp.pin_mode == 1) {
                     wp.ends[g_lo].c_end = ((uint32_t)bj_lo + ls_lo) & ~1u;
                     wp.ends[g_lo].aux = ((uint32_t)bj_lo + ls_lo) & ~1u;
                 } else {
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
         }
         if ((uint32_t)lig == ls_hi) {
             if (bi_hi < K) {
-                if (wp.pin_mode) {
+                if (wp.pin_mode == 1) {
                     wp.ends[g_hi].c_end = ((uint32_t)bj_hi + ls_hi) & ~1u;
                     wp.ends[g_hi].aux = ((uint32_t)bj_hi + ls_hi) & ~1u;
                 } else {

@@ -1390,8 +1390,109 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
     const uint32_t gpb = plan.threads / k->G;
     const uint32_t max_blocks = (uint32_t)(d.sm_count * plan.blocks_per_sm);
     CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
-    fn<<<std::min<uint32_t>(max_blocks, (p.n_tasks + gpb - 1) / gpb), plan.threads, plan.smem, d.stream>>>(ep);
-    CU(ctx, cudaGetLastError());
+    if (packed && !getenv("ZOE_CUDA_RANGES_SLOW")) {
+        // ---- forward pass, fast: the align pipeline's pass A (score-rate scan + checkpoints) followed by a pin sweep
+        //      of every mapped pair from the checkpoint before its first best column pair (about CB/2 columns) ----
+        int cb_log2 = ctx->win_cb_log2;
+        while ((1 << cb_log2) < k->G) ++cb_log2;
+        const int CKW = ckpt_words_per_lane(k->K);
+        std::vector<uint64_t> ckpt_base(n_prof);
+        uint64_t ckpt_task_stride = 0;
+        uint32_t nblk = 1;
+        for (uint32_t j = 0; j < n_prof; ++j) {
+            const uint64_t L = ctx->coff[j + 1] - ctx->coff[j];
+            ckpt_base[j] = ckpt_task_stride;
+            ckpt_task_stride += ((L - 1) >> cb_log2) * (uint64_t)CKW * k->G;
+            nblk = std::max<uint32_t>(nblk, (uint32_t)((L - 1) >> cb_log2) + 1);
+        }
+        const uint32_t pin_keys = n_prof * nblk;
+        uint64_t budget = ctx->flag_budget_bytes ? ctx->flag_budget_bytes : (uint64_t)(d.free_at_create * 0.55);
+        budget = std::min<uint64_t>(budget, (uint64_t)48 << 30);
+        uint64_t chunk_seqs = std::min<uint64_t>(d.n_count, 2 * std::max<uint64_t>(1, budget / std::max<uint64_t>(ckpt_task_stride * 4, 1)));
+        if (chunk_seqs > 1) chunk_seqs &= ~1ULL;
+        LaunchPlan plan_a, plan_p;
+        void (*scan_fn)(const WinParams) = k->scan;
+        int rc2 = plan_launch(ctx, *k, scan_fn, &plan_a);
+        if (rc2) return rc2;
+        if (!plan_a.cols_in_smem) {
+            scan_fn = k->scan_g;
+            rc2 = plan_launch(ctx, *k, scan_fn, &plan_a);
+            if (rc2) return rc2;
+        }
+        rc2 = plan_launch(ctx, *k, k->pin, &plan_p);
+        if (rc2) return rc2;
+        CU(ctx, cudaFuncSetAttribute(scan_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_a.smem));
+        CU(ctx, cudaFuncSetAttribute(k->pin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_p.smem));
+        CU(ctx, d.ckpt.reserve(std::max<uint64_t>(((chunk_seqs + 1) / 2) * ckpt_task_stride * 4, 16)));
+        CU(ctx, d.ckpt_base.reserve(n_prof * sizeof(uint64_t)));
+        CU(ctx, cudaMemcpyAsync(d.ckpt_base.p, ckpt_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        // (win_hist / win_bucket / win_items are sized for the larger key space of the reverse pass below)
+        for (uint64_t c0 = 0; c0 < d.n_count; c0 += chunk_seqs) {
+            const uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_seqs, d.n_count - c0);
+            const uint32_t cpairs = cn * n_prof;
+            const uint64_t chunk_items = (uint64_t)cpairs + pin_keys + 2;
+            WinParams wp{};
+            wp.s = p;
+            wp.s.n_rseq = cn;
+            wp.s.n_tasks = (cn + 1) / 2;
+            wp.s.cols_in_smem = plan_a.cols_in_smem;
+            wp.ends = d.ends.as<AlignEnd>();
+            wp.chunk_first = (uint32_t)c0;
+            wp.ckpt = d.ckpt.as<uint32_t>();
+            wp.ckpt_base = d.ckpt_base.as<uint64_t>();
+            wp.ckpt_task_stride = ckpt_task_stride;
+            wp.cb_log2 = cb_log2;
+            wp.slack = ctx->win_slack;
+            wp.nblk = nblk;
+            wp.hist = d.win_hist.as<uint32_t>();
+            wp.bucket_start = d.win_bucket.as<uint32_t>();
+            wp.items = d.win_items.as<uint32_t>();
+            wp.n_items = d.win_nitems.as<uint32_t>();
+            wp.counters = ctr;
+            const uint32_t gpa = plan_a.threads / k->G;
+            scan_fn<<<std::min<uint32_t>((uint32_t)(d.sm_count * plan_a.blocks_per_sm), (wp.s.n_tasks + gpa - 1) / gpa),
+                      plan_a.threads, plan_a.smem, d.stream>>>(wp);
+            CU(ctx, cudaGetLastError());
+            ClassifyParams cp{};
+            cp.ends = d.ends.as<AlignEnd>();
+            cp.roff = p.roff;
+            cp.coff = p.coff;
+            cp.n_cseq = n_prof;
+            cp.chunk_first = (uint32_t)c0;
+            cp.n_slots = cn;
+            cp.K = k->K;
+            cp.cb_log2 = cb_log2;
+            cp.slack = ctx->win_slack;
+            cp.nblk = nblk;
+            cp.all_exact = 0;
+            cp.tp = ctx->tp;
+            cp.hist = wp.hist;
+            cp.counters = ctr;
+            cp.pin_stage = 2;
+            CU(ctx, cudaMemsetAsync(d.win_hist.p, 0, pin_keys * sizeof(uint32_t), d.stream));
+            CU(ctx, cudaMemsetAsync(d.win_items.p, 0xff, chunk_items * sizeof(uint32_t), d.stream));
+            win_classify_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp);
+            CU(ctx, cudaGetLastError());
+            win_bucket_scan_kernel<<<1, 1024, 0, d.stream>>>(wp.hist, pin_keys, wp.bucket_start, wp.n_items);
+            CU(ctx, cudaGetLastError());
+            win_scatter_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp, wp.bucket_start, wp.items);
+            CU(ctx, cudaGetLastError());
+            WinParams wq = wp;
+            wq.pin_mode = 2;
+            wq.s.cols_in_smem = plan_p.cols_in_smem;
+            const uint32_t gpp = plan_p.threads / k->G;
+            k->pin<<<std::min<uint32_t>((uint32_t)(d.sm_count * plan_p.blocks_per_sm), (uint32_t)((chunk_items / 2 + gpp - 1) / gpp)),
+                     plan_p.threads, plan_p.smem, d.stream>>>(wq);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches += 5;
+        }
+        CU(ctx, cudaMemsetAsync(d.win_hist.p, 0, n_keys * sizeof(uint32_t), d.stream));
+        CU(ctx, cudaMemsetAsync(d.win_items.p, 0xff, max_items * sizeof(uint32_t), d.stream));
+    } else {
+        fn<<<std::min<uint32_t>(max_blocks, (p.n_tasks + gpb - 1) / gpb), plan.threads, plan.smem, d.stream>>>(ep);
+        CU(ctx, cudaGetLastError());
+    }
 
     RangesParams rp{};
     rp.ends = d.ends.as<AlignEnd>();
