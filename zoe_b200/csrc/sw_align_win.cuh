@@ -65,6 +65,9 @@ struct WinParams {
     uint64_t win_task_stride;    // words per pass-B task = Wmax * G * NW
     uint32_t wmax;               // window capacity in columns
     unsigned long long *counters; // [7] internal consistency failures
+    // reverse instantiation of pass A (ranges, sw_ranges.cuh): tasks = pairs of `items` sharing (profiled, end column)
+    const AlignEnd *rev_in;      // forward end cells (exact)
+    AlignEnd *rev_out;           // (best, r', c') of the reversed, truncated sub-problem
     int pin_mode;                // 0: window fill; 1: pin sweep, result back in pass A's representation;
                                  // 2: pin sweep, exact (row, column) published (ranges)
 };
@@ -99,7 +102,11 @@ __device__ __forceinline__ uint32_t win_start(uint32_t r_end, uint32_t c_end, ui
 // CSM = the profiled symbol codes are staged in shared memory (LDS with a 32-bit address in the hot loop); false = a
 // profiled set too large for that (> 96 KB): the codes are read from global memory (L1-resident: every warp of the
 // SM walks the same sequences).
-template <int G, int K, bool CSM = true>
+// REV = the reverse pass of sw_simd_score_ranges (striped.rs:355-388): a task is two (streamed, profiled) items that
+// share the profiled sequence and the end column; rows = each item's reversed prefix streamed[r_end], streamed[r_end-1],
+// ..., columns = profiled[c_end], profiled[c_end-1], ...; no checkpoints -- the reversed alignment starts in the
+// corner, so the exact best cell is pinned by re-sweeping the first columns from scratch inside the same kernel.
+template <int G, int K, bool CSM = true, bool REV = false>
 __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const WinParams wp) {
     using O = Ops<true>;
     const ScoreParams &p = wp.s;
@@ -126,39 +133,66 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
     uint32_t tab_lane_off = (uint32_t)group_in_block * (uint32_t)tab_bytes + (uint32_t)lig * 16u;
     asm volatile("" : "+r"(go_s), "+r"(neg_ge), "+r"(tab_lane_off));
 
+    const uint32_t n_tasks = REV ? *wp.n_items / 2 : p.n_tasks;
     const uint32_t total_groups = gridDim.x * groups_per_block;
-    const uint32_t trips = (p.n_tasks + total_groups - 1) / total_groups;
+    const uint32_t trips = (n_tasks + total_groups - 1) / total_groups;
     const uint32_t first = blockIdx.x * groups_per_block + group_in_block;
 
     for (uint32_t trip = 0; trip < trips; ++trip) {
         const uint32_t task = first + trip * total_groups;
-        const bool valid = task < p.n_tasks;
+        const bool valid = task < n_tasks;
         uint32_t id_lo = 0xffffffffu, id_hi = 0xffffffffu;
-        if (valid) {
-            const uint32_t a = 2 * task, b = 2 * task + 1;
-            id_lo = wp.chunk_first + a;
-            id_hi = (b < p.n_rseq) ? wp.chunk_first + b : 0xffffffffu;
-        }
-        uint64_t off_lo = 0, off_hi = 0;
+        uint32_t g_lo = 0xffffffffu, g_hi = 0xffffffffu;  // REV: global pair ids
+        uint64_t off_lo = 0, off_hi = 0;                   // byte offset of row 0
         int len_lo = 0, len_hi = 0;
-        if (id_lo != 0xffffffffu) {
-            off_lo = p.roff[id_lo];
-            len_lo = (int)(p.roff[id_lo + 1] - off_lo);
+        uint32_t rev_cj = 0;
+        int rev_cend = -1;
+        if (!REV) {
+            if (valid) {
+                const uint32_t a = 2 * task, b = 2 * task + 1;
+                id_lo = wp.chunk_first + a;
+                id_hi = (b < p.n_rseq) ? wp.chunk_first + b : 0xffffffffu;
+            }
+            if (id_lo != 0xffffffffu) {
+                off_lo = p.roff[id_lo];
+                len_lo = (int)(p.roff[id_lo + 1] - off_lo);
+            }
+            if (id_hi != 0xffffffffu) {
+                off_hi = p.roff[id_hi];
+                len_hi = (int)(p.roff[id_hi + 1] - off_hi);
+            }
+        } else {
+            if (valid) {
+                g_lo = wp.items[2 * task];
+                g_hi = wp.items[2 * task + 1];
+            }
+            if (g_lo != 0xffffffffu) {
+                const AlignEnd e = wp.rev_in[g_lo];
+                id_lo = g_lo / p.n_cseq;
+                rev_cj = g_lo % p.n_cseq;
+                rev_cend = (int)e.c_end;
+                off_lo = p.roff[id_lo] + e.r_end;  // row r' reads streamed[r_end - r']
+                len_lo = (int)e.r_end + 1;
+            }
+            if (g_hi != 0xffffffffu) {
+                const AlignEnd e = wp.rev_in[g_hi];
+                id_hi = g_hi / p.n_cseq;
+                off_hi = p.roff[id_hi] + e.r_end;
+                len_hi = (int)e.r_end + 1;
+            }
         }
-        if (id_hi != 0xffffffffu) {
-            off_hi = p.roff[id_hi];
-            len_hi = (int)(p.roff[id_hi + 1] - off_hi);
-        }
 
-        build_task_table<G, K, true>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
+        build_task_table<G, K, true>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi, REV ? -1 : 1);
 
-        uint32_t *ck_task = wp.ckpt + (size_t)task * wp.ckpt_task_stride;
+        uint32_t *ck_task = REV ? nullptr : wp.ckpt + (size_t)task * wp.ckpt_task_stride;
 
-        for (uint32_t cj = 0; cj < p.n_cseq; ++cj) {
+        for (uint32_t sweep = 0; sweep < (REV ? 1u : p.n_cseq); ++sweep) {
+            const uint32_t cj = REV ? rev_cj : sweep;
             const uint32_t c0 = p.coff[cj];
-            const int L = (int)(p.coff[cj + 1] - c0);
-            const uint8_t *cs = cc + c0;
-            uint32_t *ck = ck_task + wp.ckpt_base[cj] + lig;
+            // REV: the groups of a warp sweep different numbers of columns (sorted by end column, so nearly equal)
+            const int L = REV ? rev_cend + 1 : (int)(p.coff[cj + 1] - c0);
+            const uint8_t *cs = cc + c0 + (REV ? max(rev_cend, 0) : 0);  // column j reads cs[j] (REV: cs[-j])
+            uint32_t *ck = REV ? nullptr : ck_task + wp.ckpt_base[cj] + lig;
 
             uint32_t H[2][K], F[K];
 #pragma unroll
@@ -171,12 +205,13 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
             // step pair (s >> 1) in which this lane's column maximum reached it
             uint32_t bestp = 0, firstp = 0, lastp = 0;
             uint32_t cm = 0;               // maximum of the column(s) since the last bookkeeping
-            const int nsteps = L + G - 1;
+            const int nsteps = REV ? __reduce_max_sync(FULL, L > 0 ? L + G - 1 : 0) : L + G - 1;
+            const int L_steady = REV ? __reduce_min_sync(FULL, L) : L;  // every lane of every group has a column below it
 
             // one column of this lane: K rows, H read from set PO (column j-1), written to set PN
             auto column = [&](auto parity, const int j, const uint32_t h_in, const uint32_t e_in) {
                 constexpr int PO = decltype(parity)::value, PN = 1 - PO;
-                const uint4 *tp = reinterpret_cast<const uint4 *>(smem + tab_lane_off + (uint32_t)cs[j] * (uint32_t)(K4 * G * 16));
+                const uint4 *tp = reinterpret_cast<const uint4 *>(smem + tab_lane_off + (uint32_t)cs[REV ? -j : j] * (uint32_t)(K4 * G * 16));
                 uint32_t diag = h_up_prev, E = e_in, hp = 0;
 #pragma unroll
                 for (int i4 = 0; i4 < K4; ++i4) {
@@ -247,8 +282,8 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
                 else
                     generic_step(I0{}, s);
             }
-            for (; s + 1 < L; s += 2) {  // steps s and s+1: every lane has a column
-                if ((((uint32_t)s) & cb_mask) == 0 && valid) checkpoint(s);
+            for (; s + 1 < L_steady; s += 2) {  // steps s and s+1: every lane has a column
+                if (!REV && (((uint32_t)s) & cb_mask) == 0 && valid) checkpoint(s);
                 {
                     const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1, G), h_in = lane0 ? 0u : h_sh;
                     const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
@@ -264,7 +299,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
                 bookkeeping((uint32_t)s);
             }
             for (; s < nsteps; ++s) {
-                if ((((uint32_t)s) & cb_mask) == 0 && s >= G && s < L && valid) checkpoint(s);
+                if (!REV && (((uint32_t)s) & cb_mask) == 0 && s >= G && s < L && valid) checkpoint(s);
                 if (s & 1)
                     generic_step(I1{}, s);
                 else
@@ -282,7 +317,77 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
             const int wl_lo = G - 1 - (int)(key_lo & 0xffu), wl_hi = G - 1 - (int)(key_hi & 0xffu);
             const uint32_t f_lo = __shfl_sync(FULL, firstp, wl_lo, G) & 0xffffu, l_lo = __shfl_sync(FULL, lastp, wl_lo, G) & 0xffffu;
             const uint32_t f_hi = __shfl_sync(FULL, firstp, wl_hi, G) >> 16, l_hi = __shfl_sync(FULL, lastp, wl_hi, G) >> 16;
-            if (lig == 0 && valid) {
+            if (REV) {
+                // ---- pin: re-sweep the first columns from scratch; the winning lane looks for the maximum (smallest
+                //      row, then smallest column) in the steps between its first and last occurrence ----
+                const int b_lo = (int)(key_lo >> 8), b_hi = (int)(key_hi >> 8);
+                const int fs_lo = 2 * (int)f_lo, se_lo = 2 * (int)l_lo + 1, fs_hi = 2 * (int)f_hi, se_hi = 2 * (int)l_hi + 1;
+                int last_step = -1;
+                if (g_lo != 0xffffffffu && b_lo > 0) last_step = se_lo;
+                if (g_hi != 0xffffffffu && b_hi > 0) last_step = max(last_step, se_hi);
+                const int n_re = __reduce_max_sync(FULL, last_step + 1);
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    H[0][i] = H[1][i] = 0;
+                    F[i] = 0;
+                }
+                h_last = e_out = h_up_prev = 0;
+                int bi_lo = K, bi_hi = K, bj_lo = 0, bj_hi = 0;
+                auto pin_step = [&](auto parity, const int st) {
+                    constexpr int PN = 1 - decltype(parity)::value;
+                    const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1, G), h_in = lane0 ? 0u : h_sh;
+                    const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
+                    const int j = st - lig;
+                    if (j >= 0 && j < L) {
+                        column(parity, j, h_in, e_in);
+                        if (lig == wl_lo && st >= fs_lo && st <= se_lo) {
+                            int irow = K;
+#pragma unroll
+                            for (int i = K - 1; i >= 0; --i)
+                                if ((int)(int16_t)(H[PN][i] & 0xffffu) == b_lo) irow = i;
+                            if (irow < bi_lo) {
+                                bi_lo = irow;
+                                bj_lo = j;
+                            }
+                        }
+                        if (lig == wl_hi && st >= fs_hi && st <= se_hi) {
+                            int irow = K;
+#pragma unroll
+                            for (int i = K - 1; i >= 0; --i)
+                                if ((int)(int16_t)(H[PN][i] >> 16) == b_hi) irow = i;
+                            if (irow < bi_hi) {
+                                bi_hi = irow;
+                                bj_hi = j;
+                            }
+                        }
+                    }
+                    h_up_prev = h_in;
+                };
+                for (int st = 0; st < n_re; ++st) {
+                    if (st & 1)
+                        pin_step(I1{}, st);
+                    else
+                        pin_step(I0{}, st);
+                }
+                if (g_lo != 0xffffffffu && lig == wl_lo) {
+                    AlignEnd e;
+                    e.best = b_lo;
+                    e.r_end = (uint32_t)(wl_lo * K + bi_lo);
+                    e.c_end = (uint32_t)bj_lo;
+                    e.aux = 0;
+                    if (b_lo > 0 && bi_lo >= K) atomicAdd(&wp.counters[7], 1ULL);  // scan and pin disagree: internal error
+                    wp.rev_out[g_lo] = e;
+                }
+                if (g_hi != 0xffffffffu && lig == wl_hi) {
+                    AlignEnd e;
+                    e.best = b_hi;
+                    e.r_end = (uint32_t)(wl_hi * K + bi_hi);
+                    e.c_end = (uint32_t)bj_hi;
+                    e.aux = 0;
+                    if (b_hi > 0 && bi_hi >= K) atomicAdd(&wp.counters[7], 1ULL);
+                    wp.rev_out[g_hi] = e;
+                }
+            } else if (lig == 0 && valid) {
                 if (id_lo != 0xffffffffu) {
                     AlignEnd e;
                     const int b = (int)(key_lo >> 8);

@@ -106,6 +106,7 @@ struct KernelEntry {
     void (*ends_wide)(const EndsParams); // ... 32-bit
     void (*scan_g)(const WinParams);     // pass A with the profiled symbol codes read from global memory (sets > 96 KB)
     void (*pin)(const WinParams);        // windowed align: exact best cell of the pairs whose maximum recurs
+    void (*scan_rev)(const WinParams);   // ranges: reverse pass (score-rate scan + in-kernel pin)
 };
 
 #define ZK(G, K) \
@@ -113,7 +114,7 @@ struct KernelEntry {
         G, K, sw_score_kernel<G, K, true, 1>, sw_score_kernel<G, K, false, 1>, sw_align_fill_kernel<G, K, true>, \
             sw_score_kernel<G, K, true, 2>, sw_align_scan_kernel<G, K>, sw_align_winfill_kernel<G, K>,     \
             sw_ends_kernel<G, K, true>, sw_ends_kernel<G, K, false>, sw_align_scan_kernel<G, K, false>,     \
-            sw_align_winfill_kernel<G, K, false>                                                            \
+            sw_align_winfill_kernel<G, K, false>, sw_align_scan_kernel<G, K, true, true>                    \
     }
 
 // Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
@@ -1521,14 +1522,40 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
     ranges_scatter_kernel<<<pb, 256, 0, d.stream>>>(rp, d.win_bucket.as<uint32_t>(), d.win_items.as<uint32_t>());
     CU(ctx, cudaGetLastError());
 
-    EndsParams er = ep;
-    er.items = d.win_items.as<uint32_t>();
-    er.n_items = d.win_nitems.as<uint32_t>();
-    er.ends_in = d.ends.as<AlignEnd>();
-    er.out = d.starts.as<AlignEnd>();
     const uint64_t max_tasks = packed ? max_items / 2 : max_items;
-    fn<<<std::min<uint32_t>(max_blocks, (uint32_t)((max_tasks + gpb - 1) / gpb)), plan.threads, plan.smem, d.stream>>>(er);
-    CU(ctx, cudaGetLastError());
+    LaunchPlan plan_r;
+    bool fast_rev = packed && !getenv("ZOE_CUDA_RANGES_SLOW");
+    if (fast_rev) {
+        int rc2 = plan_launch(ctx, *k, k->scan_rev, &plan_r);
+        if (rc2) return rc2;
+        fast_rev = plan_r.cols_in_smem != 0;  // the reverse instantiation reads the profiled codes from shared memory
+    }
+    if (fast_rev) {
+        // ---- reverse pass, fast: pass A's recurrence and bookkeeping over the reversed, truncated sub-problems, the
+        //      exact start cell pinned by re-sweeping the first columns inside the same kernel ----
+        CU(ctx, cudaFuncSetAttribute(k->scan_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_r.smem));
+        WinParams wr{};
+        wr.s = p;
+        wr.s.cols_in_smem = 1;
+        wr.items = d.win_items.as<uint32_t>();
+        wr.n_items = d.win_nitems.as<uint32_t>();
+        wr.rev_in = d.ends.as<AlignEnd>();
+        wr.rev_out = d.starts.as<AlignEnd>();
+        wr.counters = ctr;
+        wr.cb_log2 = ctx->win_cb_log2;
+        const uint32_t gpr = plan_r.threads / k->G;
+        k->scan_rev<<<std::min<uint32_t>((uint32_t)(d.sm_count * plan_r.blocks_per_sm), (uint32_t)((max_tasks + gpr - 1) / gpr)),
+                      plan_r.threads, plan_r.smem, d.stream>>>(wr);
+        CU(ctx, cudaGetLastError());
+    } else {
+        EndsParams er = ep;
+        er.items = d.win_items.as<uint32_t>();
+        er.n_items = d.win_nitems.as<uint32_t>();
+        er.ends_in = d.ends.as<AlignEnd>();
+        er.out = d.starts.as<AlignEnd>();
+        fn<<<std::min<uint32_t>(max_blocks, (uint32_t)((max_tasks + gpb - 1) / gpb)), plan.threads, plan.smem, d.stream>>>(er);
+        CU(ctx, cudaGetLastError());
+    }
     CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
     d.timed_kernel = true;
     ranges_finalize_kernel<<<pb, 256, 0, d.stream>>>(rp);
