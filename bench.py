@@ -194,8 +194,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--n", type=int, default=None, help="override the number of streamed sequences per GPU")
-    ap.add_argument("--mode", default=None, choices=["score", "align", "ranges"],
-                    help="override the workload's mode (ranges = sw_score_ranges: score + alignment ranges, no traceback matrix)")
+    ap.add_argument("--mode", default=None, choices=["score", "align", "ranges", "3pass"],
+                    help="override the workload's mode (ranges = sw_score_ranges: score + alignment ranges, no traceback matrix; "
+                         "3pass = sw_align_from_i8_3pass: ranges + banded alignment of the bounding box)")
     ap.add_argument("--align-opts", default=None, help="mode,checkpoint_log2,slack for zoe_cuda_set_align_options (tuning)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -265,7 +266,8 @@ def main():
         return float(t.item())
 
     stream = torch.cuda.ExternalStream(prof.stream_handle(0), device=torch.device("cuda", local_rank))
-    run_staged = {"score": prof.run_score_staged, "align": prof.run_align_staged, "ranges": prof.run_ranges_staged}[mode]
+    run_staged = {"score": prof.run_score_staged, "align": prof.run_align_staged, "ranges": prof.run_ranges_staged,
+                  "3pass": prof.run_3pass_staged}[mode]
 
     # ---------------- device-resident leg (`value`) ----------------
     prof.stage(h_buf, h_offs)
@@ -340,7 +342,8 @@ def main():
                "ms_per_step": e2e_ms / args.steps,
                "result_checksum": int(outs["score"].sum(dtype=np.uint64)) ^ int(outs["ref_start"].sum(dtype=np.uint64))}
 
-    if mode == "align":
+    if mode in ("align", "3pass"):
+        three_pass = mode == "3pass"
         cap = n * n_prof * 8 + 1024
         t_out = {k: torch.empty(n * n_prof, dtype=torch.int32).pin_memory() for k in
                  ("score", "ref_start", "ref_end", "query_start", "query_end")}
@@ -352,13 +355,13 @@ def main():
         outs["cigar_off"] = t_off.numpy().view(np.uint64)
         outs["cigar"] = t_cig.numpy().view(np.uint32)
         for _ in range(min(args.warmup, 2)):
-            prof.align_into(h_buf, h_offs, outs)
+            prof.align_into(h_buf, h_offs, outs, three_pass=three_pass)
         barrier()
         ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev2.record(stream)
         for _ in range(args.steps):
-            prof.align_into(h_buf, h_offs, outs)
+            prof.align_into(h_buf, h_offs, outs, three_pass=three_pass)
             launches += prof.last_timing()["kernel_launches"]
         ev3.record(stream)
         barrier()
@@ -390,9 +393,11 @@ def main():
             kname, instr = "sw_score_long_kernel (chunked rows, boundary rows through L2)", "4.5 ALU + 1 FMA-pipe"
         else:
             kname, instr = "sw_score_kernel (two column streams, ping-pong register sets)", "4.5 ALU + 1 FMA-pipe"
-    elif mode == "ranges":
-        kname = "sw_ends_kernel forward + reverse (score + end cell with in-loop best-cell bookkeeping)"
+    elif mode in ("ranges", "3pass"):
+        kname = "sw_align_scan_kernel forward (+ pin sweep) and its REV instantiation (score + end / start cell, no traceback matrix)"
         instr = "4.5 ALU + 1 FMA-pipe per cell pair plus per-column bookkeeping; the reverse pass covers the truncated matrix"
+        if mode == "3pass":
+            kname += "; pass 3 = tp_classify / tp_dp kernels (no-gaps shortcut, banded box alignment)"
     else:
         # checkpointed-window pipeline: checkpoints (2K+2 words x 8 lanes per 64 columns per read pair) plus
         # ~5 bits per cell of direction flags for the window of each mapped pair (about 150+16+32+8+10 columns)
@@ -467,7 +472,7 @@ def main():
                          "not vectorised -- a checker, not a tuned baseline"}
         parity = {"checked_pairs": n_sample * n_prof, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c (score, ranges)"}
 
-    if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "align":
+    if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode in ("align", "3pass"):
         from oracle import oracle as O
         sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
         n_sample = min(n, 20000)
@@ -478,7 +483,10 @@ def main():
             for i in range(lo, hi):
                 s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
                 for j, tg in enumerate(targets):
-                    rc, want, _ = O.sw_align_from(bytes(tg), s_i, sc, streamed_is_query=True)
+                    if mode == "3pass":
+                        rc, want, _, _ = O.sw_align_3pass_from(bytes(tg), s_i, sc, streamed_is_query=True)
+                    else:
+                        rc, want, _ = O.sw_align_from(bytes(tg), s_i, sc, streamed_is_query=True)
                     k = i * n_prof + j
                     ok = int(outs["status"][k]) == rc
                     if ok and rc == 0:
@@ -493,7 +501,7 @@ def main():
         mism, oracle_threads = run_threaded(check_range, n_sample)
         dt = time.perf_counter() - t0
         cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": oracle_threads, "kind": "port",
-               "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of sw_simd_align + escalation ({dt:.1f} s); "
+               "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of {'sw_align_3pass' if mode == '3pass' else 'sw_simd_align'} + escalation ({dt:.1f} s); "
                          "not vectorised -- a checker, not a tuned baseline"}
         parity = {"checked_pairs": n_sample * n_prof, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c (score, ranges, CIGAR)"}
 

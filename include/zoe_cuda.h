@@ -123,6 +123,19 @@ int zoe_cuda_sw_score_ranges_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_co
                                    uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
                                    uint32_t *query_start, uint32_t *query_end);
 
+/* Batched ProfileSets::sw_align_from_i8_3pass (src/alignment/profile_set.rs:213-231 -> sw_align_3pass,
+ * src/alignment/sw/three_pass.rs:21-104): the memory-light alignment.  Passes 1 and 2 are the ranges pipeline above
+ * (score, end cell, start cell; no traceback matrix); pass 3 aligns only the bounding box: the no-gaps shortcut when the
+ * diagonal's weights add up to the score, else sw_banded_align (src/alignment/sw/banded.rs:40-133) with band width
+ * |ref_len - query_len| + 1 doubled until the banded score matches, else sw_scalar_align on the box
+ * (src/alignment/sw/scalar.rs:173-271).  Outputs as zoe_cuda_sw_align_batch (the score is the pass-1 score; the CIGAR
+ * carries zoe's soft clips; SeqSrc::Query results are invert()ed).  The CIGAR can differ from sw_align's in equal-score
+ * ties, exactly as zoe's two functions differ.  Streamed sequences up to 1024 residues, alphabets up to 32 symbols. */
+int zoe_cuda_sw_align_3pass_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
+                                  uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
+                                  uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
+                                  uint64_t cigar_cap);
+
 /* Which of zoe's integer types may report a result (default 8..32 signed = ProfileSets::sw_*_from_i8).
  *   first_bits..last_bits   8/16/32: the escalation chain starts at first_bits and stops at last_bits:
  *                 (8,32) = sw_score_from_i8 / sw_align_from_i8, (16,32) = ..._from_i16, (32,32) = ..._from_i32
@@ -154,6 +167,7 @@ int zoe_cuda_stage_streamed(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
 int zoe_cuda_run_score_staged(zoe_cuda_ctx *ctx);
 int zoe_cuda_run_align_staged(zoe_cuda_ctx *ctx);
 int zoe_cuda_run_ranges_staged(zoe_cuda_ctx *ctx);
+int zoe_cuda_run_3pass_staged(zoe_cuda_ctx *ctx);
 int zoe_cuda_fetch_scores(zoe_cuda_ctx *ctx, uint32_t *score, uint8_t *status, uint8_t *tier);
 
 /* Timing of the most recent batch/staged call, from CUDA events on the library's own streams
@@ -168,6 +182,8 @@ typedef struct {
     uint64_t rerun_wide, hazard;
     uint64_t window_fallback; /* pairs whose walk left its checkpoint window (re-done by the literal kernel) */
     uint64_t window_pinned;   /* pairs whose maximum recurs in the winning lane: best cell found by a pin sweep */
+    /* 3-pass alignment: how pass 3 produced the CIGAR (three_pass.rs:39-84) */
+    uint64_t tp_nogaps, tp_banded, tp_scalar, tp_band_attempts;
 } zoe_cuda_stats;
 int zoe_cuda_last_stats(const zoe_cuda_ctx *ctx, zoe_cuda_stats *out);
 

@@ -229,3 +229,45 @@ def striped_profile(profiled: bytes, sc: Scoring, bits: int, lanes: int, signed:
     if rc:
         raise ValueError(f"profile error {rc}")
     return out[: sc.S * nv.value * lanes].reshape(sc.S, nv.value, lanes)
+
+
+def banded_align(profiled: bytes, streamed: bytes, sc: Scoring, band_width: int):
+    """``sw_banded_align(streamed, &ScalarProfile::new(profiled,..), band_width)`` (banded.rs:40-133)."""
+    cap = _cap(profiled, streamed)
+    ops = (C.c_uint8 * cap)()
+    lens = (C.c_uint32 * cap)()
+    a = _Alignment()
+    s = sc.c()
+    rc = lib().zo_banded_align(_buf(profiled), C.c_uint64(len(profiled)), _buf(streamed), C.c_uint64(len(streamed)),
+                               C.byref(s), C.c_uint64(band_width), C.byref(a), ops, lens, cap)
+    return rc, (_mk_aln(a, ops, lens) if rc == SOME else None)
+
+
+def striped_align_3pass(profiled: bytes, streamed: bytes, sc: Scoring, bits: int, lanes: int, signed: bool = True,
+                        streamed_is_query: bool = False):
+    """``StripedProfile::sw_align_3pass(SeqSrc, ..)`` (three_pass.rs:21-104) -> (status, Aln | None, path)."""
+    cap = _cap(profiled, streamed)
+    ops = (C.c_uint8 * cap)()
+    lens = (C.c_uint32 * cap)()
+    a = _Alignment()
+    path = C.c_int(-1)
+    s = sc.c()
+    rc = lib().zo_striped_align_3pass(_buf(profiled), C.c_uint64(len(profiled)), _buf(streamed),
+                                      C.c_uint64(len(streamed)), C.byref(s), bits, int(signed), lanes,
+                                      int(streamed_is_query), C.byref(a), ops, lens, cap, C.byref(path))
+    return rc, (_mk_aln(a, ops, lens) if rc == SOME else None), path.value
+
+
+def sw_align_3pass_from(profiled: bytes, streamed: bytes, sc: Scoring, lanes=(32, 16, 8), first_bits: int = 8,
+                        streamed_is_query: bool = False):
+    """``ProfileSets::sw_align_from_i{8,16,32}_3pass(SeqSrc)`` -> (status, Aln | None, tier, path)."""
+    cap = _cap(profiled, streamed)
+    ops = (C.c_uint8 * cap)()
+    lens = (C.c_uint32 * cap)()
+    a = _Alignment()
+    tier, path = C.c_int(0), C.c_int(-1)
+    s = sc.c()
+    rc = lib().zo_sw_align_3pass_from(_buf(profiled), C.c_uint64(len(profiled)), _buf(streamed),
+                                      C.c_uint64(len(streamed)), C.byref(s), first_bits, lanes[0], lanes[1], lanes[2],
+                                      int(streamed_is_query), C.byref(a), ops, lens, cap, C.byref(tier), C.byref(path))
+    return rc, (_mk_aln(a, ops, lens) if rc == SOME else None), tier.value, path.value

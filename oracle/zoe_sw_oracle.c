@@ -279,12 +279,24 @@ static void st_reverse(zo_states *s) {
  * striped addressing for BacktrackMatrixStriped (:473-477). */
 typedef struct {
     const uint8_t *data;
-    int striped;
+    int striped; /* 0 row-major, 1 striped, 2 banded (BandedBacktrackMatrix::move_to, backtrack.rs:628-633) */
     int nv, N;
     uint64_t cols;
+    uint64_t band_width, len; /* banded only */
+    int oob;                  /* banded only: a move_to outside the stored vector (zoe would panic) */
 } zo_bt;
 
-static inline uint8_t bt_cell(const zo_bt *b, uint64_t r, uint64_t c) {
+static inline uint8_t bt_cell(zo_bt *b, uint64_t r, uint64_t c) {
+    if (b->striped == 2) {
+        /* band_col = c - r.saturating_sub(band_width); cursor = r * (2*band_width+1) + band_col */
+        int64_t skipped = r > b->band_width ? (int64_t)(r - b->band_width) : 0;
+        int64_t idx = (int64_t)r * (int64_t)(2 * b->band_width + 1) + ((int64_t)c - skipped);
+        if ((int64_t)c < skipped || idx < 0 || (uint64_t)idx >= b->len) {
+            b->oob = 1;
+            return F_STOP;
+        }
+        return b->data[idx];
+    }
     if (b->striped) {
         uint64_t v = c % (uint64_t)b->nv;
         uint64_t lane = (c - v) / (uint64_t)b->nv;
@@ -293,7 +305,7 @@ static inline uint8_t bt_cell(const zo_bt *b, uint64_t r, uint64_t c) {
     return b->data[b->cols * r + c];
 }
 
-static void zo_to_alignment(const zo_bt *b, uint32_t score, uint64_t r_end, uint64_t c_end, uint64_t ref_len,
+static void zo_to_alignment(zo_bt *b, uint32_t score, uint64_t r_end, uint64_t c_end, uint64_t ref_len,
                             uint64_t query_len, zo_alignment *out, zo_states *st) {
     uint8_t op = 0;
     uint8_t cur = bt_cell(b, r_end, c_end);
@@ -460,7 +472,7 @@ static int zo_striped_align_profile(const zo_profile *p, const uint8_t *referenc
         uint32_t score = 0;
         status = zo_score_to_maybe_aligned(p, best, &score);
         if (status == ZO_SOME) {
-            zo_bt b = {backtrack, 1, nv, N, 0};
+            zo_bt b = {backtrack, 1, nv, N, 0, 0, 0, 0};
             zo_to_alignment(&b, score, r_end, c_end, n, p->seq_len, out, st);
         }
     }
@@ -844,7 +856,7 @@ int zo_scalar_align(const uint8_t *profiled, uint64_t m, const uint8_t *streamed
     if (best_score == 0) {
         status = ZO_UNMAPPED;
     } else {
-        zo_bt b = {bt, 0, 0, 0, m};
+        zo_bt b = {bt, 0, 0, 0, m, 0, 0, 0};
         zo_to_alignment(&b, (uint32_t)best_score, r_end, c_end, n, m, out, &st);
         if (streamed_is_query) zo_invert(out, &st);
         status = ZO_SOME;
@@ -960,7 +972,7 @@ int zo_scalar_align_hazard(const uint8_t *profiled, uint64_t m, const uint8_t *s
                 cur = bt[(size_t)cr * m + cc];
             }
         }
-        zo_bt b = {bt, 0, 0, 0, m};
+        zo_bt b = {bt, 0, 0, 0, m, 0, 0, 0};
         zo_to_alignment(&b, (uint32_t)best_score, r_end, c_end, n, m, out, &st);
         if (streamed_is_query) zo_invert(out, &st);
         status = ZO_SOME;
@@ -971,4 +983,209 @@ int zo_scalar_align_hazard(const uint8_t *profiled, uint64_t m, const uint8_t *s
     free(tie);
     if (st.overflow) return ZO_ERR_CIGAR_CAP;
     return status;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Banded alignment and the 3-pass algorithm.
+ * --------------------------------------------------------------------------------------------- */
+
+/* AlignmentStates::prepend_ciglet, src/alignment/types/state.rs:156-166 */
+static void st_prepend(zo_states *s, uint64_t inc, uint8_t op) {
+    if (inc == 0) return;
+    if (s->n > 0 && s->ops[0] == op) {
+        s->lens[0] += (uint32_t)inc;
+        return;
+    }
+    if (s->n >= s->cap) {
+        s->overflow = 1;
+        return;
+    }
+    memmove(s->ops + 1, s->ops, s->n);
+    memmove(s->lens + 1, s->lens, sizeof(uint32_t) * s->n);
+    s->ops[0] = op;
+    s->lens[0] = (uint32_t)inc;
+    s->n++;
+}
+
+/* ---- src/alignment/sw/banded.rs:40-133 sw_banded_align (ScalarProfile of `profiled`, reference = `streamed`).
+ * No inversion here: three_pass.rs calls it on the un-inverted sub-problem.  Returns -101 if the traceback ever
+ * addressed a cell outside the stored band (zoe would panic on the vector index). ---- */
+static int zo_banded_align_core(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n,
+                                const zo_scoring *sc, uint64_t band_width, zo_alignment *out, zo_states *st) {
+    memset(out, 0, sizeof(*out));
+    if (n == 0) return ZO_UNMAPPED;
+    const int32_t go = sc->gap_open, ge = sc->gap_extend;
+    int32_t best_score = 0;
+    uint64_t r_end = 0, c_end = 0;
+    const uint64_t q_len = m;
+    int32_t *h_row = (int32_t *)calloc(q_len ? q_len : 1, sizeof(int32_t));
+    int32_t *e_row = (int32_t *)malloc(sizeof(int32_t) * (q_len ? q_len : 1));
+    for (uint64_t c = 0; c < q_len; c++) e_row[c] = go;
+    const uint64_t bfw = 2 * band_width + 1;
+    const size_t bt_len = (size_t)n * bfw;
+    uint8_t *bt = (uint8_t *)calloc(bt_len > 0 ? bt_len : 1, 1);
+    int32_t h_store = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        const int ri = sc->map[streamed[r]];
+        int32_t f = go;
+        int32_t h = h_store;
+        const uint64_t start_col = r > band_width ? r - band_width : 0;
+        const uint64_t end_col = r + band_width + 1 < q_len ? r + band_width + 1 : q_len;
+        if (start_col >= end_col) break;
+        if (start_col + band_width == r) {
+            const int32_t match_score = sc->weights[ri * sc->S + sc->map[profiled[start_col]]];
+            const int32_t e = e_row[start_col];
+            int32_t v = h + match_score;
+            if (e > v) v = e;
+            if (v < 0) v = 0;
+            h_store = v;
+        }
+        for (uint64_t c = start_col; c < end_col; c++) {
+            uint8_t *cell = bt + (size_t)r * bfw + (c - start_col); /* move_to(r, c) */
+            h += sc->weights[ri * sc->S + sc->map[profiled[c]]];
+            int32_t e = e_row[c];
+            if (e > h) h = e;
+            if (f > h) h = f;
+            if (h < 0) h = 0;
+            if (h > best_score) {
+                best_score = h;
+                r_end = r;
+                c_end = c;
+            }
+            if (e == h) *cell |= F_UP;
+            if (f == h) *cell |= F_LEFT;
+            if (h == 0) *cell = F_STOP;
+            const int32_t next_diag = h_row[c];
+            h_row[c] = h;
+            h += go;
+            e = e + ge > h ? e + ge : h;
+            f = f + ge > h ? f + ge : h;
+            if (h != go) {
+                if (e > h) *cell |= F_UP_EXT;
+                if (f > h) *cell |= F_LEFT_EXT;
+            }
+            h = next_diag;
+            e_row[c] = e;
+        }
+    }
+    int status;
+    if (best_score == 0) {
+        status = ZO_UNMAPPED;
+    } else {
+        zo_bt b = {bt, 2, 0, 0, 0, band_width, (uint64_t)n * bfw, 0};
+        zo_to_alignment(&b, (uint32_t)best_score, r_end, c_end, n, q_len, out, st);
+        status = b.oob ? -101 : ZO_SOME;
+    }
+    free(h_row);
+    free(e_row);
+    free(bt);
+    return status;
+}
+
+/* sw_banded_align as a caller sees it (banded.rs doc example). */
+int zo_banded_align(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                    uint64_t band_width, zo_alignment *out, uint8_t *ops, uint32_t *lens, uint32_t cap) {
+    int rc = zo_validate_profile_args(m, sc->gap_open, sc->gap_extend);
+    if (rc) return rc;
+    zo_states st = {ops, lens, 0, cap, 0};
+    rc = zo_banded_align_core(profiled, m, streamed, n, sc, band_width, out, &st);
+    if (st.overflow) return ZO_ERR_CIGAR_CAP;
+    return rc;
+}
+
+/* ---- src/alignment/sw/three_pass.rs:21-104 sw_align_3pass (+ StripedProfile::sw_align_3pass, profile.rs:546-552:
+ * make_alignment inverts for SeqSrc::Query).  `path` (may be NULL) reports which branch produced the states:
+ * 0 no-gaps shortcut, 1 banded (path >> 8 = the accepted band width), 2 scalar fallback. ---- */
+int zo_striped_align_3pass(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                           int bits, int is_signed, int lanes, int streamed_is_query, zo_alignment *out, uint8_t *ops,
+                           uint32_t *lens, uint32_t cap, int *path) {
+    uint32_t score = 0;
+    uint64_t rs = 0, re = 0, qs = 0, qe = 0;
+    memset(out, 0, sizeof(*out));
+    if (path) *path = -1;
+    int rc = zo_striped_score_ranges(profiled, m, streamed, n, sc, bits, is_signed, lanes, 0, &score, &rs, &re, &qs, &qe);
+    if (rc != ZO_SOME) return rc;
+    if (qe <= qs) return ZO_UNMAPPED; /* query_range.is_empty(), :37-38 */
+    zo_states st = {ops, lens, 0, cap, 0};
+    const uint64_t qn = qe - qs, rn = re - rs;
+    int done = 0;
+    if (qn == rn) { /* :39-49 */
+        int64_t sum = 0;
+        for (uint64_t i = 0; i < qn; i++)
+            sum += sc->weights[sc->map[streamed[rs + i]] * sc->S + sc->map[profiled[qs + i]]];
+        const uint32_t as_u32 = sum < 0 ? 0u : (uint32_t)sum; /* try_into().unwrap_or(0) */
+        if (as_u32 == score) {
+            /* AlignmentStates::new_no_gaps(query_range, query.len()), state.rs:201-208 */
+            st_add(&st, qs, 'S');
+            st_add(&st, qn, 'M');
+            st_add(&st, m - qe, 'S');
+            out->score = score;
+            out->ref_start = rs;
+            out->ref_end = re;
+            out->query_start = qs;
+            out->query_end = qe;
+            done = 1;
+            if (path) *path = 0;
+        }
+    }
+    if (!done) {
+        zo_alignment sub;
+        uint64_t band_width = (rn > qn ? rn - qn : qn - rn) + 1;
+        const uint64_t max_bandwidth = (qn - 1) / 2;
+        int have = 0;
+        while (band_width <= max_bandwidth) { /* :71-79 */
+            st.n = 0;
+            int brc = zo_banded_align_core(profiled + qs, qn, streamed + rs, rn, sc, band_width, &sub, &st);
+            if (brc == -101) return brc;
+            if (brc == ZO_SOME && sub.score == score) {
+                have = 1;
+                if (path) *path = 1 | (int)(band_width << 8);
+                break;
+            }
+            band_width *= 2;
+        }
+        if (!have) { /* :83-84 sw_scalar_align(reference_new, &query_new).unwrap() */
+            st.n = 0;
+            zo_states inner = {ops, lens, 0, cap, 0};
+            int src = zo_scalar_align(profiled + qs, qn, streamed + rs, rn, sc, 0, &sub, ops, lens, cap);
+            if (src != ZO_SOME) return src == ZO_UNMAPPED ? -102 /* unwrap() on Unmapped panics */ : src;
+            inner.n = sub.n_ops;
+            st = inner;
+            if (path) *path = 2;
+        }
+        const uint64_t adj_q0 = sub.query_start + qs, adj_q1 = sub.query_end + qs;
+        const uint64_t adj_r0 = sub.ref_start + rs, adj_r1 = sub.ref_end + rs;
+        st_prepend(&st, adj_q0, 'S');  /* :95 */
+        st_add(&st, m - adj_q1, 'S');  /* :96 */
+        out->score = score;            /* :98-105: the score of the ranges pass */
+        out->ref_start = adj_r0;
+        out->ref_end = adj_r1;
+        out->query_start = adj_q0;
+        out->query_end = adj_q1;
+    }
+    out->ref_len = n;
+    out->query_len = m;
+    out->n_ops = st.n;
+    if (st.overflow) return ZO_ERR_CIGAR_CAP;
+    if (streamed_is_query) {
+        zo_invert(out, &st);
+        if (st.overflow) return ZO_ERR_CIGAR_CAP;
+    }
+    return ZO_SOME;
+}
+
+/* ProfileSets::sw_align_from_i8_3pass / _i16_3pass / _i32_3pass: profile_set.rs:213-290 */
+int zo_sw_align_3pass_from(const uint8_t *profiled, uint64_t m, const uint8_t *streamed, uint64_t n, const zo_scoring *sc,
+                           int first_bits, int lanes8, int lanes16, int lanes32, int streamed_is_query, zo_alignment *out,
+                           uint8_t *ops, uint32_t *lens, uint32_t cap, int *tier, int *path) {
+    int bitsv[3] = {8, 16, 32}, lanesv[3] = {lanes8, lanes16, lanes32};
+    int rc = ZO_OVERFLOWED;
+    for (int k = 0; k < 3; k++) {
+        if (bitsv[k] < first_bits) continue;
+        *tier = bitsv[k];
+        rc = zo_striped_align_3pass(profiled, m, streamed, n, sc, bitsv[k], 1, lanesv[k], streamed_is_query, out, ops, lens,
+                                    cap, path);
+        if (rc != ZO_OVERFLOWED) return rc;
+    }
+    return rc;
 }

@@ -18,14 +18,15 @@ SYMBOLS = [
     "zoe_cuda_set_profiled", "zoe_cuda_sw_score_batch", "zoe_cuda_sw_align_batch", "zoe_cuda_stage_streamed",
     "zoe_cuda_run_score_staged", "zoe_cuda_run_align_staged", "zoe_cuda_fetch_scores", "zoe_cuda_last_timing",
     "zoe_cuda_last_stats", "zoe_cuda_dpx_peak", "zoe_cuda_stream", "zoe_cuda_set_align_options", "zoe_cuda_set_width_policy",
-    "zoe_cuda_sw_score_ranges_batch", "zoe_cuda_run_ranges_staged",
+    "zoe_cuda_sw_score_ranges_batch", "zoe_cuda_run_ranges_staged", "zoe_cuda_sw_align_3pass_batch",
+    "zoe_cuda_run_3pass_staged",
 ]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in
                 ("pairs", "cells", "tier8", "tier16", "tier32", "overflowed", "unmapped", "rerun_wide", "hazard",
-                 "window_fallback", "window_pinned")]
+                 "window_fallback", "window_pinned", "tp_nogaps", "tp_banded", "tp_scalar", "tp_band_attempts")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -61,6 +62,9 @@ def load() -> C.CDLL:
                                             u64p, C.c_uint64, u8p]
     lib.zoe_cuda_sw_score_ranges_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p, u32p, u32p, u32p, u32p]
     lib.zoe_cuda_run_ranges_staged.argtypes = [p]
+    lib.zoe_cuda_sw_align_3pass_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p, u32p, u32p, u32p, u32p, u32p,
+                                                  u64p, C.c_uint64]
+    lib.zoe_cuda_run_3pass_staged.argtypes = [p]
     lib.zoe_cuda_stage_streamed.argtypes = [p, u8p, u64p, C.c_uint64]
     lib.zoe_cuda_run_score_staged.argtypes = [p]
     lib.zoe_cuda_run_align_staged.argtypes = [p]

@@ -287,8 +287,9 @@ class CudaProfiles:
         self._check(self._lib.zoe_cuda_dpx_peak(self._h, kind, C.byref(g), C.byref(ms)))
         return g.value, ms.value
 
-    def align_arrays(self, buf: np.ndarray, offs: np.ndarray, cigar_cap: Optional[int] = None):
-        """Alignments for a packed batch; returns a dict of flat arrays (pair index = i*n_profiled+j)."""
+    def align_arrays(self, buf: np.ndarray, offs: np.ndarray, cigar_cap: Optional[int] = None, three_pass: bool = False):
+        """Alignments for a packed batch; returns a dict of flat arrays (pair index = i*n_profiled+j).
+        ``three_pass``: ``sw_align_from_i8_3pass`` (ranges + banded box alignment) instead of ``sw_align_from_i8``."""
         n = len(offs) - 1
         pairs = max(n * self.n_profiled, 1)
         out = {
@@ -300,12 +301,8 @@ class CudaProfiles:
         }
         cap = int(cigar_cap) if cigar_cap else max(16 * pairs, 1024)
         for _ in range(2):
-            cigar = np.zeros(cap, dtype=np.uint32)
-            rc = self._lib.zoe_cuda_sw_align_batch(
-                self._h, _p(buf, C.c_uint8), _p(offs, C.c_uint64), n, _p(out["score"], C.c_uint32),
-                _p(out["status"], C.c_uint8), _p(out["tier"], C.c_uint8), _p(out["ref_start"], C.c_uint32),
-                _p(out["ref_end"], C.c_uint32), _p(out["query_start"], C.c_uint32), _p(out["query_end"], C.c_uint32),
-                _p(cigar, C.c_uint32), _p(out["cigar_off"], C.c_uint64), cap, _p(out["hazard"], C.c_uint8))
+            out["cigar"] = np.zeros(cap, dtype=np.uint32)
+            rc = self._align_call(buf, offs, out, three_pass)
             if rc == _lib.E_CIGAR_CAP:
                 cap = int(out["cigar_off"][0]) + 16
                 continue
@@ -313,17 +310,23 @@ class CudaProfiles:
             break
         else:
             self._check(rc)
-        out["cigar"] = cigar
         return out
 
-    def align_into(self, buf: np.ndarray, offs: np.ndarray, out: dict):
+    def _align_call(self, buf: np.ndarray, offs: np.ndarray, out: dict, three_pass: bool) -> int:
+        args = [self._h, _p(buf, C.c_uint8), _p(offs, C.c_uint64), len(offs) - 1, _p(out["score"], C.c_uint32),
+                _p(out["status"], C.c_uint8), _p(out["tier"], C.c_uint8), _p(out["ref_start"], C.c_uint32),
+                _p(out["ref_end"], C.c_uint32), _p(out["query_start"], C.c_uint32), _p(out["query_end"], C.c_uint32),
+                _p(out["cigar"], C.c_uint32), _p(out["cigar_off"], C.c_uint64), len(out["cigar"])]
+        if three_pass:
+            return self._lib.zoe_cuda_sw_align_3pass_batch(*args)
+        return self._lib.zoe_cuda_sw_align_batch(*args, _p(out["hazard"], C.c_uint8))
+
+    def align_into(self, buf: np.ndarray, offs: np.ndarray, out: dict, three_pass: bool = False):
         """Like :meth:`align_arrays` but into caller-owned (ideally pinned) arrays; ``out['cigar']`` is the capacity."""
-        n = len(offs) - 1
-        self._check(self._lib.zoe_cuda_sw_align_batch(
-            self._h, _p(buf, C.c_uint8), _p(offs, C.c_uint64), n, _p(out["score"], C.c_uint32),
-            _p(out["status"], C.c_uint8), _p(out["tier"], C.c_uint8), _p(out["ref_start"], C.c_uint32),
-            _p(out["ref_end"], C.c_uint32), _p(out["query_start"], C.c_uint32), _p(out["query_end"], C.c_uint32),
-            _p(out["cigar"], C.c_uint32), _p(out["cigar_off"], C.c_uint64), len(out["cigar"]), _p(out["hazard"], C.c_uint8)))
+        self._check(self._align_call(buf, offs, out, three_pass))
+
+    def run_3pass_staged(self):
+        self._check(self._lib.zoe_cuda_run_3pass_staged(self._h))
 
     def ranges_arrays(self, buf: np.ndarray, offs: np.ndarray):
         """``sw_score_ranges`` for a packed batch: dict of flat arrays (pair index = i*n_profiled+j)."""
@@ -393,7 +396,11 @@ class CudaProfiles:
             return MaybeAligned.some(value)
         return MaybeAligned.Overflowed if status == _lib.OVERFLOWED else MaybeAligned.Unmapped  # type: ignore
 
-    def sw_align_batch(self, src: SeqSrc):
+    def sw_align_3pass_batch(self, src: SeqSrc):
+        """``out[i][j] == profiles[j].sw_align_from_i8_3pass(SeqSrc::X(seqs[i]))`` (profile_set.rs:213-231)."""
+        return self.sw_align_batch(src, three_pass=True)
+
+    def sw_align_batch(self, src: SeqSrc, three_pass: bool = False):
         """``out[i][j] == profiles[j].sw_align_from_i8(SeqSrc::X(seqs[i]))`` for the SeqSrc given."""
         want_pq = src.kind == "Reference"  # streamed sequences are references <=> profiled are queries
         if want_pq != self.profiled_is_query:
@@ -402,7 +409,7 @@ class CudaProfiles:
                 f"SeqSrc.{src.kind} needs the opposite orientation")
         seqs = [bytes(s) for s in src.seq]
         buf, offs = _pack(seqs)
-        a = self.align_arrays(buf, offs)
+        a = self.align_arrays(buf, offs, three_pass=three_pass)
         out = []
         for i in range(len(seqs)):
             row = []

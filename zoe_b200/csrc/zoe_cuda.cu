@@ -26,6 +26,7 @@
 #include "sw_score_long.cuh"
 #include "sw_score_rows.cuh"
 #include "sw_ranges.cuh"
+#include "sw_3pass.cuh"
 
 using namespace zoe_cuda;
 
@@ -86,6 +87,7 @@ struct Device {
     DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems;
     DevBuf starts;  // ranges: reverse-pass results
     DevBuf cig_bsum;  // CIGAR scan: per-block sums
+    DevBuf tp_pair, tp_off, tp_cap, tp_slot, tp_blob, tp_ctr;  // 3-pass alignment: DP work list + scratch (sw_3pass.cuh)
     uint64_t cig_total = 0;
     // long-row score path
     DevBuf long_ids, long_bnd, long_queue;
@@ -1570,6 +1572,121 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3-pass alignment (one device): ranges pipeline (passes 1 + 2) -> no-gaps shortcut / banded / scalar DP on the
+// bounding box (pass 3, sw_3pass.cuh) -> CIGAR compaction.  zoe: sw_align_3pass, src/alignment/sw/three_pass.rs:21-104.
+// ---------------------------------------------------------------------------------------------
+int run_3pass_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) {
+    d.cig_total = 0;
+    if (d.n_count == 0) return 0;
+    if (ctx->S > 32) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "3-pass alignment supports alphabets up to 32 symbols");
+    int rc = run_ranges_on_device(ctx, d);
+    if (rc) return rc;
+    CU(ctx, cudaSetDevice(d.id));
+    const uint32_t n_prof = ctx->n_prof;
+    const uint64_t pairs = (uint64_t)d.n_count * n_prof;
+    uint64_t budget = ctx->flag_budget_bytes ? ctx->flag_budget_bytes : (uint64_t)(d.free_at_create * 0.4);
+    budget = std::min<uint64_t>(budget, (uint64_t)32 << 30);
+    uint64_t chunk_pairs = std::min<uint64_t>(pairs, 1ull << 24);
+    CU(ctx, d.cig_count.reserve(pairs * sizeof(uint32_t)));
+    CU(ctx, d.cig_off.reserve((pairs + 1) * sizeof(uint64_t)));
+    CU(ctx, d.cig_out.reserve(std::max<uint64_t>(cigar_cap_words, 1) * sizeof(uint32_t)));
+    CU(ctx, d.tp_pair.reserve(chunk_pairs * sizeof(uint32_t)));
+    CU(ctx, d.tp_cap.reserve(chunk_pairs * sizeof(uint32_t)));
+    CU(ctx, d.tp_slot.reserve(chunk_pairs * sizeof(uint32_t)));
+    CU(ctx, d.tp_off.reserve(chunk_pairs * sizeof(unsigned long long)));
+    CU(ctx, d.tp_ctr.reserve(16 * sizeof(unsigned long long)));
+    CU(ctx, cudaMemsetAsync(d.tp_ctr.p, 0, 16 * sizeof(unsigned long long), d.stream));
+    unsigned long long *ctr = d.tp_ctr.as<unsigned long long>();
+
+    ThreePassParams t{};
+    t.rseq = d.rseq.as<uint8_t>();
+    t.roff = d.roff.as<uint64_t>();
+    t.pbytes = d.pbytes.as<uint8_t>();
+    t.coff = d.coff.as<uint32_t>();
+    t.n_cseq = n_prof;
+    t.weights = d.weights.as<int8_t>();
+    t.S = ctx->S;
+    t.lut = d.lut.as<uint8_t>();
+    t.go = -ctx->go;
+    t.ge = -ctx->ge;
+    t.invert = ctx->profiled_is_query ? 0 : 1;
+    t.score = d.score.as<uint32_t>();
+    t.status = d.status.as<uint8_t>();
+    t.ref_start = d.ref_start.as<uint32_t>();
+    t.ref_end = d.ref_end.as<uint32_t>();
+    t.query_start = d.query_start.as<uint32_t>();
+    t.query_end = d.query_end.as<uint32_t>();
+    t.cig_count = d.cig_count.as<uint32_t>();
+    t.dp_pair = d.tp_pair.as<uint32_t>();
+    t.dp_cap = d.tp_cap.as<uint32_t>();
+    t.dp_slot = d.tp_slot.as<uint32_t>();
+    t.dp_off = d.tp_off.as<unsigned long long>();
+    t.ctr = ctr;
+
+    for (uint64_t p0 = 0; p0 < pairs;) {
+        uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_pairs, pairs - p0);
+        unsigned long long work[2] = {0, 0};  // DP pairs, scratch bytes
+        for (;;) {
+            t.pair_first = p0;
+            t.n_pairs = cn;
+            CU(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), d.stream));
+            tp_classify_kernel<<<(cn + 255) / 256, 256, 0, d.stream>>>(t);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+            CU(ctx, cudaMemcpyAsync(work, ctr, sizeof(work), cudaMemcpyDeviceToHost, d.stream));
+            CU(ctx, cudaStreamSynchronize(d.stream));
+            if (work[1] <= budget || cn == 1) break;
+            cn = std::max<uint32_t>(1, cn / 2);  // the boxes of this chunk need more scratch than the budget: split it
+            chunk_pairs = cn;
+        }
+        if (work[0] > 0) {
+            CU(ctx, d.tp_blob.reserve(work[1] + 16));
+            t.blob = d.tp_blob.as<uint8_t>();
+            tp_dp_kernel<<<(uint32_t)((work[0] + 63) / 64), 64, 0, d.stream>>>(t, (uint32_t)work[0]);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+        }
+        // CIGAR compaction, chained through the device-side running base ctr[9]
+        if (cn >= (1u << 16)) {
+            const uint32_t nbk = (cn + 1023) / 1024;
+            CU(ctx, d.cig_bsum.reserve((size_t)nbk * sizeof(unsigned long long)));
+            cigar_block_sum_kernel<<<nbk, 1024, 0, d.stream>>>(t.cig_count, p0, cn, d.cig_bsum.as<unsigned long long>());
+            CU(ctx, cudaGetLastError());
+            cigar_scan_sums_kernel<<<1, 1024, 0, d.stream>>>(d.cig_bsum.as<unsigned long long>(), nbk, ctr + 9,
+                                                             d.cig_off.as<uint64_t>() + p0 + cn);
+            CU(ctx, cudaGetLastError());
+            cigar_block_scan_kernel<<<nbk, 1024, 0, d.stream>>>(t.cig_count, p0, cn, d.cig_bsum.as<unsigned long long>(),
+                                                                d.cig_off.as<uint64_t>());
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches += 3;
+        } else {
+            cigar_scan_kernel<<<1, 1024, 0, d.stream>>>(t.cig_count, p0, cn, d.cig_off.as<uint64_t>(), ctr + 9);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+        }
+        tp_gather_kernel<<<(cn + 255) / 256, 256, 0, d.stream>>>(t, d.cig_off.as<uint64_t>(), d.cig_out.as<uint32_t>(),
+                                                                 cigar_cap_words);
+        CU(ctx, cudaGetLastError());
+        ctx->last_launches++;
+        p0 += cn;
+    }
+    unsigned long long tail[16];
+    CU(ctx, cudaMemcpyAsync(tail, ctr, sizeof(tail), cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    d.cig_total = tail[9];
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->stats.tp_nogaps += tail[5];
+        ctx->stats.tp_banded += tail[6];
+        ctx->stats.tp_scalar += tail[7];
+        ctx->stats.tp_band_attempts += tail[8];
+    }
+    if (tail[2]) return fail(ctx, ZOE_CUDA_E_STATE, "3-pass: %llu banded walks left the band storage (zoe would panic here)", tail[2]);
+    if (tail[4]) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: CIGAR scratch overflow on %llu pairs", tail[4]);
+    return 0;
+}
+
 // Drives every device of the context with `fn`.  The align and ranges pipelines synchronise with the host between
 // their stages, so with several devices in one process each device gets its own host thread (the streams alone
 // would serialise the devices); a single device runs inline.
@@ -1628,6 +1745,50 @@ void begin_call(zoe_cuda_ctx *ctx) {
     for (Device &d : ctx->devs) d.timed_kernel = false;
 }
 
+// Copies the per-pair alignment outputs and the compacted CIGAR stream of every device into the caller's arrays
+// (devices own contiguous index ranges; CIGAR offsets become global).  Shared by the align and 3-pass entry points.
+int fetch_alignments(zoe_cuda_ctx *ctx, uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start,
+                     uint32_t *ref_end, uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
+                     uint64_t cigar_cap, uint8_t *hazard) {
+    // CIGAR offsets: device-local running sums -> global offsets (devices own contiguous index ranges)
+    uint64_t total = 0;
+    for (Device &d : ctx->devs) total += d.cig_total;
+    if (total > cigar_cap) {
+        cigar_off[0] = total;
+        sync_and_time(ctx);
+        return fail(ctx, ZOE_CUDA_E_CIGAR_CAP, "CIGAR buffer too small: need %llu words, have %llu",
+                    (unsigned long long)total, (unsigned long long)cigar_cap);
+    }
+    uint64_t base = 0;
+    for (Device &d : ctx->devs) {
+        if (d.n_count == 0) continue;
+        CU(ctx, cudaSetDevice(d.id));
+        size_t first = (size_t)d.n_first * ctx->n_prof, pairs = (size_t)d.n_count * ctx->n_prof;
+        auto d2h = [&](void *dst, const DevBuf &src, size_t elem) -> cudaError_t {
+            if (!dst) return cudaSuccess;
+            return cudaMemcpyAsync((uint8_t *)dst + first * elem, src.p, pairs * elem, cudaMemcpyDeviceToHost, d.stream);
+        };
+        CU(ctx, d2h(score, d.score, 4));
+        CU(ctx, d2h(status, d.status, 1));
+        CU(ctx, d2h(tier, d.tier, 1));
+        CU(ctx, d2h(ref_start, d.ref_start, 4));
+        CU(ctx, d2h(ref_end, d.ref_end, 4));
+        CU(ctx, d2h(query_start, d.query_start, 4));
+        CU(ctx, d2h(query_end, d.query_end, 4));
+        if (hazard) CU(ctx, d2h(hazard, d.hazard, 1));
+        CU(ctx, cudaMemcpyAsync(cigar_off + first, d.cig_off.p, (pairs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                                d.stream));
+        if (d.cig_total)
+            CU(ctx, cudaMemcpyAsync(cigar + base, d.cig_out.p, d.cig_total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                    d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        if (base)
+            for (size_t i = 0; i <= pairs; ++i) cigar_off[first + i] += base;
+        base += d.cig_total;
+    }
+    return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1670,7 +1831,8 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
         for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.corder, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
-                          &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.long_ids, &d.long_bnd,
+                          &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.tp_pair, &d.tp_off, &d.tp_cap, &d.tp_slot,
+                          &d.tp_blob, &d.tp_ctr, &d.long_ids, &d.long_bnd,
                           &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.starts, &d.cig_bsum})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -1893,42 +2055,9 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
     rc = for_each_device(ctx, [&](Device &d) { return run_align_on_device(ctx, d, cigar_cap); });
     if (rc) return rc;
     dbg.lap("align: run_align_on_device");
-    // CIGAR offsets: device-local running sums -> global offsets (devices own contiguous index ranges)
-    uint64_t total = 0;
-    for (Device &d : ctx->devs) total += d.cig_total;
-    if (total > cigar_cap) {
-        cigar_off[0] = total;
-        sync_and_time(ctx);
-        return fail(ctx, ZOE_CUDA_E_CIGAR_CAP, "CIGAR buffer too small: need %llu words, have %llu",
-                    (unsigned long long)total, (unsigned long long)cigar_cap);
-    }
-    uint64_t base = 0;
-    for (Device &d : ctx->devs) {
-        if (d.n_count == 0) continue;
-        CU(ctx, cudaSetDevice(d.id));
-        size_t first = (size_t)d.n_first * ctx->n_prof, pairs = (size_t)d.n_count * ctx->n_prof;
-        auto d2h = [&](void *dst, const DevBuf &src, size_t elem) -> cudaError_t {
-            if (!dst) return cudaSuccess;
-            return cudaMemcpyAsync((uint8_t *)dst + first * elem, src.p, pairs * elem, cudaMemcpyDeviceToHost, d.stream);
-        };
-        CU(ctx, d2h(score, d.score, 4));
-        CU(ctx, d2h(status, d.status, 1));
-        CU(ctx, d2h(tier, d.tier, 1));
-        CU(ctx, d2h(ref_start, d.ref_start, 4));
-        CU(ctx, d2h(ref_end, d.ref_end, 4));
-        CU(ctx, d2h(query_start, d.query_start, 4));
-        CU(ctx, d2h(query_end, d.query_end, 4));
-        CU(ctx, d2h(hazard, d.hazard, 1));
-        CU(ctx, cudaMemcpyAsync(cigar_off + first, d.cig_off.p, (pairs + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost,
-                                d.stream));
-        if (d.cig_total)
-            CU(ctx, cudaMemcpyAsync(cigar + base, d.cig_out.p, d.cig_total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                    d.stream));
-        CU(ctx, cudaStreamSynchronize(d.stream));
-        if (base)
-            for (size_t i = 0; i <= pairs; ++i) cigar_off[first + i] += base;
-        base += d.cig_total;
-    }
+    rc = fetch_alignments(ctx, score, status, tier, ref_start, ref_end, query_start, query_end, cigar, cigar_off, cigar_cap,
+                          hazard);
+    if (rc) return rc;
     if (n == 0) cigar_off[0] = 0;
     dbg.lap("align: d2h");
     rc = sync_and_time(ctx);
@@ -1975,6 +2104,41 @@ int zoe_cuda_run_ranges_staged(zoe_cuda_ctx *ctx) {
         CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
     }
     int rc = for_each_device(ctx, [&](Device &d) { return run_ranges_on_device(ctx, d); });
+    if (rc) return rc;
+    rc = sync_and_time(ctx);
+    if (rc) return rc;
+    return gather_stats(ctx);
+}
+
+int zoe_cuda_sw_align_3pass_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
+                                  uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
+                                  uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
+                                  uint64_t cigar_cap) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (!cigar_off || (!cigar && cigar_cap)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null CIGAR outputs");
+    begin_call(ctx);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    if (rc) return rc;
+    rc = for_each_device(ctx, [&](Device &d) { return run_3pass_on_device(ctx, d, cigar_cap); });
+    if (rc) return rc;
+    rc = fetch_alignments(ctx, score, status, tier, ref_start, ref_end, query_start, query_end, cigar, cigar_off, cigar_cap,
+                          nullptr);
+    if (rc) return rc;
+    if (n == 0) cigar_off[0] = 0;
+    rc = sync_and_time(ctx);
+    if (rc) return rc;
+    return gather_stats(ctx);
+}
+
+int zoe_cuda_run_3pass_staged(zoe_cuda_ctx *ctx) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (!ctx->staged) return fail(ctx, ZOE_CUDA_E_STATE, "nothing staged");
+    begin_call(ctx);
+    for (Device &d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+    }
+    int rc = for_each_device(ctx, [&](Device &d) { return run_3pass_on_device(ctx, d, (uint64_t)d.n_count * ctx->n_prof * 8 + 1024); });
     if (rc) return rc;
     rc = sync_and_time(ctx);
     if (rc) return rc;
