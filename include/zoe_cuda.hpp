@@ -141,7 +141,13 @@ class CudaProfiles {
     }
 
     // out[i * n_profiled + j] == profiles[j].sw_align_from_i8(SeqSrc::X(&seqs[i])) with X as given at construction
-    std::vector<MaybeAligned<Alignment>> sw_align_batch(const std::vector<std::string> &seqs) {
+    std::vector<MaybeAligned<Alignment>> sw_align_batch(const std::vector<std::string> &seqs) { return align(seqs, false); }
+
+    // out[i * n_profiled + j] == profiles[j].sw_align_from_i8_3pass(SeqSrc::X(&seqs[i])) (profile_set.rs:213-231)
+    std::vector<MaybeAligned<Alignment>> sw_align_3pass_batch(const std::vector<std::string> &seqs) { return align(seqs, true); }
+
+  private:
+    std::vector<MaybeAligned<Alignment>> align(const std::vector<std::string> &seqs, bool three_pass) {
         std::vector<uint8_t> buf;
         std::vector<uint64_t> off;
         pack(seqs, buf, off);
@@ -150,12 +156,19 @@ class CudaProfiles {
         std::vector<uint8_t> status(pairs + 1), tier(pairs + 1);
         std::vector<uint64_t> coff(pairs + 2);
         std::vector<uint32_t> cig(16 * pairs + 1024);
-        int rc = zoe_cuda_sw_align_batch(ctx_, buf.data(), off.data(), seqs.size(), score.data(), status.data(), tier.data(),
-                                         rs.data(), re.data(), qs.data(), qe.data(), cig.data(), coff.data(), cig.size(), nullptr);
+        auto call = [&]() {
+            return three_pass
+                       ? zoe_cuda_sw_align_3pass_batch(ctx_, buf.data(), off.data(), seqs.size(), score.data(), status.data(),
+                                                       tier.data(), rs.data(), re.data(), qs.data(), qe.data(), cig.data(),
+                                                       coff.data(), cig.size())
+                       : zoe_cuda_sw_align_batch(ctx_, buf.data(), off.data(), seqs.size(), score.data(), status.data(),
+                                                 tier.data(), rs.data(), re.data(), qs.data(), qe.data(), cig.data(),
+                                                 coff.data(), cig.size(), nullptr);
+        };
+        int rc = call();
         if (rc == ZOE_CUDA_E_CIGAR_CAP) {
             cig.resize(coff[0] + 16);
-            rc = zoe_cuda_sw_align_batch(ctx_, buf.data(), off.data(), seqs.size(), score.data(), status.data(), tier.data(),
-                                         rs.data(), re.data(), qs.data(), qe.data(), cig.data(), coff.data(), cig.size(), nullptr);
+            rc = call();
         }
         check(rc);
         static const char ops[] = {'M', 'I', 'D', '?', 'S'};
@@ -177,7 +190,6 @@ class CudaProfiles {
         return out;
     }
 
-  private:
     CudaProfiles(const std::vector<std::string> &targets, const WeightMatrix &m, int8_t go, int8_t ge, int l8, int l16,
                  int l32, SeqSrc streamed_are, int n_devices)
         : targets_(targets), streamed_are_(streamed_are) {

@@ -35,6 +35,10 @@ pub struct zoe_cuda_stats {
     pub hazard: u64,
     pub window_fallback: u64,
     pub window_pinned: u64,
+    pub tp_nogaps: u64,
+    pub tp_banded: u64,
+    pub tp_scalar: u64,
+    pub tp_band_attempts: u64,
 }
 
 unsafe extern "C" {
@@ -63,7 +67,13 @@ unsafe extern "C" {
         status: *mut u8, tier: *mut u8, ref_start: *mut u32, ref_end: *mut u32, query_start: *mut u32,
         query_end: *mut u32,
     ) -> c_int;
+    pub fn zoe_cuda_sw_align_3pass_batch(
+        ctx: *mut zoe_cuda_ctx, streamed_concat: *const u8, offsets: *const u64, n: u64, score: *mut u32,
+        status: *mut u8, tier: *mut u8, ref_start: *mut u32, ref_end: *mut u32, query_start: *mut u32,
+        query_end: *mut u32, cigar: *mut u32, cigar_off: *mut u64, cigar_cap: u64,
+    ) -> c_int;
     pub fn zoe_cuda_run_ranges_staged(ctx: *mut zoe_cuda_ctx) -> c_int;
+    pub fn zoe_cuda_run_3pass_staged(ctx: *mut zoe_cuda_ctx) -> c_int;
     pub fn zoe_cuda_stage_streamed(ctx: *mut zoe_cuda_ctx, streamed_concat: *const u8, offsets: *const u64, n: u64) -> c_int;
     pub fn zoe_cuda_run_score_staged(ctx: *mut zoe_cuda_ctx) -> c_int;
     pub fn zoe_cuda_run_align_staged(ctx: *mut zoe_cuda_ctx) -> c_int;

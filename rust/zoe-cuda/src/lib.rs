@@ -87,6 +87,16 @@ impl CudaProfiles {
     /// `out[i * n_profiled + j] == profiles[j].sw_align_from_i8(seq_src(seqs[i]))` where `seq_src` is
     /// `SeqSrc::Query` when the profiled sequences are references, `SeqSrc::Reference` otherwise.
     pub fn sw_align_batch(&self, seqs: &[&[u8]]) -> Result<Vec<MaybeAligned<Alignment<u32>>>, CudaError> {
+        self.align(seqs, false)
+    }
+
+    /// `out[i * n_profiled + j] == profiles[j].sw_align_from_i8_3pass(seq_src(seqs[i]))` (profile_set.rs:213-231):
+    /// ranges from two score passes, then a banded alignment of the bounding box (three_pass.rs:21-104).
+    pub fn sw_align_3pass_batch(&self, seqs: &[&[u8]]) -> Result<Vec<MaybeAligned<Alignment<u32>>>, CudaError> {
+        self.align(seqs, true)
+    }
+
+    fn align(&self, seqs: &[&[u8]], three_pass: bool) -> Result<Vec<MaybeAligned<Alignment<u32>>>, CudaError> {
         let (concat, offsets) = pack(seqs);
         let np = self.profiled_lens.len();
         let pairs = seqs.len() * np;
@@ -97,10 +107,16 @@ impl CudaProfiles {
         let mut cigar = vec![0u32; 16 * pairs + 1024];
         loop {
             let rc = unsafe {
-                sys::zoe_cuda_sw_align_batch(self.ctx, concat.as_ptr(), offsets.as_ptr(), seqs.len() as u64,
-                    score.as_mut_ptr(), status.as_mut_ptr(), tier.as_mut_ptr(), rs.as_mut_ptr(), re.as_mut_ptr(),
-                    qs.as_mut_ptr(), qe.as_mut_ptr(), cigar.as_mut_ptr(), coff.as_mut_ptr(), cigar.len() as u64,
-                    std::ptr::null_mut())
+                if three_pass {
+                    sys::zoe_cuda_sw_align_3pass_batch(self.ctx, concat.as_ptr(), offsets.as_ptr(), seqs.len() as u64,
+                        score.as_mut_ptr(), status.as_mut_ptr(), tier.as_mut_ptr(), rs.as_mut_ptr(), re.as_mut_ptr(),
+                        qs.as_mut_ptr(), qe.as_mut_ptr(), cigar.as_mut_ptr(), coff.as_mut_ptr(), cigar.len() as u64)
+                } else {
+                    sys::zoe_cuda_sw_align_batch(self.ctx, concat.as_ptr(), offsets.as_ptr(), seqs.len() as u64,
+                        score.as_mut_ptr(), status.as_mut_ptr(), tier.as_mut_ptr(), rs.as_mut_ptr(), re.as_mut_ptr(),
+                        qs.as_mut_ptr(), qe.as_mut_ptr(), cigar.as_mut_ptr(), coff.as_mut_ptr(), cigar.len() as u64,
+                        std::ptr::null_mut())
+                }
             };
             if rc == sys::ZOE_CUDA_E_CIGAR_CAP {
                 cigar.resize(coff[0] as usize + 16, 0);

@@ -32,6 +32,10 @@ int main() {
     CHECK(a[0].unwrap().query_range.first == 0 && a[0].unwrap().query_range.second == 15);
     CHECK(a[0].unwrap().ref_range.first == 14 && a[0].unwrap().ref_range.second == 31);
     CHECK(a[3].unwrap().cigar() == "5M1D4M" && a[3].unwrap().ref_range.first == 3);
+    // profile_set.rs:192-208: sw_align_from_i8_3pass(SeqSrc::Reference(reference)).score == 26
+    auto a3 = prof.sw_align_3pass_batch({"ATGCATCGATCGATCGATCGATCGATCGATGC", "GGCCACAGGATTGAG"});
+    CHECK(a3[0].unwrap().score == 26 && a3[0].unwrap().ref_range.first == 14 && a3[0].unwrap().ref_range.second == 31);
+    CHECK(a3[3].unwrap().score == 27 && a3[3].unwrap().cigar() == "5M1D4M");
     // sw/test.rs:81-84 and an Unmapped pair
     auto w25 = WeightMatrix::new_dna_matrix(2, -5);
     auto p2 = CudaProfiles::new_with_w256({std::string(100, 'A')}, w25, -10, -1);
