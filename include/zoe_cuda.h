@@ -136,6 +136,16 @@ int zoe_cuda_sw_align_3pass_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_con
                                   uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
                                   uint64_t cigar_cap);
 
+/* Batched sneaky_snake(reference, query, threshold) (src/alignment/sneaky_snake.rs:78-131): the SneakySnake
+ * pre-alignment filter for pair i = (reference i, query i).  out[i]: 1 = Some(true) (edits within
+ * floor(len(query) * threshold)), 0 = Some(false), 2 = None (threshold outside 0..=1, or the length difference exceeds
+ * the edit threshold).  Needs no scoring and no profiled set. */
+#define ZOE_CUDA_SNAKE_FALSE 0
+#define ZOE_CUDA_SNAKE_TRUE 1
+#define ZOE_CUDA_SNAKE_NONE 2
+int zoe_cuda_sneaky_snake_batch(zoe_cuda_ctx *ctx, const uint8_t *refs, const uint64_t *ref_offsets, const uint8_t *queries,
+                                const uint64_t *query_offsets, uint64_t n, float threshold, uint8_t *out);
+
 /* Which of zoe's integer types may report a result (default 8..32 signed = ProfileSets::sw_*_from_i8).
  *   first_bits..last_bits   8/16/32: the escalation chain starts at first_bits and stops at last_bits:
  *                 (8,32) = sw_score_from_i8 / sw_align_from_i8, (16,32) = ..._from_i16, (32,32) = ..._from_i32

@@ -271,3 +271,12 @@ def sw_align_3pass_from(profiled: bytes, streamed: bytes, sc: Scoring, lanes=(32
                                       C.c_uint64(len(streamed)), C.byref(s), first_bits, lanes[0], lanes[1], lanes[2],
                                       int(streamed_is_query), C.byref(a), ops, lens, cap, C.byref(tier), C.byref(path))
     return rc, (_mk_aln(a, ops, lens) if rc == SOME else None), tier.value, path.value
+
+
+def sneaky_snake(reference: bytes, query: bytes, threshold: float):
+    """``sneaky_snake(reference, query, threshold)`` (sneaky_snake.rs:78-131) -> True / False / None."""
+    f = lib().zo_sneaky_snake
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float]
+    rb, qb = _buf(reference), _buf(query)
+    rc = f(C.cast(rb, C.c_void_p), len(reference), C.cast(qb, C.c_void_p), len(query), C.c_float(threshold))
+    return {0: False, 1: True, 2: None}[rc]

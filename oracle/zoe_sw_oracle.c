@@ -1189,3 +1189,43 @@ int zo_sw_align_3pass_from(const uint8_t *profiled, uint64_t m, const uint8_t *s
     }
     return rc;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * src/alignment/sneaky_snake.rs:78-131 sneaky_snake: pre-alignment filter.
+ * Returns 1 = Some(true), 0 = Some(false), 2 = None.
+ * --------------------------------------------------------------------------------------------- */
+int zo_sneaky_snake(const uint8_t *reference, uint64_t rl, const uint8_t *query, uint64_t ql, float threshold) {
+    if (!(threshold >= 0.0f && threshold <= 1.0f)) return 2; /* (0. ..=1.).contains(&threshold) */
+    const volatile float prod = (float)ql * threshold;       /* f32 arithmetic, as in zoe */
+    const uint64_t edit_thresh = (uint64_t)__builtin_floorf(prod);
+    const uint64_t len_diff = rl > ql ? rl - ql : ql - rl;
+    if (len_diff > edit_thresh) return 2;
+    if (edit_thresh == ql) return 1;
+    const uint8_t *s1 = reference, *s2 = query;
+    uint64_t n1 = rl, n2 = ql;
+    if (rl > ql) { /* choose shorter string */
+        s1 = query;
+        n1 = ql;
+        s2 = reference;
+        n2 = rl;
+    }
+    const uint64_t window = 2 * edit_thresh + 1, diffpad_len = len_diff / 2;
+    uint64_t obstacles = 0, checkpoint = 0;
+    while (checkpoint < n1 && obstacles <= edit_thresh && n1 - checkpoint > edit_thresh - obstacles) {
+        uint64_t last_col = checkpoint;
+        for (uint64_t row = 0; row < window; row++) {
+            for (uint64_t col = checkpoint; col < n1; col++) {
+                const uint64_t shifted = col + row + diffpad_len;
+                if (shifted >= edit_thresh && shifted - edit_thresh < n2 && s2[shifted - edit_thresh] == s1[col]) {
+                    if (col == n1 - 1 || n1 - col - 1 <= edit_thresh - obstacles) return 1;
+                } else {
+                    if (col > last_col) last_col = col;
+                    break;
+                }
+            }
+        }
+        checkpoint = last_col + 1;
+        obstacles += 1;
+    }
+    return obstacles <= edit_thresh ? 1 : 0;
+}

@@ -12,6 +12,7 @@ from .alignment import (  # noqa: F401
     SeqSrc,
     ZoeCudaError,
 )
+from .sneaky_snake import SneakySnake  # noqa: F401
 from .matrices import (  # noqa: F401
     AA_ALL_AMBIG_PROFILE_MAP_WITH_STOP,
     BLOSUM_62,

@@ -471,6 +471,11 @@ struct ExactParams {
 
 // Values are kept in true (un-offset) form: zoe stores x + T::MIN and saturates, so saturation at MIN is a
 // clamp at 0 here; saturation at MAX cannot happen because the tier was chosen from the exact score.
+// SMEM: the H / E rows, the current flag row, the profiled indices and the weights live in shared memory.  A template
+// parameter rather than a run-time choice so that every access in the hot loops is an LDS / STS with a 32-bit address:
+// with the pointers selected at run time the compiler emitted generic LD / ST (and 64-bit address arithmetic) for all
+// of them.
+template <bool SMEM>
 __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x) {
     const int warps_per_block = blockDim.x / 32;
     const uint32_t slot = blockIdx.x * warps_per_block + threadIdx.x / 32;
@@ -495,22 +500,21 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
         // H / E rows: shared memory when the profiled sequence is short enough (latency 30 vs ~600 cycles),
         // else the per-slot global scratch
         extern __shared__ __align__(16) int32_t ex_smem[];
-        int32_t *load = x.rows_in_smem ? ex_smem + (size_t)(threadIdx.x / 32) * 4 * x.vcap
-                                       : x.hbuf + (size_t)slot * 4 * x.vcap;
-        int32_t *store = load + x.vcap, *es = store + x.vcap, *max_row = es + x.vcap;
+        const uint32_t vcap = (uint32_t)x.vcap;
+        int32_t *load = SMEM ? ex_smem + (threadIdx.x / 32) * 4 * vcap : x.hbuf + (size_t)slot * 4 * x.vcap;
+        int32_t *store = load + vcap, *es = store + vcap, *max_row = es + vcap;
         uint8_t *bt = x.fbuf + (size_t)slot * x.fcap;
         // the flag bytes of the row being computed live in shared memory (the lazy-F pass reads and rewrites them);
         // a finished row is copied to the per-slot global scratch the traceback reads
-        uint8_t *frow = x.rows_in_smem ? reinterpret_cast<uint8_t *>(ex_smem + (size_t)warps_per_block * 4 * x.vcap) +
-                                             (size_t)(threadIdx.x / 32) * 2 * x.vcap
-                                       : nullptr;
+        uint8_t *frow = SMEM ? reinterpret_cast<uint8_t *>(ex_smem + warps_per_block * 4 * vcap) + (threadIdx.x / 32) * 2 * vcap
+                             : nullptr;
         // profiled symbol indices and the weight matrix staged in shared memory: the inner loop would otherwise
         // chain three global loads (residue -> index -> weight) per vector
-        uint8_t *pidx = frow ? frow + x.vcap : nullptr;
+        uint8_t *pidx = SMEM ? frow + vcap : nullptr;
         const int8_t *wmat = x.weights;
-        if (frow) {
-            int8_t *ws = reinterpret_cast<int8_t *>(ex_smem + (size_t)warps_per_block * 4 * x.vcap) +
-                         (size_t)warps_per_block * 2 * x.vcap + (size_t)(threadIdx.x / 32) * 4096;
+        if (SMEM) {
+            int8_t *ws = reinterpret_cast<int8_t *>(ex_smem + warps_per_block * 4 * vcap) + warps_per_block * 2 * vcap +
+                         (threadIdx.x / 32) * 4096;
             for (int i = lane; i < m; i += 32) pidx[i] = x.lut[P[i]];
             for (int i = lane; i < x.S * x.S; i += 32) ws[i] = x.weights[i];
             wmat = ws;
@@ -524,8 +528,17 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
         __syncwarp();
         int best = 0;
         int r_end = n - 1;
+#ifdef ZOE_EXACT_PROFILE
+        long long t_main = 0, t_lazy = 0, t_pub = 0, t_all0 = clock64(), tt;
+#define EXACT_TICK(acc) { long long now_ = clock64(); acc += now_ - tt; tt = now_; }
+#else
+#define EXACT_TICK(acc)
+#endif
 
         for (int r = 0; r < n; ++r) {
+#ifdef ZOE_EXACT_PROFILE
+            tt = clock64();
+#endif
             const int ref_index = x.lut[R[r]];
             const int8_t *wrow = wmat + ref_index * x.S;
             int F[2] = {0, 0}, H[2], rowmax[2] = {0, 0};
@@ -547,15 +560,30 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
                 store = sw;
             }
             uint8_t *grow = bt + (size_t)r * nv * N;
-            uint8_t *brow = frow ? frow : grow;
+            uint8_t *brow = SMEM ? frow : grow;
+            // The weight of vector v + 1 (two dependent shared-memory loads: symbol index, then weight) is fetched
+            // before vector v's stores, which takes it off the loop-carried critical path (216 -> ~160 cycles per vector).
+            int pw[2] = {0, 0};
+            auto fetch_w = [&](int v) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int l = lane + 32 * q;
+                    if (q < NL && l < N) {
+                        const int cidx = v + l * nv;
+                        pw[q] = cidx < m ? (int)wrow[SMEM ? pidx[cidx] : x.lut[P[cidx]]] : 0;
+                    }
+                }
+            };
+            fetch_w(0);
             for (int v = 0; v < nv; ++v) {
+                const int cw[2] = {pw[0], pw[1]};
+                if (v + 1 < nv) fetch_w(v + 1);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     int l = lane + 32 * q;
                     if (q < NL && l < N) {
-                        int cidx = v + l * nv;
-                        int w = cidx < m ? (int)wrow[pidx ? pidx[cidx] : x.lut[P[cidx]]] : 0;
-                        int E = es[(size_t)v * N + l];
+                        const int w = cw[q];
+                        int E = es[v * N + l];
                         int h = max(H[q] + w, 0);  // saturating_add, floor at MIN
                         h = max(max(h, E), F[q]);
                         uint8_t fl = 0;
@@ -563,20 +591,21 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
                         if (E == h) fl |= 1;
                         if (F[q] == h) fl |= 4;
                         bool stopped = (h == 0);
-                        store[(size_t)v * N + l] = h;
+                        store[v * N + l] = h;
                         int ho = max(h - x.go, 0);
                         E = max(max(E - x.ge, 0), ho);
                         F[q] = max(max(F[q] - x.ge, 0), ho);
                         if (E > ho) fl |= 2;
                         if (F[q] > ho) fl |= 8;
                         if (stopped) fl = 16;
-                        brow[(size_t)v * N + l] = fl;
-                        es[(size_t)v * N + l] = E;
-                        H[q] = load[(size_t)v * N + l];
+                        brow[v * N + l] = fl;
+                        es[v * N + l] = E;
+                        H[q] = load[v * N + l];
                     }
                 }
             }
             __syncwarp();
+            EXACT_TICK(t_main)
             // lazy-F: striped.rs:528-553
             for (int pass = 0; pass < N; ++pass) {
                 // F = F.shift_elements_right(MIN)
@@ -594,7 +623,7 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
                     for (int q = 0; q < 2; ++q) {
                         int l = lane + 32 * q;
                         if (q < NL && l < N) {
-                            hs[q] = store[(size_t)v * N + l];
+                            hs[q] = store[v * N + l];
                             if (F[q] > max(hs[q] - x.go, 0)) trig = true;
                         }
                     }
@@ -607,22 +636,23 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
                         int l = lane + 32 * q;
                         if (q < NL && l < N) {
                             int h = max(hs[q], F[q]);
-                            store[(size_t)v * N + l] = h;
-                            uint8_t fl = brow[(size_t)v * N + l];
+                            store[v * N + l] = h;
+                            uint8_t fl = brow[v * N + l];
                             bool stopped = (h == 0);
                             if (F[q] == h) fl = (uint8_t)((fl & 2) | 4);
                             int ho = max(h - x.go, 0);
                             F[q] = max(F[q] - x.ge, 0);
                             if (F[q] > ho) fl |= 8;
                             if (stopped) fl = 16;
-                            brow[(size_t)v * N + l] = fl;
+                            brow[v * N + l] = fl;
                         }
                     }
                 }
                 if (broke) break;
             }
             __syncwarp();
-            if (frow) {  // publish the finished row
+            EXACT_TICK(t_lazy)
+            if (SMEM) {  // publish the finished row
                 const int nb = nv * N;
                 if ((nb & 3) == 0) {
                     const uint32_t *src = reinterpret_cast<const uint32_t *>(frow);
@@ -640,8 +670,14 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
                 best = rb;
                 r_end = r;
             }
+            EXACT_TICK(t_pub)
         }
         __syncwarp();
+#ifdef ZOE_EXACT_PROFILE
+        if (lane == 0 && pi == 0)
+            printf("exact profile: N %d nv %d rows %d main %lld lazy %lld publish+reduce %lld loop-total %lld cycles\n", N, nv, n,
+                   t_main, t_lazy, t_pub, clock64() - t_all0);
+#endif
         if (r_end == n - 1)
             max_row = store;
         else if (n >= 2 && r_end == n - 2)

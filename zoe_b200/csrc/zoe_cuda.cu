@@ -27,6 +27,7 @@
 #include "sw_score_rows.cuh"
 #include "sw_ranges.cuh"
 #include "sw_3pass.cuh"
+#include "sneaky_snake.cuh"
 
 using namespace zoe_cuda;
 
@@ -87,6 +88,7 @@ struct Device {
     DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems;
     DevBuf starts;  // ranges: reverse-pass results
     DevBuf cig_bsum;  // CIGAR scan: per-block sums
+    DevBuf sn_refs, sn_roff, sn_qry, sn_qoff, sn_out;  // SneakySnake filter batch (sneaky_snake.cuh)
     DevBuf tp_pair, tp_off, tp_cap, tp_slot, tp_blob, tp_ctr;  // 3-pass alignment: DP work list + scratch (sw_3pass.cuh)
     uint64_t cig_total = 0;
     // long-row score path
@@ -984,7 +986,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     }
     dbg.lap("align: plan");
-    const bool all_exact = (ctx->go == 0);
+    // ZOE_CUDA_ALL_EXACT: every pair through the literal kernel (testing / timing; results are identical by design)
+    const bool all_exact = (ctx->go == 0) || getenv("ZOE_CUDA_ALL_EXACT") != nullptr;
     const int invert = ctx->profiled_is_query ? 0 : 1;
     float dp_ms_total = 0.f;
 
@@ -1111,8 +1114,11 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             x.rows_in_smem = rows_bytes * 4 <= 200 * 1024 ? 1 : 0;
             const size_t ex_smem = x.rows_in_smem ? rows_bytes * 4 : 0;
             if (ex_smem > 48 * 1024)
-                CU(ctx, cudaFuncSetAttribute(sw_align_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-            sw_align_exact_kernel<<<slots / 4, 128, ex_smem, stream>>>(x);
+                CU(ctx, cudaFuncSetAttribute(sw_align_exact_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+            if (x.rows_in_smem)
+                sw_align_exact_kernel<true><<<slots / 4, 128, ex_smem, stream>>>(x);
+            else
+                sw_align_exact_kernel<false><<<slots / 4, 128, 0, stream>>>(x);
             CU(ctx, cudaGetLastError());
             ctx->last_launches++;
             return 0;
@@ -1832,7 +1838,7 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.tp_pair, &d.tp_off, &d.tp_cap, &d.tp_slot,
-                          &d.tp_blob, &d.tp_ctr, &d.long_ids, &d.long_bnd,
+                          &d.tp_blob, &d.tp_ctr, &d.sn_refs, &d.sn_roff, &d.sn_qry, &d.sn_qoff, &d.sn_out, &d.long_ids, &d.long_bnd,
                           &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.starts, &d.cig_bsum})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -2143,6 +2149,50 @@ int zoe_cuda_run_3pass_staged(zoe_cuda_ctx *ctx) {
     rc = sync_and_time(ctx);
     if (rc) return rc;
     return gather_stats(ctx);
+}
+
+int zoe_cuda_sneaky_snake_batch(zoe_cuda_ctx *ctx, const uint8_t *refs, const uint64_t *ref_offsets, const uint8_t *queries,
+                                const uint64_t *query_offsets, uint64_t n, float threshold, uint8_t *out) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    if (n == 0) return 0;
+    if (!ref_offsets || !query_offsets || !out) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null argument");
+    begin_call(ctx);
+    // pairs are split over the context's devices by contiguous index range, like every other batch call
+    const size_t nd = ctx->devs.size();
+    for (size_t k = 0; k < nd; ++k) {
+        Device &d = ctx->devs[k];
+        const uint64_t lo = n * k / nd, hi = n * (k + 1) / nd, cnt = hi - lo;
+        if (cnt == 0) continue;
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+        const uint64_t rb = ref_offsets[hi] - ref_offsets[lo], qb = query_offsets[hi] - query_offsets[lo];
+        if ((rb && !refs) || (qb && !queries)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null sequence buffer");
+        CU(ctx, d.sn_refs.reserve(std::max<uint64_t>(rb, 1)));
+        CU(ctx, d.sn_qry.reserve(std::max<uint64_t>(qb, 1)));
+        CU(ctx, d.sn_roff.reserve((cnt + 1) * sizeof(uint64_t)));
+        CU(ctx, d.sn_qoff.reserve((cnt + 1) * sizeof(uint64_t)));
+        CU(ctx, d.sn_out.reserve(cnt));
+        if (rb) CU(ctx, cudaMemcpyAsync(d.sn_refs.p, refs + ref_offsets[lo], rb, cudaMemcpyHostToDevice, d.stream));
+        if (qb) CU(ctx, cudaMemcpyAsync(d.sn_qry.p, queries + query_offsets[lo], qb, cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaMemcpyAsync(d.sn_roff.p, ref_offsets + lo, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaMemcpyAsync(d.sn_qoff.p, query_offsets + lo, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+        SnakeParams sp{};
+        // the offsets stay absolute; the kernel subtracts the shard's first offset
+        sp.refs = d.sn_refs.as<uint8_t>();
+        sp.ref_off = d.sn_roff.as<uint64_t>();
+        sp.ref_base = ref_offsets[lo];
+        sp.queries = d.sn_qry.as<uint8_t>();
+        sp.qry_off = d.sn_qoff.as<uint64_t>();
+        sp.qry_base = query_offsets[lo];
+        sp.n = cnt;
+        sp.threshold = threshold;
+        sp.out = d.sn_out.as<uint8_t>();
+        sneaky_snake_kernel<<<(uint32_t)((cnt + 127) / 128), 128, 0, d.stream>>>(sp);
+        CU(ctx, cudaGetLastError());
+        ctx->last_launches++;
+        CU(ctx, cudaMemcpyAsync(out + lo, d.sn_out.p, cnt, cudaMemcpyDeviceToHost, d.stream));
+    }
+    return sync_and_time(ctx);
 }
 
 int zoe_cuda_last_timing(const zoe_cuda_ctx *ctx, float *total_ms, float *dp_kernel_ms, uint32_t *kernel_launches) {
