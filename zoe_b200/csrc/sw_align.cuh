@@ -561,28 +561,13 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
             }
             uint8_t *grow = bt + (size_t)r * nv * N;
             uint8_t *brow = SMEM ? frow : grow;
-            // The weight of vector v + 1 (two dependent shared-memory loads: symbol index, then weight) is fetched
-            // before vector v's stores, which takes it off the loop-carried critical path (216 -> ~160 cycles per vector).
-            int pw[2] = {0, 0};
-            auto fetch_w = [&](int v) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int l = lane + 32 * q;
-                    if (q < NL && l < N) {
-                        const int cidx = v + l * nv;
-                        pw[q] = cidx < m ? (int)wrow[SMEM ? pidx[cidx] : x.lut[P[cidx]]] : 0;
-                    }
-                }
-            };
-            fetch_w(0);
             for (int v = 0; v < nv; ++v) {
-                const int cw[2] = {pw[0], pw[1]};
-                if (v + 1 < nv) fetch_w(v + 1);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     int l = lane + 32 * q;
                     if (q < NL && l < N) {
-                        const int w = cw[q];
+                        int cidx = v + l * nv;
+                        int w = cidx < m ? (int)wrow[SMEM ? pidx[cidx] : x.lut[P[cidx]]] : 0;
                         int E = es[v * N + l];
                         int h = max(H[q] + w, 0);  // saturating_add, floor at MIN
                         h = max(max(h, E), F[q]);
