@@ -168,6 +168,11 @@ int zoe_cuda_set_width_policy(zoe_cuda_ctx *ctx, int first_bits, int last_bits, 
  *                   is redone by the literal kernel and counted in zoe_cuda_stats.window_fallback */
 int zoe_cuda_set_align_options(zoe_cuda_ctx *ctx, int mode, int checkpoint_log2, int slack);
 
+/* Upper bound on the device scratch one align / ranges / 3-pass call may hold at a time (checkpoints, direction-bit
+ * windows, box scratch); batches that need more are processed in chunks of streamed sequences.  0 = automatic (a
+ * fraction of the memory that was free when the context was created, at most 48 GB).  Results never depend on it. */
+int zoe_cuda_set_memory_budget(zoe_cuda_ctx *ctx, uint64_t scratch_bytes);
+
 /* ---- measurement hooks (not part of the zoe-facing surface) ---- */
 
 /* Device-resident variant of zoe_cuda_sw_score_batch for kernel-only timing: upload once with

@@ -52,6 +52,11 @@ unsafe extern "C" {
     pub fn zoe_cuda_set_lanes(ctx: *mut zoe_cuda_ctx, lanes_i8: c_int, lanes_i16: c_int, lanes_i32: c_int) -> c_int;
     pub fn zoe_cuda_set_width_policy(ctx: *mut zoe_cuda_ctx, first_bits: c_int, last_bits: c_int, is_unsigned: c_int) -> c_int;
     pub fn zoe_cuda_set_align_options(ctx: *mut zoe_cuda_ctx, mode: c_int, checkpoint_log2: c_int, slack: c_int) -> c_int;
+    pub fn zoe_cuda_set_memory_budget(ctx: *mut zoe_cuda_ctx, scratch_bytes: u64) -> c_int;
+    pub fn zoe_cuda_sneaky_snake_batch(
+        ctx: *mut zoe_cuda_ctx, refs: *const u8, ref_offsets: *const u64, queries: *const u8, query_offsets: *const u64,
+        n: u64, threshold: f32, out: *mut u8,
+    ) -> c_int;
     pub fn zoe_cuda_set_profiled(ctx: *mut zoe_cuda_ctx, concat: *const u8, offsets: *const u64, n: u32) -> c_int;
     pub fn zoe_cuda_sw_score_batch(
         ctx: *mut zoe_cuda_ctx, streamed_concat: *const u8, offsets: *const u64, n: u64, score: *mut u32,

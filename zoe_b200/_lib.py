@@ -19,7 +19,7 @@ SYMBOLS = [
     "zoe_cuda_run_score_staged", "zoe_cuda_run_align_staged", "zoe_cuda_fetch_scores", "zoe_cuda_last_timing",
     "zoe_cuda_last_stats", "zoe_cuda_dpx_peak", "zoe_cuda_stream", "zoe_cuda_set_align_options", "zoe_cuda_set_width_policy",
     "zoe_cuda_sw_score_ranges_batch", "zoe_cuda_run_ranges_staged", "zoe_cuda_sw_align_3pass_batch",
-    "zoe_cuda_run_3pass_staged", "zoe_cuda_sneaky_snake_batch",
+    "zoe_cuda_run_3pass_staged", "zoe_cuda_sneaky_snake_batch", "zoe_cuda_set_memory_budget",
 ]
 
 
@@ -56,6 +56,7 @@ def load() -> C.CDLL:
     lib.zoe_cuda_set_lanes.argtypes = [p, C.c_int, C.c_int, C.c_int]
     lib.zoe_cuda_set_align_options.argtypes = [p, C.c_int, C.c_int, C.c_int]
     lib.zoe_cuda_set_width_policy.argtypes = [p, C.c_int, C.c_int, C.c_int]
+    lib.zoe_cuda_set_memory_budget.argtypes = [p, C.c_uint64]
     lib.zoe_cuda_set_profiled.argtypes = [p, u8p, u64p, C.c_uint32]
     lib.zoe_cuda_sw_score_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p]
     lib.zoe_cuda_sw_align_batch.argtypes = [p, u8p, u64p, C.c_uint64, u32p, u8p, u8p, u32p, u32p, u32p, u32p, u32p,

@@ -202,6 +202,10 @@ class CudaProfiles:
         """Tuning of the align pipeline (never changes results): see ``zoe_cuda_set_align_options``."""
         self._check(self._lib.zoe_cuda_set_align_options(self._h, mode, checkpoint_log2, slack))
 
+    def set_memory_budget(self, scratch_bytes: int = 0):
+        """Bound the device scratch of one align / ranges / 3-pass call (0 = automatic); larger batches run in chunks."""
+        self._check(self._lib.zoe_cuda_set_memory_budget(self._h, int(scratch_bytes)))
+
     def set_width_policy(self, first_bits: int = 8, last_bits: int = 32, unsigned: bool = False):
         """Which zoe integer types may report a result: ``(8, 32)`` = ``sw_*_from_i8`` (default), ``(16, 32)`` =
         ``..._from_i16``, ``(32, 32)`` = ``..._from_i32`` (profile_set.rs:71-179); ``first == last`` = a standalone

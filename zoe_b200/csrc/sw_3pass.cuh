@@ -38,9 +38,9 @@ struct ThreePassParams {
     uint32_t *dp_cap;           // [n_pairs] slot -> CIGAR scratch capacity (words) at the head of the pair's scratch
     uint32_t *dp_slot;          // [n_pairs] chunk-local pair -> slot, kTpNoDp or kTpNoGaps
     uint8_t *blob;
-    unsigned long long *ctr;    // [0] DP pairs, [1] scratch bytes, [2] walks outside the band storage (zoe would panic),
-                                // [4] CIGAR scratch overflows, [5] no-gaps pairs, [6] banded, [7] scalar fallbacks,
-                                // [8] banded attempts, [9] running CIGAR base
+    unsigned long long *ctr;    // per classification: [0] DP pairs, [1] scratch bytes, [5] no-gaps pairs; per call:
+                                // [6] banded, [7] scalar fallbacks, [8] banded attempts, [9] running CIGAR base,
+                                // [10] walks outside the band storage (zoe would panic), [11] CIGAR scratch overflows
 };
 
 __host__ __device__ inline unsigned long long tp_align16(unsigned long long x) { return (x + 15ull) & ~15ull; }
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(64) tp_dp_kernel(const ThreePassParams t, uint
         cg.push(4u, c + b.qs);   // three_pass.rs:95 prepend_soft_clip(adjusted_query_range.start)
     }
     cg.flush();
-    if (cg.overflow) atomicAdd(&t.ctr[4], 1ULL);
-    if (oob) atomicAdd(&t.ctr[2], 1ULL);
+    if (cg.overflow) atomicAdd(&t.ctr[11], 1ULL);
+    if (oob) atomicAdd(&t.ctr[10], 1ULL);
     t.cig_count[gid] = cg.n;
     // three_pass.rs:89-105: ranges of the sub-alignment shifted into the full sequences
     const uint32_t ar0 = r + b.rs, ar1 = r_end1 + b.rs, aq0 = c + b.qs, aq1 = c_end1 + b.qs;

@@ -1630,13 +1630,14 @@ int run_3pass_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     t.dp_off = d.tp_off.as<unsigned long long>();
     t.ctr = ctr;
 
+    unsigned long long n_nogaps = 0;
     for (uint64_t p0 = 0; p0 < pairs;) {
         uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_pairs, pairs - p0);
-        unsigned long long work[2] = {0, 0};  // DP pairs, scratch bytes
+        unsigned long long work[6] = {0, 0, 0, 0, 0, 0};  // [0] DP pairs, [1] scratch bytes, [5] no-gaps pairs
         for (;;) {
             t.pair_first = p0;
             t.n_pairs = cn;
-            CU(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), d.stream));
+            CU(ctx, cudaMemsetAsync(ctr, 0, 6 * sizeof(unsigned long long), d.stream));
             tp_classify_kernel<<<(cn + 255) / 256, 256, 0, d.stream>>>(t);
             CU(ctx, cudaGetLastError());
             ctx->last_launches++;
@@ -1646,6 +1647,7 @@ int run_3pass_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             cn = std::max<uint32_t>(1, cn / 2);  // the boxes of this chunk need more scratch than the budget: split it
             chunk_pairs = cn;
         }
+        n_nogaps += work[5];
         if (work[0] > 0) {
             CU(ctx, d.tp_blob.reserve(work[1] + 16));
             t.blob = d.tp_blob.as<uint8_t>();
@@ -1683,13 +1685,13 @@ int run_3pass_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     d.cig_total = tail[9];
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        ctx->stats.tp_nogaps += tail[5];
+        ctx->stats.tp_nogaps += n_nogaps;
         ctx->stats.tp_banded += tail[6];
         ctx->stats.tp_scalar += tail[7];
         ctx->stats.tp_band_attempts += tail[8];
     }
-    if (tail[2]) return fail(ctx, ZOE_CUDA_E_STATE, "3-pass: %llu banded walks left the band storage (zoe would panic here)", tail[2]);
-    if (tail[4]) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: CIGAR scratch overflow on %llu pairs", tail[4]);
+    if (tail[10]) return fail(ctx, ZOE_CUDA_E_STATE, "3-pass: %llu banded walks left the band storage (zoe would panic here)", tail[10]);
+    if (tail[11]) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: CIGAR scratch overflow on %llu pairs", tail[11]);
     return 0;
 }
 
@@ -1904,6 +1906,12 @@ int zoe_cuda_set_align_options(zoe_cuda_ctx *ctx, int mode, int checkpoint_log2,
     ctx->align_mode = mode;
     ctx->win_cb_log2 = checkpoint_log2;
     ctx->win_slack = (uint32_t)slack;
+    return 0;
+}
+
+int zoe_cuda_set_memory_budget(zoe_cuda_ctx *ctx, uint64_t scratch_bytes) {
+    if (!ctx) return ZOE_CUDA_E_BAD_ARG;
+    ctx->flag_budget_bytes = scratch_bytes;  // 0 = automatic
     return 0;
 }
 
