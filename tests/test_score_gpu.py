@@ -188,3 +188,35 @@ def test_long_rows_vs_cpu_port_and_oracle():
         rc, s_, t_ = O.sw_score_from(bytes(genome), bytes(reads[i]), sc)
         assert (int(status[i, 0]), int(score[i, 0]), int(tier[i, 0])) == (rc, s_, t_)
     prof.close()
+
+
+def test_panel_larger_than_the_staging_area():
+    """A profiled set beyond 96 KB of symbol codes is swept group by group (launch_score): every pair must still land
+    in its own output slot with the score of the one-launch path.  Includes one sequence that alone exceeds the limit."""
+    rng = np.random.default_rng(31)
+    lens = [int(x) for x in rng.integers(900, 2400, 70)] + [100_000, 37, 1500]
+    targets = [synth.random_dna(rng, L) for L in lens]
+    assert sum(lens) > 2 * 96 * 1024
+    reads = []
+    for i in range(96):
+        t = targets[(i * 7) % len(targets)]
+        st = int(rng.integers(0, max(1, len(t) - 150)))
+        r = t[st:st + 150].copy()
+        flip = rng.random(len(r)) < 0.03
+        r[flip] = synth.random_dna(rng, int(flip.sum()))
+        reads.append(r)
+    reads.append(synth.random_dna(rng, 150))
+    prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], W25, -10, -1)
+    buf, offs = synth.pack(reads)
+    score, status, tier = prof.sw_score_arrays(buf, offs)
+    assert prof.last_timing()["kernel_launches"] >= 3  # several group launches
+    prof.close()
+    sc = osc(W25)
+    rs = np.random.default_rng(2)
+    pairs = [(i, (i * 7) % len(targets)) for i in range(96)]  # the true-origin pair of every read
+    pairs += [(int(rs.integers(0, len(reads))), int(rs.integers(0, len(targets)))) for _ in range(150)]
+    pairs += [(i, 70) for i in range(0, 97, 16)]               # the 100-kb sequence (read from global memory)
+    for i, j in pairs:
+        rc, s_, t_ = O.sw_score_from(bytes(targets[j]), bytes(reads[i]), sc)
+        assert (int(status[i, j]), int(score[i, j]) if rc == 0 else 0, int(tier[i, j]) if rc == 0 else 0) == \
+               (rc, s_ if rc == 0 else 0, t_ if rc == 0 else 0), (i, j)

@@ -98,6 +98,8 @@ struct ScoreParams {
     int go, ge;                // positive penalties
     int ovf_thresh;            // packed mode only
     int32_t *best;             // [n_rseq * n_cseq] exact score, or -1 = needs the wide kernel
+    uint32_t best_stride;      // row stride of `best` (0 = n_cseq) and first column: a launch may cover a sub-range of the
+    uint32_t best_col0;        // profiled set (panels larger than the shared-memory staging area are swept group by group)
 };
 
 template <bool PACKED>
@@ -532,14 +534,15 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_sc
                     if (st == 1 && !(ci + 1 < p.n_cseq)) break;
                     const uint32_t best = st == 0 ? abest : bbest;
                     const uint32_t cj = st == 0 ? cjA : cjB;
+                    const size_t bstride = p.best_stride ? p.best_stride : p.n_cseq, bcol = (size_t)p.best_col0 + cj;
                     if (PACKED) {
                         int b_lo = (int)(int16_t)(best & 0xffff), b_hi = (int)(int16_t)(best >> 16);
                         if (id_lo != 0xffffffffu)
-                            p.best[(size_t)id_lo * p.n_cseq + cj] = (b_lo >= p.ovf_thresh) ? -1 : b_lo;
+                            p.best[(size_t)id_lo * bstride + bcol] = (b_lo >= p.ovf_thresh) ? -1 : b_lo;
                         if (id_hi != 0xffffffffu)
-                            p.best[(size_t)id_hi * p.n_cseq + cj] = (b_hi >= p.ovf_thresh) ? -1 : b_hi;
+                            p.best[(size_t)id_hi * bstride + bcol] = (b_hi >= p.ovf_thresh) ? -1 : b_hi;
                     } else {
-                        p.best[(size_t)id_lo * p.n_cseq + cj] = (int)best;
+                        p.best[(size_t)id_lo * bstride + bcol] = (int)best;
                     }
                 }
             }

@@ -79,6 +79,7 @@ struct Device {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     // scoring + profiled (replicated on every device)
     DevBuf ccodes, coff, wk, lut, corder;
+    DevBuf ccodes_g, coff_g, corder_g;  // profiled set regrouped for panels beyond the shared-memory staging area
     // batch state
     DevBuf rseq, roff, best, score, status, tier, wide_ids, counters;
     // align state
@@ -158,6 +159,16 @@ struct zoe_cuda_ctx {
     std::vector<int8_t> wk;
     int n_csym = 0;
     uint32_t max_prof_len = 0;
+    // Panels whose symbol codes exceed the shared-memory staging area (kColsSmemLimit) are swept group by group by the
+    // score kernel: contiguous runs of profiled sequences that fit, each with its own 16-byte aligned copy of the codes.
+    struct ColGroup {
+        uint32_t j0, n;             // profiled sequences [j0, j0 + n)
+        uint32_t byte_start, bytes; // into ccodes_g
+        uint32_t coff_start;        // into coff_g (n + 1 entries, relative to byte_start) and corder_g (n entries)
+    };
+    std::vector<ColGroup> groups;
+    std::vector<uint8_t> ccodes_g;
+    std::vector<uint32_t> coff_g, corder_g;
     // staged batch (host view)
     uint64_t staged_n = 0;
     uint32_t staged_max_len = 0;
@@ -358,15 +369,19 @@ struct LaunchPlan {
     int cols_in_smem = 0;
 };
 
-size_t score_smem_bytes(const zoe_cuda_ctx *ctx, const KernelEntry &k, int threads, int cols_in_smem) {
+constexpr size_t kColsSmemLimit = 96 * 1024;  // profiled symbol codes staged per CTA (leaves room for the task tables)
+
+size_t score_smem_bytes(const zoe_cuda_ctx *ctx, const KernelEntry &k, int threads, int cols_in_smem, size_t cc_bytes) {
     size_t tab = (size_t)score_tab_bytes(ctx->n_csym, k.G, k.K) * (threads / k.G);
     size_t s = tab + 256 + (((size_t)ctx->n_csym * ctx->S + 15) & ~(size_t)15);
-    if (cols_in_smem) s += (ctx->ccodes.size() + 15) & ~(size_t)15;
+    if (cols_in_smem) s += (cc_bytes + 15) & ~(size_t)15;
     return s;
 }
 
+// cc_bytes: symbol-code bytes the launch covers (default: the whole profiled set)
 template <class Fn>
-int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan) {
+int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan, size_t cc_bytes = ~(size_t)0) {
+    if (cc_bytes == ~(size_t)0) cc_bytes = ctx->ccodes.size();
     int best_warps = 0;
     LaunchPlan bp;
     cudaFuncAttributes fa{};
@@ -375,11 +390,11 @@ int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan
         fa.maxThreadsPerBlock = 1024;
     }
     for (int cols_in_smem = 1; cols_in_smem >= 0; --cols_in_smem) {
-        if (cols_in_smem && ctx->ccodes.size() > 96 * 1024) continue;
+        if (cols_in_smem && cc_bytes > kColsSmemLimit) continue;
         static const int env_max_threads = getenv("ZOE_CUDA_MAX_THREADS") ? atoi(getenv("ZOE_CUDA_MAX_THREADS")) : 1024;
         for (int threads : {512, 384, 256, 128, 64, 32}) {
             if (threads < k.G || threads % k.G || threads > fa.maxThreadsPerBlock || threads > env_max_threads) continue;
-            size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem);
+            size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem, cc_bytes);
             if (smem > 227 * 1024) continue;
             int nb = 0;
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -425,6 +440,16 @@ int upload_scoring_and_profiled(zoe_cuda_ctx *ctx) {
         CU(ctx, d.corder.reserve(ctx->corder.size() * sizeof(uint32_t)));
         CU(ctx, cudaMemcpyAsync(d.corder.p, ctx->corder.data(), ctx->corder.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                 d.stream));
+        if (!ctx->groups.empty()) {
+            CU(ctx, d.ccodes_g.reserve(ctx->ccodes_g.size()));
+            CU(ctx, d.coff_g.reserve(ctx->coff_g.size() * sizeof(uint32_t)));
+            CU(ctx, d.corder_g.reserve(ctx->corder_g.size() * sizeof(uint32_t)));
+            CU(ctx, cudaMemcpyAsync(d.ccodes_g.p, ctx->ccodes_g.data(), ctx->ccodes_g.size(), cudaMemcpyHostToDevice, d.stream));
+            CU(ctx, cudaMemcpyAsync(d.coff_g.p, ctx->coff_g.data(), ctx->coff_g.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                    d.stream));
+            CU(ctx, cudaMemcpyAsync(d.corder_g.p, ctx->corder_g.data(), ctx->corder_g.size() * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, d.stream));
+        }
         CU(ctx, d.pbytes.reserve(ctx->prof_bytes.size()));
         CU(ctx, d.weights.reserve(ctx->weights.size()));
         CU(ctx, cudaMemcpyAsync(d.pbytes.p, ctx->prof_bytes.data(), ctx->prof_bytes.size(), cudaMemcpyHostToDevice,
@@ -499,12 +524,6 @@ int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *o
 
 int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed, const uint32_t *task_ids,
                  uint32_t n_ids) {
-    const bool two_streams = packed && ctx->n_prof >= 2 && !getenv("ZOE_CUDA_ONE_STREAM");
-    void (*fn)(const ScoreParams) = packed ? (two_streams ? k.packed2 : k.packed) : k.wide;
-
-    LaunchPlan plan;
-    int rc = plan_launch(ctx, k, fn, &plan);
-    if (rc) return rc;
     ScoreParams p{};
     p.rseq = d.rseq.as<uint8_t>();
     p.roff = d.roff.as<uint64_t>();
@@ -512,12 +531,6 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
     uint32_t n_seq = task_ids ? n_ids : (uint32_t)d.n_count;
     p.n_rseq = n_seq;
     p.n_tasks = packed ? (n_seq + 1) / 2 : n_seq;
-    p.ccodes = d.ccodes.as<uint8_t>();
-    p.coff = d.coff.as<uint32_t>();
-    p.corder = two_streams ? d.corder.as<uint32_t>() : nullptr;
-    p.n_cseq = ctx->n_prof;
-    p.ccodes_bytes = (uint32_t)ctx->ccodes.size();
-    p.cols_in_smem = plan.cols_in_smem;
     p.wk = d.wk.as<int8_t>();
     p.n_csym = ctx->n_csym;
     p.S = ctx->S;
@@ -526,15 +539,48 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
     p.ge = ctx->ge;
     p.ovf_thresh = kPackedLimit - std::max(ctx->max_weight, 0) - 1;
     p.best = d.best.as<int32_t>();
+    p.best_stride = ctx->n_prof;
     if (p.n_tasks == 0) return 0;
-    CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-    uint32_t groups_per_block = plan.threads / k.G;
-    uint32_t max_blocks = (uint32_t)(d.sm_count * plan.blocks_per_sm);
-    uint32_t need_blocks = (p.n_tasks + groups_per_block - 1) / groups_per_block;
-    uint32_t blocks = std::min(max_blocks, need_blocks);
-    fn<<<blocks, plan.threads, plan.smem, d.stream>>>(p);
-    CU(ctx, cudaGetLastError());
-    ctx->last_launches++;
+
+    // one launch over the whole profiled set, or (panels beyond the staging area) one launch per group of profiled
+    // sequences whose codes fit shared memory: the steady-state loops read the column codes from shared memory
+    // (5.8 -> 6.9 TCUPS on a 131-kb panel); every launch re-reads the streamed batch, which is tiny next to the sweep
+    const size_t n_launches = ctx->groups.empty() ? 1 : ctx->groups.size();
+    for (size_t gi = 0; gi < n_launches; ++gi) {
+        uint32_t n_cseq = ctx->n_prof;
+        size_t cc_bytes = ctx->ccodes.size();
+        if (!ctx->groups.empty()) {
+            const zoe_cuda_ctx::ColGroup &g = ctx->groups[gi];
+            n_cseq = g.n;
+            cc_bytes = g.bytes;
+            p.ccodes = d.ccodes_g.as<uint8_t>() + g.byte_start;
+            p.coff = d.coff_g.as<uint32_t>() + g.coff_start + gi;  // group gi's n + 1 offsets follow gi earlier "+1"s
+            p.best_col0 = g.j0;
+        } else {
+            p.ccodes = d.ccodes.as<uint8_t>();
+            p.coff = d.coff.as<uint32_t>();
+            p.best_col0 = 0;
+        }
+        const bool two_streams = packed && n_cseq >= 2 && !getenv("ZOE_CUDA_ONE_STREAM");
+        void (*fn)(const ScoreParams) = packed ? (two_streams ? k.packed2 : k.packed) : k.wide;
+        LaunchPlan plan;
+        int rc = plan_launch(ctx, k, fn, &plan, cc_bytes);
+        if (rc) return rc;
+        p.corder = nullptr;
+        if (two_streams)
+            p.corder = ctx->groups.empty() ? d.corder.as<uint32_t>() : d.corder_g.as<uint32_t>() + ctx->groups[gi].coff_start;
+        p.n_cseq = n_cseq;
+        p.ccodes_bytes = (uint32_t)cc_bytes;
+        p.cols_in_smem = plan.cols_in_smem;
+        CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        uint32_t groups_per_block = plan.threads / k.G;
+        uint32_t max_blocks = (uint32_t)(d.sm_count * plan.blocks_per_sm);
+        uint32_t need_blocks = (p.n_tasks + groups_per_block - 1) / groups_per_block;
+        uint32_t blocks = std::min(max_blocks, need_blocks);
+        fn<<<blocks, plan.threads, plan.smem, d.stream>>>(p);
+        CU(ctx, cudaGetLastError());
+        ctx->last_launches++;
+    }
     return 0;
 }
 
@@ -637,7 +683,7 @@ int launch_score_long(zoe_cuda_ctx *ctx, Device &d, const uint32_t *d_ids, uint3
     int best_warps = 0, best_threads = 0, best_blocks = 0, best_cols = 0;
     size_t best_smem = 0;
     for (int cols_in_smem = 1; cols_in_smem >= 0 && best_warps == 0; --cols_in_smem) {
-        if (cols_in_smem && ctx->ccodes.size() > 96 * 1024) continue;
+        if (cols_in_smem && ctx->ccodes.size() > kColsSmemLimit) continue;
         for (int threads : {512, 384, 256, 128, 64, 32}) {
             size_t smem = tab_per_warp * (threads / 32) + fixed + (cols_in_smem ? ((ctx->ccodes.size() + 15) & ~(size_t)15) : 0);
             if (smem > 227 * 1024) continue;
@@ -1836,7 +1882,7 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
     if (!ctx) return;
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
-        for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.corder, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
+        for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.corder, &d.ccodes_g, &d.coff_g, &d.corder_g, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.tp_pair, &d.tp_off, &d.tp_cap, &d.tp_slot,
@@ -1963,6 +2009,40 @@ int zoe_cuda_set_profiled(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64
     ctx->wk.assign((size_t)ctx->n_csym * ctx->S, 0);
     for (int c = 0; c < ctx->n_csym; ++c)
         for (int r = 0; r < ctx->S; ++r) ctx->wk[(size_t)c * ctx->S + r] = ctx->weights[(size_t)r * ctx->S + sym_of_dense[c]];
+    // regroup a panel that does not fit the staging area (see launch_score)
+    ctx->groups.clear();
+    ctx->ccodes_g.clear();
+    ctx->coff_g.clear();
+    ctx->corder_g.clear();
+    if (total > kColsSmemLimit && n > 1) {
+        uint32_t j = 0;
+        while (j < n) {
+            zoe_cuda_ctx::ColGroup g{};
+            g.j0 = j;
+            g.byte_start = (uint32_t)ctx->ccodes_g.size();
+            g.coff_start = (uint32_t)ctx->corder_g.size();
+            uint32_t bytes = 0;
+            while (j < n && (bytes == 0 || bytes + (ctx->coff[j + 1] - ctx->coff[j]) <= kColsSmemLimit)) {
+                ctx->coff_g.push_back(bytes);
+                bytes += ctx->coff[j + 1] - ctx->coff[j];
+                ++j;
+            }
+            ctx->coff_g.push_back(bytes);
+            g.n = j - g.j0;
+            g.bytes = bytes;
+            ctx->ccodes_g.insert(ctx->ccodes_g.end(), ctx->ccodes.begin() + ctx->coff[g.j0], ctx->ccodes.begin() + ctx->coff[j]);
+            ctx->ccodes_g.resize((ctx->ccodes_g.size() + 15) & ~(size_t)15, 0);  // next group starts 16-byte aligned (TMA)
+            std::vector<uint32_t> order(g.n);
+            for (uint32_t q = 0; q < g.n; ++q) order[q] = q;
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+                return ctx->coff[g.j0 + a + 1] - ctx->coff[g.j0 + a] > ctx->coff[g.j0 + b + 1] - ctx->coff[g.j0 + b];
+            });
+            ctx->corder_g.insert(ctx->corder_g.end(), order.begin(), order.end());
+            ctx->groups.push_back(g);
+        }
+        ctx->ccodes_g.resize(ctx->ccodes_g.size() + 16, 0);
+        if (ctx->groups.size() < 2) ctx->groups.clear();
+    }
     int rc = upload_scoring_and_profiled(ctx);
     if (rc) return rc;
     ctx->have_profiled = true;
