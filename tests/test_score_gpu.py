@@ -220,3 +220,44 @@ def test_panel_larger_than_the_staging_area():
         rc, s_, t_ = O.sw_score_from(bytes(targets[j]), bytes(reads[i]), sc)
         assert (int(status[i, j]), int(score[i, j]) if rc == 0 else 0, int(tier[i, j]) if rc == 0 else 0) == \
                (rc, s_ if rc == 0 else 0, t_ if rc == 0 else 0), (i, j)
+
+
+def _protein_batch(rng, target, n, min_len, max_len):
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    seqs = []
+    for i in range(n):
+        L = int(rng.integers(min_len, max_len + 1))
+        if i % 3 == 0:
+            s = rng.choice(aa, L)
+        else:
+            st = int(rng.integers(0, max(1, len(target) - L)))
+            s = target[st:st + L].copy()
+            if len(s) < L:
+                s = np.concatenate([s, rng.choice(aa, L - len(s))])
+            flip = rng.random(L) < 0.2
+            s[flip] = rng.choice(aa, int(flip.sum()))
+        seqs.append(s.astype(np.uint8))
+    return seqs
+
+
+@pytest.mark.parametrize("min_len,max_len", [(300, 300), (64, 420), (64, 65)])
+def test_streamed_trips_large_alphabet(min_len, max_len):
+    """The shared-rows kernel sweeps a warp's trips back to back (sw_score_rows_stream_kernel): enough queries that every
+    warp streams several trips, equal and ragged lengths, checked element-wise against the vectorised CPU port (which
+    tests/test_cpu_baseline.py ties to the plain-C oracle)."""
+    from oracle import cpu_baseline as CB
+    rng = np.random.default_rng(41)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    target = rng.choice(aa, 566).astype(np.uint8)
+    seqs = _protein_batch(rng, target, 30011, min_len, max_len)
+    buf, offs = synth.pack(seqs)
+    prof = CudaProfiles.new_with_w256([bytes(target)], BLOSUM_62, -10, -1)
+    score, status, tier = prof.sw_score_arrays(buf, offs)
+    stats = prof.last_stats()
+    prof.close()
+    pbuf, poff = synth.pack([target])
+    c_score, c_status, c_tier = CB.score_batch(pbuf, poff, buf, offs, BLOSUM_62.weights, BLOSUM_62.mapping.index_map, -10, -1)
+    assert np.array_equal(status, c_status)
+    some = c_status == 0
+    assert np.array_equal(score[some], c_score[some]) and np.array_equal(tier[some], c_tier[some])
+    assert stats["tier16"] > 100 and stats["tier8"] > 100

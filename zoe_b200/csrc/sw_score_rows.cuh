@@ -219,4 +219,248 @@ __global__ void __launch_bounds__(K > 20 ? 256 : 384) sw_score_rows_kernel(const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Streaming variant: a warp sweeps its trips back to back instead of draining the systolic array after each one.
+// With sweeps as short as 300 columns the lane skew costs 31 half-idle ramp steps plus 31 tail steps per trip (10 % of
+// config 5); here lane l starts trip t's first column at the step after it finished trip t-1's last one, so only the
+// very first ramp and the very last tail of a warp's whole stream are idle.
+//   * a trip's length is max over its four sequences (pad symbols beyond a sequence's own end, as before);
+//   * boundary steps (the first 32 steps of a trip): lane l is still in trip t-1 while step < l, crosses at step == l
+//     (parks its per-trip maxima in shared memory, zeroes its H / F registers and the pending diagonal), and reads the
+//     column symbols of whichever trip it is in (two staging buffers per warp);
+//   * steady steps: every lane is in the current trip, no per-lane tests -- the same loop as above.
+// Requires every streamed sequence to have at least 64 residues (the host falls back to sw_score_rows_kernel otherwise).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t rows_stream_stage_bytes(uint32_t max_rlen) {
+    return (size_t)8 * ((max_rlen + 7) & ~7u) * 2 + 64 * 4;  // two staging buffers + the parked maxima (32 lanes x 2 chains)
+}
+
+template <int G, int K>
+__global__ void __launch_bounds__(K > 20 ? 256 : 384) sw_score_rows_stream_kernel(const RowsParams rp) {
+    constexpr bool PACKED = true;
+    using O = Ops<true>;
+    const ScoreParams &p = rp.s;
+    constexpr int K4 = (K + 3) / 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(G == 32, "one task pair per warp");
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int lig = lane;
+
+    const uint32_t sym_stride = (uint32_t)(K4 * G * 16);
+    const size_t tab_bytes = rows_tab_bytes(p.S, G, K);
+    const uint32_t stage_len = (rp.max_rlen + 7) & ~7u;
+    uint8_t *wbase = smem + tab_bytes + (size_t)warp * rows_stream_stage_bytes(rp.max_rlen);
+    uint16_t *stage2 = reinterpret_cast<uint16_t *>(wbase);                              // [2][4][stage_len]
+    uint32_t *parked = reinterpret_cast<uint32_t *>(wbase + (size_t)16 * stage_len);     // [32 lanes][2 chains]
+
+    const uint32_t c0 = p.coff[rp.cj];
+    const int Lrows = (int)(p.coff[rp.cj + 1] - c0);
+    for (int idx = tid; idx < (p.S + 1) * K4 * G * 4; idx += blockDim.x) {
+        const int e = idx & 3, l = (idx >> 2) % G, i4 = ((idx >> 2) / G) % K4, q = (idx >> 2) / (G * K4);
+        const int i = i4 * 4 + e, r = l * K + i;
+        int w = kPadWeight;
+        if (q < p.S && i < K && r < Lrows) w = (int)p.wk[(size_t)p.ccodes[c0 + r] * p.S + q];
+        reinterpret_cast<uint32_t *>(smem)[idx] = (uint32_t)(w & 0xffff);
+    }
+    __syncthreads();
+
+    uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+    uint32_t lane_off = (uint32_t)lane * 16u;
+    uint32_t nz = lane != 0 ? 1u : 0u;
+    uint32_t sym_stride_r = sym_stride;
+    asm volatile("" : "+r"(go_s), "+r"(neg_ge), "+r"(lane_off), "+r"(nz), "+r"(sym_stride_r));
+    const uint32_t pad_sym = (uint32_t)p.S;
+
+    const uint32_t n_tasks = (p.n_rseq + 1) / 2;
+    const uint32_t n_trips_total = (n_tasks + 1) / 2;
+    const uint32_t total_warps = gridDim.x * warps_per_block;
+
+    uint32_t aH[2][K], aF[K], bH[2][K], bF[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        aH[0][i] = aH[1][i] = 0;
+        aF[i] = 0;
+        bH[0][i] = bH[1][i] = 0;
+        bF[i] = 0;
+    }
+    uint32_t abest = 0, ah_last = 0, ae_out = 0, ah_up_prev = 0;
+    uint32_t bbest = 0, bh_last = 0, be_out = 0, bh_up_prev = 0;
+
+    // one column of one chain, its symbols read from the staging buffer `sb` (trip-local column j)
+    auto chain_col = [&](auto parity, auto which, const uint16_t *sb, const int j, const uint32_t e_in) {
+        constexpr int PO = decltype(parity)::value, PN = 1 - PO;
+        constexpr bool IS_A = decltype(which)::value == 0;
+        const uint16_t *c_lo = sb + (IS_A ? 0 : 2) * stage_len, *c_hi = c_lo + stage_len;
+        const uint32_t off_lo = (uint32_t)c_lo[j] * sym_stride_r, off_hi = (uint32_t)c_hi[j] * sym_stride_r;
+        const uint4 *tl = reinterpret_cast<const uint4 *>(smem + lane_off + off_lo);
+        const uint4 *th = reinterpret_cast<const uint4 *>(smem + lane_off + off_hi);
+        if (IS_A) {
+            uint32_t adiag = ah_up_prev, aE = e_in, ahp = 0;
+#pragma unroll
+            for (int i4 = 0; i4 < K4; ++i4) {
+                const uint4 l4 = tl[i4 * G], h4 = th[i4 * G];
+                const uint32_t w[4] = {h4.x * 65536u + l4.x, h4.y * 65536u + l4.y, h4.z * 65536u + l4.z, h4.w * 65536u + l4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i4 * 4 + q;
+                    if (i < K) ZOE_SCORE_ROW(a, w[q])
+                }
+            }
+            if (K & 1) abest = O::max2(abest, ahp);
+            ah_last = aH[PN][K - 1];
+            ae_out = aE;
+        } else {
+            uint32_t bdiag = bh_up_prev, bE = e_in, bhp = 0;
+#pragma unroll
+            for (int i4 = 0; i4 < K4; ++i4) {
+                const uint4 l4 = tl[i4 * G], h4 = th[i4 * G];
+                const uint32_t w[4] = {h4.x * 65536u + l4.x, h4.y * 65536u + l4.y, h4.z * 65536u + l4.z, h4.w * 65536u + l4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i4 * 4 + q;
+                    if (i < K) ZOE_SCORE_ROW(b, w[q])
+                }
+            }
+            if (K & 1) bbest = O::max2(bbest, bhp);
+            bh_last = bH[PN][K - 1];
+            be_out = bE;
+        }
+    };
+    using C0 = std::integral_constant<int, 0>;
+    using C1 = std::integral_constant<int, 1>;
+
+    // boundary / ramp / tail step: local step k of the current trip; a lane is in the current trip when k >= lane,
+    // else still in the previous one (column Lprev + k - lane)
+    auto generic_step = [&](auto parity, const int k, const bool have_cur, const bool have_prev, const int Lprev,
+                            const uint16_t *sb_cur, const uint16_t *sb_prev) {
+        const uint32_t ah_in = __shfl_up_sync(FULL, ah_last, 1) * nz, ae_in = __shfl_up_sync(FULL, ae_out, 1) * nz;
+        const uint32_t bh_in = __shfl_up_sync(FULL, bh_last, 1) * nz, be_in = __shfl_up_sync(FULL, be_out, 1) * nz;
+        const int jn = k - lig;
+        const bool in_cur = have_cur && jn >= 0;
+        if (in_cur && jn == 0) {  // crossing into the current trip
+            parked[2 * lane] = abest;
+            parked[2 * lane + 1] = bbest;
+            abest = bbest = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                aH[0][i] = aH[1][i] = 0;
+                aF[i] = 0;
+                bH[0][i] = bH[1][i] = 0;
+                bF[i] = 0;
+            }
+            ah_up_prev = bh_up_prev = 0;
+        }
+        // one pass over the columns for the whole warp: each lane reads the trip it is in
+        if (in_cur || (have_prev && jn < 0)) {
+            const uint16_t *sb = in_cur ? sb_cur : sb_prev;
+            const int j = in_cur ? jn : Lprev + jn;
+            chain_col(parity, C0{}, sb, j, ae_in);
+            chain_col(parity, C1{}, sb, j, be_in);
+        }
+        ah_up_prev = ah_in;
+        bh_up_prev = bh_in;
+    };
+    auto steady_step = [&](auto parity, const int k, const uint16_t *sb_cur) {
+        const uint32_t ah_in = __shfl_up_sync(FULL, ah_last, 1) * nz, ae_in = __shfl_up_sync(FULL, ae_out, 1) * nz;
+        const uint32_t bh_in = __shfl_up_sync(FULL, bh_last, 1) * nz, be_in = __shfl_up_sync(FULL, be_out, 1) * nz;
+        const int j = k - lig;
+        chain_col(parity, C0{}, sb_cur, j, ae_in);
+        chain_col(parity, C1{}, sb_cur, j, be_in);
+        ah_up_prev = ah_in;
+        bh_up_prev = bh_in;
+    };
+
+    uint32_t pids[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    bool have_prev = false;
+    int Lprev = 0, buf = 0;
+    uint32_t gs = 0;  // global step of this warp: its parity selects the ping-pong register set
+    for (uint32_t trip = blockIdx.x * warps_per_block + warp;; trip += total_warps) {
+        const bool have_cur = trip < n_trips_total;
+        if (!have_cur && !have_prev) break;
+        uint32_t ids[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        int Lcur = 0;
+        uint16_t *sb_cur = stage2 + (size_t)buf * 4 * stage_len;
+        const uint16_t *sb_prev = stage2 + (size_t)(buf ^ 1) * 4 * stage_len;
+        if (have_cur) {
+            int lens[4];
+            uint64_t offs[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const uint64_t a = (uint64_t)4 * trip + h;
+                uint32_t id = 0xffffffffu;
+                if (a < p.n_rseq) id = p.task_ids ? p.task_ids[a] : (uint32_t)a;
+                ids[h] = id;
+                offs[h] = id != 0xffffffffu ? p.roff[id] : 0;
+                lens[h] = id != 0xffffffffu ? (int)(p.roff[id + 1] - offs[h]) : 0;
+            }
+            Lcur = max(max(lens[0], lens[1]), max(lens[2], lens[3]));
+            // ---- stage the column symbols of the four sequences (the other buffer still serves trip t-1's tail) ----
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+                for (int j = lane; j < Lcur; j += 32) {
+                    uint32_t sym = pad_sym;
+                    if (j < lens[h]) sym = (uint32_t)p.lut[p.rseq[offs[h] + j]];
+                    sb_cur[h * stage_len + j] = (uint16_t)sym;
+                }
+            __syncwarp();
+        }
+
+        // ---- boundary segment: 32 steps (every lane has crossed by step 31), plus one when the steady loop would
+        //      otherwise start on an odd global step; without a current trip it is the 31-step tail of the stream ----
+        int k = 0;
+        const int nb = have_cur ? 32 : 31;
+        for (; k < nb || (have_cur && (gs & 1)); ++k, ++gs) {
+            if (gs & 1)
+                generic_step(C1{}, k, have_cur, have_prev, Lprev, sb_cur, sb_prev);
+            else
+                generic_step(C0{}, k, have_cur, have_prev, Lprev, sb_cur, sb_prev);
+        }
+        if (!have_cur) {  // end of the stream: park the last trip's maxima
+            parked[2 * lane] = abest;
+            parked[2 * lane + 1] = bbest;
+        }
+        if (have_prev) {  // every lane has parked trip t-1's maxima: reduce and write
+            __syncwarp();
+            uint32_t va = parked[2 * lane], vb = parked[2 * lane + 1];
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                va = O::max2(va, __shfl_xor_sync(FULL, va, d));
+                vb = O::max2(vb, __shfl_xor_sync(FULL, vb, d));
+            }
+            if (lane == 0) {
+                const int v[4] = {(int)(int16_t)(va & 0xffff), (int)(int16_t)(va >> 16), (int)(int16_t)(vb & 0xffff),
+                                  (int)(int16_t)(vb >> 16)};
+#pragma unroll
+                for (int h = 0; h < 4; ++h)
+                    if (pids[h] != 0xffffffffu) p.best[(size_t)pids[h] * p.n_cseq + rp.cj] = (v[h] >= p.ovf_thresh) ? -1 : v[h];
+            }
+            __syncwarp();
+        }
+        if (!have_cur) break;
+
+        // ---- steady segment: every lane is inside the current trip ----
+        for (; k + 1 < Lcur; k += 2, gs += 2) {
+            steady_step(C0{}, k, sb_cur);
+            steady_step(C1{}, k + 1, sb_cur);
+        }
+        for (; k < Lcur; ++k, ++gs) {
+            if (gs & 1)
+                generic_step(C1{}, k, true, false, 0, sb_cur, sb_prev);
+            else
+                generic_step(C0{}, k, true, false, 0, sb_cur, sb_prev);
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) pids[h] = ids[h];
+        have_prev = true;
+        Lprev = Lcur;
+        buf ^= 1;
+    }
+}
+
 }  // namespace zoe_cuda

@@ -172,6 +172,7 @@ struct zoe_cuda_ctx {
     // staged batch (host view)
     uint64_t staged_n = 0;
     uint32_t staged_max_len = 0;
+    uint32_t staged_min_len = 0;
     uint64_t staged_cells = 0;
     bool staged = false;
     std::vector<uint32_t> staged_len;  // per streamed sequence (only kept when the long-row path is needed)
@@ -475,15 +476,17 @@ int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *o
     if (!ctx->have_profiled) return fail(ctx, ZOE_CUDA_E_STATE, "set_profiled must be called before a batch");
     if (n > 0 && (!concat || !offsets)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null batch pointers");
     if (n >= 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "batch too large");
-    uint32_t max_len = 0;
+    uint32_t max_len = 0, min_len = n ? 0xffffffffu : 0u;
     uint64_t tot = 0;
     for (uint64_t i = 0; i < n; ++i) {
         if (offsets[i + 1] < offsets[i]) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "offsets must be non-decreasing");
         uint64_t len = offsets[i + 1] - offsets[i];
         if (len > 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "sequence too long");
         max_len = std::max<uint32_t>(max_len, (uint32_t)len);
+        min_len = std::min<uint32_t>(min_len, (uint32_t)len);
         tot += len;
     }
+    ctx->staged_min_len = min_len;
     uint64_t prof_total = ctx->prof_off[ctx->n_prof];
     ctx->staged_n = n;
     ctx->staged_max_len = max_len;
@@ -592,6 +595,12 @@ struct RowsEntry {
     int K;
     void (*fn)(const RowsParams);
 };
+// streaming variants (trips swept back to back; every streamed sequence >= 64 residues), same K list
+const RowsEntry kRowsStreamKernels[] = {
+    {8, sw_score_rows_stream_kernel<32, 8>},   {12, sw_score_rows_stream_kernel<32, 12>}, {16, sw_score_rows_stream_kernel<32, 16>},
+    {18, sw_score_rows_stream_kernel<32, 18>}, {20, sw_score_rows_stream_kernel<32, 20>}, {24, sw_score_rows_stream_kernel<32, 24>},
+    {28, sw_score_rows_stream_kernel<32, 28>}, {32, sw_score_rows_stream_kernel<32, 32>},
+};
 const RowsEntry kRowsKernels[] = {
     {8, sw_score_rows_kernel<32, 8>},   {12, sw_score_rows_kernel<32, 12>}, {16, sw_score_rows_kernel<32, 16>},
     {18, sw_score_rows_kernel<32, 18>}, {20, sw_score_rows_kernel<32, 20>}, {24, sw_score_rows_kernel<32, 24>},
@@ -607,7 +616,8 @@ bool rows_path_applies(const zoe_cuda_ctx *ctx) {
 
 int launch_score_rows(zoe_cuda_ctx *ctx, Device &d) {
     const RowsEntry *k = nullptr;
-    for (const RowsEntry &e : kRowsKernels)
+    const bool stream = ctx->staged_min_len >= 64 && !getenv("ZOE_CUDA_NO_ROWS_STREAM");
+    for (const RowsEntry &e : (stream ? kRowsStreamKernels : kRowsKernels))
         if ((uint32_t)(32 * e.K) >= ctx->max_prof_len) {
             k = &e;
             break;
@@ -632,7 +642,8 @@ int launch_score_rows(zoe_cuda_ctx *ctx, Device &d) {
     p.ovf_thresh = 32767 - std::max(ctx->max_weight, 0) - 1;
     p.best = d.best.as<int32_t>();
     rp.max_rlen = ctx->staged_max_len;
-    const size_t tab = rows_tab_bytes(ctx->S, 32, k->K), stage = rows_stage_bytes(rp.max_rlen);
+    const size_t tab = rows_tab_bytes(ctx->S, 32, k->K);
+    const size_t stage = stream ? rows_stream_stage_bytes(rp.max_rlen) : rows_stage_bytes(rp.max_rlen);
     int best_warps = 0, best_threads = 0, best_blocks = 0;
     size_t best_smem = 0;
     cudaFuncAttributes fa{};
