@@ -28,9 +28,17 @@ def test_two_devices_equal_one_device_score_align_ranges():
         aln = prof.align_arrays(buf, offs)
         rng = prof.ranges_arrays(buf, offs)
         st = prof.last_stats()
+        tp = prof.align_arrays(buf, offs, three_pass=True)
+        st_tp = prof.last_stats()
         prof.close()
-        res.append((score, aln, rng, st))
-    (s1, a1, r1, st1), (s2, a2, r2, st2) = res
+        res.append((score, aln, rng, st, tp, st_tp))
+    (s1, a1, r1, st1, t1, stt1), (s2, a2, r2, st2, t2, stt2) = res
+    n3 = int(t1["cigar_off"][-1])
+    assert n3 == int(t2["cigar_off"][-1])
+    for k in ("score", "status", "tier", "ref_start", "ref_end", "query_start", "query_end", "cigar_off"):
+        assert np.array_equal(t1[k], t2[k]), ("3pass", k)
+    assert np.array_equal(t1["cigar"][:n3], t2["cigar"][:n3])
+    assert (stt1["tp_nogaps"], stt1["tp_banded"], stt1["tp_scalar"]) == (stt2["tp_nogaps"], stt2["tp_banded"], stt2["tp_scalar"])
     for x, y in zip(s1, s2):
         assert np.array_equal(x, y)
     n_words = int(a1["cigar_off"][-1])
@@ -41,3 +49,22 @@ def test_two_devices_equal_one_device_score_align_ranges():
     for k in r1:
         assert np.array_equal(r1[k], r2[k]), k
     assert st1["tier8"] == st2["tier8"] and st1["tier16"] == st2["tier16"]
+
+
+@pytest.mark.skipif("_n_gpus() < 2")
+def test_two_devices_sneaky_snake():
+    from oracle import oracle as O
+    from zoe_b200 import SneakySnake
+    rng = np.random.default_rng(12)
+    refs, qs = [], []
+    for _ in range(1001):
+        ref = rng.choice(list(b"ACGT"), 100).astype(np.uint8)
+        q = ref.copy()
+        for pos in rng.integers(0, 100, int(rng.integers(0, 20))):
+            q[pos] = rng.choice(list(b"ACGT"))
+        refs.append(bytes(ref))
+        qs.append(bytes(q))
+    snake = SneakySnake(n_devices=2)
+    assert snake.sneaky_snake_batch(refs, qs, 0.1) == [O.sneaky_snake(r, q, 0.1) for r, q in zip(refs, qs)]
+    assert snake.sneaky_snake_batch(refs[:1], qs[:1], 0.1) == [O.sneaky_snake(refs[0], qs[0], 0.1)]  # fewer pairs than devices
+    snake.close()

@@ -2258,12 +2258,15 @@ int zoe_cuda_sneaky_snake_batch(zoe_cuda_ctx *ctx, const uint8_t *refs, const ui
     begin_call(ctx);
     // pairs are split over the context's devices by contiguous index range, like every other batch call
     const size_t nd = ctx->devs.size();
+    for (Device &d : ctx->devs) {  // every device takes part in the timing, also one that gets no pairs
+        CU(ctx, cudaSetDevice(d.id));
+        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+    }
     for (size_t k = 0; k < nd; ++k) {
         Device &d = ctx->devs[k];
         const uint64_t lo = n * k / nd, hi = n * (k + 1) / nd, cnt = hi - lo;
         if (cnt == 0) continue;
         CU(ctx, cudaSetDevice(d.id));
-        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
         const uint64_t rb = ref_offsets[hi] - ref_offsets[lo], qb = query_offsets[hi] - query_offsets[lo];
         if ((rb && !refs) || (qb && !queries)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null sequence buffer");
         CU(ctx, d.sn_refs.reserve(std::max<uint64_t>(rb, 1)));
