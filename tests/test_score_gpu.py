@@ -261,3 +261,22 @@ def test_streamed_trips_large_alphabet(min_len, max_len):
     some = c_status == 0
     assert np.array_equal(score[some], c_score[some]) and np.array_equal(tier[some], c_tier[some])
     assert stats["tier16"] > 100 and stats["tier8"] > 100
+
+
+def test_offsets_need_not_start_at_zero():
+    # a batch may be a window of a larger buffer: offsets[0] != 0 (the shard's offsets are rebased on the device)
+    targets, reads = synth.config1(ROOT, n_reads=257)
+    buf, offs = synth.fixed_len_batch(reads)
+    prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], W25, -10, -1)
+    want = prof.sw_score_arrays(buf, offs)
+    junk = np.frombuffer(b"GATTACA" * 11, dtype=np.uint8)
+    buf2 = np.concatenate([junk, buf])
+    offs2 = (offs + np.uint64(len(junk))).astype(np.uint64)
+    got = prof.sw_score_arrays(buf2, offs2)
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    a1 = prof.align_arrays(buf, offs)
+    a2 = prof.align_arrays(buf2, offs2)
+    for k in ("score", "status", "ref_start", "ref_end", "query_start", "query_end", "cigar_off"):
+        assert np.array_equal(a1[k], a2[k]), k
+    prof.close()

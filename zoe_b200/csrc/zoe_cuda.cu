@@ -472,6 +472,11 @@ void shard(zoe_cuda_ctx *ctx, uint64_t n) {
     }
 }
 
+__global__ void rebase_offsets_kernel(uint64_t *off, uint64_t n, uint64_t base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] -= base;
+}
+
 int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n) {
     if (!ctx->have_profiled) return fail(ctx, ZOE_CUDA_E_STATE, "set_profiled must be called before a batch");
     if (n > 0 && (!concat || !offsets)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null batch pointers");
@@ -507,12 +512,15 @@ int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *o
         CU(ctx, d.roff.reserve((d.n_count + 1) * sizeof(uint64_t)));
         if (d.rseq_bytes)
             CU(ctx, cudaMemcpyAsync(d.rseq.p, concat + b0, d.rseq_bytes, cudaMemcpyHostToDevice, d.stream));
-        // offsets are rebased on the device by the kernel reading (off - base): keep them absolute
-        // on the host and subtract here in a small staging vector (pageable -> the copy is staged).
-        std::vector<uint64_t> rel(d.n_count + 1);
-        for (uint64_t i = 0; i <= d.n_count; ++i) rel[i] = offsets[d.n_first + i] - b0;
-        CU(ctx, cudaMemcpyAsync(d.roff.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
-        CU(ctx, cudaStreamSynchronize(d.stream));  // `rel` dies at scope end
+        // the shard's offsets go up as the caller holds them (one copy straight from the caller's buffer, which
+        // outlives the call) and are rebased to the shard's first byte on the device
+        CU(ctx, cudaMemcpyAsync(d.roff.p, offsets + d.n_first, (d.n_count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                d.stream));
+        if (b0) {
+            rebase_offsets_kernel<<<(uint32_t)((d.n_count + 256) / 256), 256, 0, d.stream>>>(d.roff.as<uint64_t>(),
+                                                                                             d.n_count + 1, b0);
+            CU(ctx, cudaGetLastError());
+        }
         size_t pairs = (size_t)d.n_count * ctx->n_prof;
         CU(ctx, d.best.reserve(pairs * sizeof(int32_t)));
         CU(ctx, d.score.reserve(pairs * sizeof(uint32_t)));
