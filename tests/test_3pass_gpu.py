@@ -33,8 +33,12 @@ def check_3pass(targets, seqs, wm, go=-10, ge=-1, profiled_is_query=False, lanes
     paths = {0: 0, 1: 0, 2: 0}
     for i, s in enumerate(seqs):
         for j, t in enumerate(targets):
-            rc, aln, _tier, path = O.sw_align_3pass_from(t, s, sc, lanes=lanes, first_bits=policy[0] if policy else 8,
-                                                         streamed_is_query=not profiled_is_query)
+            if policy and policy[0] == policy[1]:  # a standalone StripedProfile<T, N, S>
+                rc, aln, path = O.striped_align_3pass(t, s, sc, policy[0], lanes[0], signed=not policy[2],
+                                                      streamed_is_query=not profiled_is_query)
+            else:
+                rc, aln, _tier, path = O.sw_align_3pass_from(t, s, sc, lanes=lanes, first_bits=policy[0] if policy else 8,
+                                                             streamed_is_query=not profiled_is_query)
             g = got[i][j]
             assert g.status.value == rc, (i, j, g, rc, aln)
             if rc == O.SOME:
@@ -121,7 +125,10 @@ def test_protein_and_width_policies():
     t = [synth.random_dna(rng, 200)]
     seqs = [t[0][10:150].copy(), synth.random_dna(rng, 90), t[0][:64].copy(), np.concatenate([t[0][10:60], t[0][66:150]])]
     check_3pass(t, seqs, W25, policy=(16, 32, False), profiled_is_query=True)
-    check_3pass(t, seqs, W25, policy=(32, 32, False))
+    check_3pass(t, seqs, W25, policy=(32, 32, False), lanes=(8, 8, 8))
+    # unsigned standalone profiles over the biased matrix: u8 overflows where i8 would not (limit 255 - bias - 1)
+    check_3pass(t, seqs, W25, policy=(8, 8, True), lanes=(16, 16, 16), profiled_is_query=True)
+    check_3pass(t, seqs, W25, policy=(16, 16, True), lanes=(16, 16, 16))
     w = WeightMatrix.new(DNA_PROFILE_MAP, 127, -5, b"N")
     stats = check_3pass([b"A" * 600], [b"A" * 600, b"A" * 300, b"A" * 100 + b"C" + b"A" * 100], w)
     assert stats["tier32"] == 1
