@@ -66,6 +66,7 @@ struct WinParams {
     uint32_t wmax;               // window capacity in columns
     unsigned long long *counters; // [7] internal consistency failures
     // reverse instantiation of pass A (ranges, sw_ranges.cuh): tasks = pairs of `items` sharing (profiled, end column)
+    int rev_maxw;                // largest substitution weight (bounds how many columns a reversed sub-problem needs)
     const AlignEnd *rev_in;      // forward end cells (exact)
     AlignEnd *rev_out;           // (best, r', c') of the reversed, truncated sub-problem
     int pin_mode;                // 0: window fill; 1: pin sweep, result back in pass A's representation;
@@ -146,7 +147,22 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
         uint64_t off_lo = 0, off_hi = 0;                   // byte offset of row 0
         int len_lo = 0, len_hi = 0;
         uint32_t rev_cj = 0;
-        int rev_cend = -1;
+        int rev_cend = -1, rev_cols = 0;
+        // Columns a reversed sub-problem can need.  Every cell of the reversed matrix that holds the forward score S is
+        // the start of an optimal alignment ending in the forward end cell (that cell is the first one holding S, so
+        // nothing else inside the prefix rectangle reaches S).  Such an alignment consumes n_r <= r_end + 1 rows and
+        // n_c = (diagonal moves) + I columns with  S <= n_r * maxw - go - (I - 1) * ge  for I >= 1 (one gap run is the
+        // cheapest way to spend I column-only moves), hence  n_c <= n_r + 1 + (n_r * maxw - go - S) / ge.  Columns
+        // beyond that cannot hold S, so the sweep stops there: zoe's reverse pass (striped.rs:355-388) sweeps the whole
+        // prefix and finds the same first cell.  ge == 0: no bound.
+        auto rev_bound = [&](const AlignEnd &e) -> int {
+            if (p.ge <= 0) return 0x7fffffff;
+            const long long nr = (long long)e.r_end + 1;
+            const long long num = nr * (long long)wp.rev_maxw - (long long)p.go - (long long)e.best;
+            const long long ic = num >= 0 ? 1 + num / (long long)p.ge : 0;
+            const long long w = nr + ic + 1;
+            return w > 0x7fffffffLL ? 0x7fffffff : (int)w;
+        };
         if (!REV) {
             if (valid) {
                 const uint32_t a = 2 * task, b = 2 * task + 1;
@@ -173,12 +189,14 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
                 rev_cend = (int)e.c_end;
                 off_lo = p.roff[id_lo] + e.r_end;  // row r' reads streamed[r_end - r']
                 len_lo = (int)e.r_end + 1;
+                rev_cols = rev_bound(e);
             }
             if (g_hi != 0xffffffffu) {
                 const AlignEnd e = wp.rev_in[g_hi];
                 id_hi = g_hi / p.n_cseq;
                 off_hi = p.roff[id_hi] + e.r_end;
                 len_hi = (int)e.r_end + 1;
+                rev_cols = max(rev_cols, rev_bound(e));
             }
         }
 
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
             const uint32_t cj = REV ? rev_cj : sweep;
             const uint32_t c0 = p.coff[cj];
             // REV: the groups of a warp sweep different numbers of columns (sorted by end column, so nearly equal)
-            const int L = REV ? rev_cend + 1 : (int)(p.coff[cj + 1] - c0);
+            const int L = REV ? min(rev_cend + 1, rev_cols) : (int)(p.coff[cj + 1] - c0);
             const uint8_t *cs = cc + c0 + (REV ? max(rev_cend, 0) : 0);  // column j reads cs[j] (REV: cs[-j])
             uint32_t *ck = REV ? nullptr : ck_task + wp.ckpt_base[cj] + lig;
 

@@ -1613,6 +1613,7 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
         wr.items = d.win_items.as<uint32_t>();
         wr.n_items = d.win_nitems.as<uint32_t>();
         wr.rev_in = d.ends.as<AlignEnd>();
+        wr.rev_maxw = getenv("ZOE_CUDA_REV_FULL") ? 0x3fffffff / 2048 : std::max(ctx->max_weight, 0);  // env: sweep the whole prefix
         wr.rev_out = d.starts.as<AlignEnd>();
         wr.counters = ctr;
         wr.cb_log2 = ctx->win_cb_log2;
