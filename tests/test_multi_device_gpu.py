@@ -68,3 +68,28 @@ def test_two_devices_sneaky_snake():
     assert snake.sneaky_snake_batch(refs, qs, 0.1) == [O.sneaky_snake(r, q, 0.1) for r, q in zip(refs, qs)]
     assert snake.sneaky_snake_batch(refs[:1], qs[:1], 0.1) == [O.sneaky_snake(refs[0], qs[0], 0.1)]  # fewer pairs than devices
     snake.close()
+
+
+@pytest.mark.skipif("_n_gpus() < 2")
+def test_two_devices_pipelined_score_batch():
+    # sub-batches alternate between the two streams of each GPU: same scores as one device, one shot
+    rng = np.random.default_rng(3)
+    target = synth.random_dna(rng, 150)
+    n = 540_001
+    reads = synth.random_dna(rng, n * 64).reshape(n, 64)
+    own = rng.random(n) < 0.5
+    idx = rng.integers(0, 80, n)[:, None] + np.arange(64)[None, :]
+    reads[own] = target[idx[own]]
+    buf, offs = synth.fixed_len_batch(reads.astype(np.uint8))
+    out = []
+    for nd, env in ((1, "ZOE_CUDA_NO_PIPELINE"), (2, "ZOE_CUDA_PIPELINE")):
+        prof = CudaProfiles.new_with_w256([bytes(target)], W25, -10, -1, n_devices=nd)
+        os.environ[env] = "1"
+        try:
+            out.append((prof.sw_score_arrays(buf, offs), prof.last_stats()))
+        finally:
+            del os.environ[env]
+        prof.close()
+    for x, y in zip(out[0][0], out[1][0]):
+        assert np.array_equal(x, y)
+    assert out[0][1] == out[1][1]

@@ -280,3 +280,41 @@ def test_offsets_need_not_start_at_zero():
     for k in ("score", "status", "ref_start", "ref_end", "query_start", "query_end", "cigar_off"):
         assert np.array_equal(a1[k], a2[k]), k
     prof.close()
+
+
+def test_pipelined_batch_equals_one_shot():
+    """zoe_cuda_sw_score_batch cuts large batches into sub-batches on two streams (copies overlap kernels); outputs and
+    the tier histogram must not depend on it."""
+    rng = np.random.default_rng(77)
+    target = synth.random_dna(rng, 240)
+    n = 300_003
+    reads = synth.random_dna(rng, n * 100).reshape(n, 100)
+    own = rng.random(n) < 0.5
+    starts = rng.integers(0, 140, n)
+    idx = starts[:, None] + np.arange(100)[None, :]
+    reads[own] = target[idx[own]]
+    flip = rng.random(reads.shape) < 0.02
+    reads = np.where(flip, synth.random_dna(rng, reads.size).reshape(reads.shape), reads).astype(np.uint8)
+    buf, offs = synth.fixed_len_batch(reads)
+    prof = CudaProfiles.new_with_w256([bytes(target), bytes(target[:90])], W25, -10, -1)
+    os.environ["ZOE_CUDA_PIPELINE"] = "1"  # force it (the library pipelines only when copies are a visible share)
+    try:
+        a = prof.sw_score_arrays(buf, offs)
+        st_a = prof.last_stats()
+    finally:
+        del os.environ["ZOE_CUDA_PIPELINE"]
+    os.environ["ZOE_CUDA_NO_PIPELINE"] = "1"
+    try:
+        b = prof.sw_score_arrays(buf, offs)
+        st_b = prof.last_stats()
+    finally:
+        del os.environ["ZOE_CUDA_NO_PIPELINE"]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert st_a == st_b and st_a["tier8"] > 1000 and st_a["unmapped"] + st_a["tier8"] + st_a["tier16"] == 2 * n
+    sc = osc(W25)
+    for i in list(range(0, n, 29989)) + [n - 1, n - 2, 75000, 75001, 150000, 150001, 225001]:
+        for j, t in enumerate((target, target[:90])):
+            rc, s_, t_ = O.sw_score_from(bytes(t), bytes(reads[i]), sc)
+            assert (int(a[1][i, j]), int(a[0][i, j]) if rc == 0 else 0) == (rc, s_ if rc == 0 else 0), (i, j)
+    prof.close()

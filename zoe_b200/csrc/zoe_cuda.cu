@@ -136,6 +136,10 @@ constexpr int kMaxRowsSinglePass = 32 * 32;
 
 struct zoe_cuda_ctx {
     std::vector<Device> devs;
+    // One extra stream + buffer set per GPU: zoe_cuda_sw_score_batch alternates sub-batches between devs[k] and alt[k]
+    // so that the H2D copy of sub-batch i+1 and the D2H copy of sub-batch i-1 overlap the kernels of sub-batch i.
+    std::vector<Device> alt;
+    bool alt_used = false;  // the last call spread its work over both
     std::string err;
     // scoring
     bool have_scoring = false;
@@ -427,7 +431,11 @@ int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan
 }
 
 int upload_scoring_and_profiled(zoe_cuda_ctx *ctx) {
-    for (Device &d : ctx->devs) {
+    std::vector<Device *> all;
+    for (Device &d : ctx->devs) all.push_back(&d);
+    for (Device &d : ctx->alt) all.push_back(&d);
+    for (Device *dp : all) {
+        Device &d = *dp;
         CU(ctx, cudaSetDevice(d.id));
         CU(ctx, d.ccodes.reserve(ctx->ccodes.size()));
         CU(ctx, d.coff.reserve(ctx->coff.size() * sizeof(uint32_t)));
@@ -477,7 +485,8 @@ __global__ void rebase_offsets_kernel(uint64_t *off, uint64_t n, uint64_t base) 
     if (i < n) off[i] -= base;
 }
 
-int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n) {
+// Validates a batch, records its global properties (count, longest / shortest sequence, cells) and shards it.
+int prepare_batch(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n) {
     if (!ctx->have_profiled) return fail(ctx, ZOE_CUDA_E_STATE, "set_profiled must be called before a batch");
     if (n > 0 && (!concat || !offsets)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null batch pointers");
     if (n >= 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "batch too large");
@@ -501,33 +510,48 @@ int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *o
         for (uint64_t i = 0; i < n; ++i) ctx->staged_len[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
     }
     ctx->staged_cells = tot * prof_total;
+    ctx->staged = false;
+    ctx->alt_used = false;
     shard(ctx, n);
+    return 0;
+}
+
+// Uploads the sequences [d.n_first, d.n_first + d.n_count) of the batch to `d` (async on d.stream).
+int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint64_t *offsets, bool record_begin = true) {
+    CU(ctx, cudaSetDevice(d.id));
+    if (record_begin) CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+    if (d.n_count == 0) return 0;
+    uint64_t b0 = offsets[d.n_first], b1 = offsets[d.n_first + d.n_count];
+    d.rseq_bytes = b1 - b0;
+    CU(ctx, d.rseq.reserve(d.rseq_bytes + 16));
+    CU(ctx, d.roff.reserve((d.n_count + 1) * sizeof(uint64_t)));
+    if (d.rseq_bytes)
+        CU(ctx, cudaMemcpyAsync(d.rseq.p, concat + b0, d.rseq_bytes, cudaMemcpyHostToDevice, d.stream));
+    // the shard's offsets go up as the caller holds them (one copy straight from the caller's buffer, which
+    // outlives the call) and are rebased to the shard's first byte on the device
+    CU(ctx, cudaMemcpyAsync(d.roff.p, offsets + d.n_first, (d.n_count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                            d.stream));
+    if (b0) {
+        rebase_offsets_kernel<<<(uint32_t)((d.n_count + 256) / 256), 256, 0, d.stream>>>(d.roff.as<uint64_t>(),
+                                                                                         d.n_count + 1, b0);
+        CU(ctx, cudaGetLastError());
+    }
+    size_t pairs = (size_t)d.n_count * ctx->n_prof;
+    CU(ctx, d.best.reserve(pairs * sizeof(int32_t)));
+    CU(ctx, d.score.reserve(pairs * sizeof(uint32_t)));
+    CU(ctx, d.status.reserve(pairs));
+    CU(ctx, d.tier.reserve(pairs));
+    CU(ctx, d.wide_ids.reserve((d.n_count + 1) * sizeof(uint32_t)));
+    CU(ctx, d.counters.reserve(16 * sizeof(unsigned long long)));
+    return 0;
+}
+
+int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n) {
+    int rc = prepare_batch(ctx, concat, offsets, n);
+    if (rc) return rc;
     for (Device &d : ctx->devs) {
-        CU(ctx, cudaSetDevice(d.id));
-        CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
-        if (d.n_count == 0) continue;
-        uint64_t b0 = offsets[d.n_first], b1 = offsets[d.n_first + d.n_count];
-        d.rseq_bytes = b1 - b0;
-        CU(ctx, d.rseq.reserve(d.rseq_bytes + 16));
-        CU(ctx, d.roff.reserve((d.n_count + 1) * sizeof(uint64_t)));
-        if (d.rseq_bytes)
-            CU(ctx, cudaMemcpyAsync(d.rseq.p, concat + b0, d.rseq_bytes, cudaMemcpyHostToDevice, d.stream));
-        // the shard's offsets go up as the caller holds them (one copy straight from the caller's buffer, which
-        // outlives the call) and are rebased to the shard's first byte on the device
-        CU(ctx, cudaMemcpyAsync(d.roff.p, offsets + d.n_first, (d.n_count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
-                                d.stream));
-        if (b0) {
-            rebase_offsets_kernel<<<(uint32_t)((d.n_count + 256) / 256), 256, 0, d.stream>>>(d.roff.as<uint64_t>(),
-                                                                                             d.n_count + 1, b0);
-            CU(ctx, cudaGetLastError());
-        }
-        size_t pairs = (size_t)d.n_count * ctx->n_prof;
-        CU(ctx, d.best.reserve(pairs * sizeof(int32_t)));
-        CU(ctx, d.score.reserve(pairs * sizeof(uint32_t)));
-        CU(ctx, d.status.reserve(pairs));
-        CU(ctx, d.tier.reserve(pairs));
-        CU(ctx, d.wide_ids.reserve((d.n_count + 1) * sizeof(uint32_t)));
-        CU(ctx, d.counters.reserve(16 * sizeof(unsigned long long)));
+        rc = stage_device(ctx, d, concat, offsets);
+        if (rc) return rc;
     }
     ctx->staged = true;
     return 0;
@@ -806,11 +830,11 @@ int run_score_long_on_device(zoe_cuda_ctx *ctx, Device &d) {
 }
 
 // The score pipeline on one device, all asynchronous on d.stream.
-int run_score_on_device(zoe_cuda_ctx *ctx, Device &d) {
+int run_score_on_device(zoe_cuda_ctx *ctx, Device &d, bool reset_counters = true) {
     if (d.n_count == 0) return 0;
     CU(ctx, cudaSetDevice(d.id));
     size_t pairs = (size_t)d.n_count * ctx->n_prof;
-    CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
+    if (reset_counters) CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
     if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass) {
         int rc = run_score_long_on_device(ctx, d);
         if (rc) return rc;
@@ -1778,7 +1802,12 @@ int for_each_device(zoe_cuda_ctx *ctx, Fn fn) {
 
 int sync_and_time(zoe_cuda_ctx *ctx) {
     float total = 0.f, dp = 0.f;
-    for (Device &d : ctx->devs) {
+    std::vector<Device *> all;
+    for (Device &d : ctx->devs) all.push_back(&d);
+    if (ctx->alt_used)
+        for (Device &d : ctx->alt) all.push_back(&d);
+    for (Device *dp_ : all) {
+        Device &d = *dp_;
         CU(ctx, cudaSetDevice(d.id));
         CU(ctx, cudaEventRecord(d.ev_end, d.stream));
         CU(ctx, cudaStreamSynchronize(d.stream));
@@ -1796,8 +1825,13 @@ int sync_and_time(zoe_cuda_ctx *ctx) {
 }
 
 int gather_stats(zoe_cuda_ctx *ctx) {
-    for (Device &d : ctx->devs) {
-        if (d.n_count == 0) continue;
+    std::vector<Device *> all;
+    for (Device &d : ctx->devs) all.push_back(&d);
+    if (ctx->alt_used)
+        for (Device &d : ctx->alt) all.push_back(&d);
+    for (Device *dp_ : all) {
+        Device &d = *dp_;
+        if (d.n_count == 0 || !d.counters.p) continue;
         CU(ctx, cudaSetDevice(d.id));
         unsigned long long c[16];
         CU(ctx, cudaMemcpy(c, d.counters.p, sizeof(c), cudaMemcpyDeviceToHost));
@@ -1817,6 +1851,7 @@ void begin_call(zoe_cuda_ctx *ctx) {
     ctx->last_dp_ms = 0.f;
     ctx->stats = zoe_cuda_stats{};
     for (Device &d : ctx->devs) d.timed_kernel = false;
+    for (Device &d : ctx->alt) d.timed_kernel = false;
 }
 
 // Copies the per-pair alignment outputs and the compacted CIGAR stream of every device into the caller's arrays
@@ -1893,6 +1928,17 @@ int zoe_cuda_create(zoe_cuda_ctx **out, const int *device_ids, int n_devices) {
             return ZOE_CUDA_E_CUDA;
         }
         ctx->devs.push_back(d);
+        Device l;  // second stream + buffer set on the same GPU (score-batch pipelining)
+        l.id = d.id;
+        l.sm_count = d.sm_count;
+        l.free_at_create = d.free_at_create;
+        if (cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreate(&l.ev_begin) != cudaSuccess || cudaEventCreate(&l.ev_end) != cudaSuccess ||
+            cudaEventCreate(&l.ev_k0) != cudaSuccess || cudaEventCreate(&l.ev_k1) != cudaSuccess) {
+            delete ctx;
+            return ZOE_CUDA_E_CUDA;
+        }
+        ctx->alt.push_back(l);
     }
     *out = ctx;
     return 0;
@@ -1900,7 +1946,11 @@ int zoe_cuda_create(zoe_cuda_ctx **out, const int *device_ids, int n_devices) {
 
 void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
     if (!ctx) return;
-    for (Device &d : ctx->devs) {
+    std::vector<Device *> all;
+    for (Device &d : ctx->devs) all.push_back(&d);
+    for (Device &d : ctx->alt) all.push_back(&d);
+    for (Device *dp : all) {
+        Device &d = *dp;
         cudaSetDevice(d.id);
         for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.corder, &d.ccodes_g, &d.coff_g, &d.corder_g, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
@@ -2134,21 +2184,78 @@ int zoe_cuda_sw_score_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
                             uint32_t *score, uint8_t *status, uint8_t *tier) {
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     begin_call(ctx);
-    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    int rc = prepare_batch(ctx, streamed_concat, offsets, n);
     if (rc) return rc;
-    for (Device &d : ctx->devs) {
-        rc = run_score_on_device(ctx, d);
-        if (rc) return rc;
-    }
-    // D2H is queued behind the kernels on each device's stream; devices overlap with each other.
-    for (Device &d : ctx->devs) {
-        if (d.n_count == 0) continue;
+    auto d2h = [&](Device &d) -> int {  // queued behind the kernels on the device's stream
+        if (d.n_count == 0) return 0;
         CU(ctx, cudaSetDevice(d.id));
         size_t first = (size_t)d.n_first * ctx->n_prof, pairs = (size_t)d.n_count * ctx->n_prof;
         if (score)
             CU(ctx, cudaMemcpyAsync(score + first, d.score.p, pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.stream));
         if (status) CU(ctx, cudaMemcpyAsync(status + first, d.status.p, pairs, cudaMemcpyDeviceToHost, d.stream));
         if (tier) CU(ctx, cudaMemcpyAsync(tier + first, d.tier.p, pairs, cudaMemcpyDeviceToHost, d.stream));
+        return 0;
+    };
+    // Large batches are cut into sub-batches that alternate between the two streams of a GPU, so the H2D copy of the
+    // next sub-batch and the D2H copy of the previous one overlap the kernels of the current one.  Not for the long-row
+    // path (its copies are negligible next to its kernels) nor when packed lanes may overflow (the 32-bit re-run
+    // synchronises with the host).
+    constexpr int kSub = 4;
+    const uint64_t bound = (uint64_t)std::min<uint32_t>(ctx->staged_max_len, ctx->max_prof_len) * (uint64_t)std::max(ctx->max_weight, 0);
+    const uint64_t per_dev = n / std::max<size_t>(ctx->devs.size(), 1);
+    // worth it only when the copies are a visible share of the step: each sub-batch is its own launch with its own
+    // tail (cfg 2: copies 3 % of the step, one shot is faster; cfg 5: 40 %, pipelining gains 7 %)
+    const double copy_s = ((double)(n ? offsets[n] - offsets[0] : 0) + (double)n * 8.0 + (double)n * ctx->n_prof * 6.0) / 25e9;
+    const double kernel_s = (double)ctx->staged_cells / 6e12;
+    const bool pipeline = per_dev >= (uint64_t)kSub * 65536 && ctx->staged_max_len <= (uint32_t)kMaxRowsSinglePass &&
+                          bound < (uint64_t)(kPackedLimit - std::max(ctx->max_weight, 0) - 1) &&
+                          (copy_s > 0.1 * kernel_s || getenv("ZOE_CUDA_PIPELINE")) && !getenv("ZOE_CUDA_NO_PIPELINE");
+    if (!pipeline) {
+        for (Device &d : ctx->devs) {
+            rc = stage_device(ctx, d, streamed_concat, offsets);
+            if (rc) return rc;
+        }
+        for (Device &d : ctx->devs) {
+            rc = run_score_on_device(ctx, d);
+            if (rc) return rc;
+        }
+        for (Device &d : ctx->devs) {
+            rc = d2h(d);
+            if (rc) return rc;
+        }
+        ctx->staged = true;
+    } else {
+        const size_t nd = ctx->devs.size();
+        std::vector<uint64_t> first(nd), count(nd);
+        for (size_t k = 0; k < nd; ++k) {
+            first[k] = ctx->devs[k].n_first;
+            count[k] = ctx->devs[k].n_count;
+        }
+        ctx->alt_used = true;
+        for (int i = 0; i < kSub; ++i) {
+            for (size_t k = 0; k < nd; ++k) {
+                Device &lane = (i & 1) ? ctx->alt[k] : ctx->devs[k];
+                // an even first index keeps the packed pairs (sequences 2t, 2t+1) of the one-shot run
+                const uint64_t lo = (count[k] * i / kSub) & ~1ull, hi = i + 1 == kSub ? count[k] : ((count[k] * (i + 1) / kSub) & ~1ull);
+                lane.n_first = first[k] + lo;
+                lane.n_count = hi - lo;
+                rc = stage_device(ctx, lane, streamed_concat, offsets, /*record_begin=*/i < 2);
+                if (rc) return rc;
+                rc = run_score_on_device(ctx, lane, /*reset_counters=*/i < 2);
+                if (rc) return rc;
+            }
+            if (i > 0)
+                for (size_t k = 0; k < nd; ++k) {
+                    rc = d2h(((i - 1) & 1) ? ctx->alt[k] : ctx->devs[k]);
+                    if (rc) return rc;
+                }
+        }
+        for (size_t k = 0; k < nd; ++k) {
+            rc = d2h(((kSub - 1) & 1) ? ctx->alt[k] : ctx->devs[k]);
+            if (rc) return rc;
+        }
+        // the device buffers now hold sub-batches only: nothing is "staged" for the run_*_staged entry points
+        ctx->staged = false;
     }
     rc = sync_and_time(ctx);
     if (rc) return rc;
