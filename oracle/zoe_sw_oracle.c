@@ -13,6 +13,12 @@
  * i32 tier have no known-answer test in zoe: for those the pin is
  * striped == scalar agreement only.
  *
+ * The banded alignment / 3-pass restatement (banded.rs, three_pass.rs) and the
+ * SneakySnake filter at the end of this file are pinned by zoe only on one
+ * score each (10, 26) and one doc-test (Some(true)): their CIGAR tie-breaks and
+ * Some(false) cases are parity-unpinned beyond the property tests in
+ * tests/test_oracle_3pass.py and tests/test_sneaky_snake.py.
+ *
  * Each function cites the reference file:line it follows (paths relative to
  * the zoe repository root).
  *
