@@ -131,6 +131,10 @@ const KernelEntry kScoreKernels[] = {
 };
 constexpr int kNumScoreKernels = sizeof(kScoreKernels) / sizeof(kScoreKernels[0]);
 constexpr int kMaxRowsSinglePass = 32 * 32;
+// Pass A of the windowed pipeline (sw_align_scan_kernel) keeps step-pair indices in 16-bit halves: L + G - 1 <= 131071.
+// Longer profiled sequences take the full-matrix align pipeline / sw_ends_kernel, whose keys hold 20-bit columns.
+constexpr uint32_t kScanMaxCols = 131072 - 64;
+constexpr uint32_t kEndsMaxCols = (1u << 20) - 64;
 
 }  // namespace
 
@@ -978,7 +982,9 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     const uint32_t CB = 1u << cb_log2;
     // window capacity in columns: the walk's reach + the distance to the previous checkpoint + the lane skew
     const uint32_t wmax = std::min<uint32_t>(ctx->max_prof_len, std::max<uint32_t>(ctx->staged_max_len, 1) + ctx->win_slack + CB) + k->G;
-    const bool window_ok = ctx->go != 0;
+    if (ctx->max_prof_len > kEndsMaxCols)
+        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "profiled sequences longer than %u are not supported by the align path", kEndsMaxCols);
+    const bool window_ok = ctx->go != 0 && ctx->max_prof_len <= kScanMaxCols;
     bool use_window = window_ok && (uint64_t)ctx->max_prof_len >= 2ull * wmax;
     if (ctx->align_mode == 1) use_window = false;
     if (ctx->align_mode == 2) use_window = window_ok;
@@ -1429,6 +1435,9 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
     if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass)
         return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "streamed sequences longer than %d are not supported by the ranges path yet",
                     kMaxRowsSinglePass);
+    if (ctx->max_prof_len > kEndsMaxCols)
+        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "profiled sequences longer than %u are not supported by the ranges path", kEndsMaxCols);
+    const bool scan_ok = ctx->max_prof_len <= kScanMaxCols && !getenv("ZOE_CUDA_RANGES_SLOW");
     const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
     if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
     const uint32_t n_prof = ctx->n_prof;
@@ -1488,7 +1497,7 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
     const uint32_t gpb = plan.threads / k->G;
     const uint32_t max_blocks = (uint32_t)(d.sm_count * plan.blocks_per_sm);
     CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
-    if (packed && !getenv("ZOE_CUDA_RANGES_SLOW")) {
+    if (packed && scan_ok) {
         // ---- forward pass, fast: the align pipeline's pass A (score-rate scan + checkpoints) followed by a pin sweep
         //      of every mapped pair from the checkpoint before its first best column pair (about CB/2 columns) ----
         int cb_log2 = ctx->win_cb_log2;
@@ -1621,7 +1630,7 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
 
     const uint64_t max_tasks = packed ? max_items / 2 : max_items;
     LaunchPlan plan_r;
-    bool fast_rev = packed && !getenv("ZOE_CUDA_RANGES_SLOW");
+    bool fast_rev = packed && scan_ok;
     if (fast_rev) {
         int rc2 = plan_launch(ctx, *k, k->scan_rev, &plan_r);
         if (rc2) return rc2;
