@@ -31,9 +31,9 @@ while time.time() < t_end:
     rand_seq = lambda L: rng.choice(alpha, L).astype(np.uint8)  # noqa: E731
     lanes = [(16, 8, 4), (32, 16, 8), (64, 32, 16)][int(rng.integers(0, 3))]
     pq = bool(rng.integers(0, 2))
-    max_t = int(rng.choice([60, 300, 1500]))
+    max_t = int(rng.choice([60, 300, 1500, 1500, 30000]))
     max_r = int(rng.choice([40, 150, 400, 1024]))
-    targets = [rand_seq(int(rng.integers(1, max_t + 1))) for _ in range(int(rng.integers(1, 4)))]
+    targets = [rand_seq(int(rng.integers(1, max_t + 1))) for _ in range(int(rng.integers(1, 7 if max_t < 30000 else 5)))]
     seqs = []
     for _ in range(int(rng.integers(20, 60))):
         L = int(rng.integers(0 if rng.random() < 0.05 else 1, max_r + 1))
