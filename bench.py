@@ -11,6 +11,9 @@ its own 1M-read shard, no collective on the data path ("weak": per-GPU work is f
 `value`  = GCUPS with the batch already resident in HBM (CUDA events on the library's stream).
 `e2e`    = GCUPS through the host-buffer C-ABI call (pinned host -> device copies and the
            device -> host result copies inside the timed region).
+`--config 1..5` selects another BASELINE.json configuration (3 = align with device traceback and CIGARs, 4 = long
+reads, 5 = protein); `--mode score|align|ranges|3pass` overrides the entry point (ranges = sw_score_ranges, 3pass =
+sw_align_from_i8_3pass).
 `--impl reference` times the CPU restatement of zoe's striped path (oracle/zoe_sw_cpu.cpp) on all
 host threads; zoe itself (Rust nightly) cannot be built in this image.
 """
