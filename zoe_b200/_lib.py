@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzoe_cuda.so")
+LIB_PATH = os.environ.get("ZOE_CUDA_LIB") or os.path.join(HERE, "libzoe_cuda.so")  # env: another build (A/B timing)
 
 SOME, OVERFLOWED, UNMAPPED = 0, 1, 2
 E_EMPTY_SEQUENCE, E_GAP_OPEN_RANGE, E_GAP_EXTEND_RANGE, E_BAD_GAP_WEIGHTS = -1, -2, -3, -4

@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
     uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
     const uint32_t cb_mask = (1u << wp.cb_log2) - 1u;
     const bool lane0 = lig == 0;  // lane 0 receives zeros from "above"
+    uint32_t nz_lane = lane0 ? 0u : 1u;
+    asm volatile("" : "+r"(nz_lane));
     const uint32_t one_s = O::splat(1);
     // loop invariants the compiler would otherwise rematerialise inside the hot loop (S2R + address arithmetic);
     // the table offset stays a 32-bit offset into the shared array so the loads remain LDS.128
@@ -223,14 +225,20 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
             // step pair (s >> 1) in which this lane's column maximum reached it
             uint32_t bestp = 0, firstp = 0, lastp = 0;
             uint32_t cm = 0;               // maximum of the column(s) since the last bookkeeping
+            uint32_t hp_pend = 0;          // odd K, steady loop: last row of an even step, folded in by the next step
             const int nsteps = REV ? __reduce_max_sync(FULL, L > 0 ? L + G - 1 : 0) : L + G - 1;
             const int L_steady = REV ? __reduce_min_sync(FULL, L) : L;  // every lane of every group has a column below it
 
             // one column of this lane: K rows, H read from set PO (column j-1), written to set PN
-            auto column = [&](auto parity, const int j, const uint32_t h_in, const uint32_t e_in) {
+            // STEADY (the two-step steady loop only): with an odd K the column's last row is not folded into the column
+            // maximum by an extra VIMNMX; it stays pending in `hp_pend` and pairs up with row 0 of the next (odd) step,
+            // so two steps fold their 2K values with exactly K VIMNMX3.
+            auto column = [&](auto parity, auto steady, const int j, const uint32_t h_in, const uint32_t e_in) {
                 constexpr int PO = decltype(parity)::value, PN = 1 - PO;
+                constexpr bool STEADY = decltype(steady)::value;
+                constexpr int PH = (STEADY && (K & 1)) ? PO : 0;  // pairing phase of this column
                 const uint4 *tp = reinterpret_cast<const uint4 *>(smem + tab_lane_off + (uint32_t)cs[REV ? -j : j] * (uint32_t)(K4 * G * 16));
-                uint32_t diag = h_up_prev, E = e_in, hp = 0;
+                uint32_t diag = h_up_prev, E = e_in, hp = hp_pend;
 #pragma unroll
                 for (int i4 = 0; i4 < K4; ++i4) {
                     const uint4 w4 = tp[i4 * G];
@@ -245,17 +253,24 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
                             E = O::addmax(E, neg_ge, Hn);
                             F[i] = O::addmax(F[i], neg_ge, Hn);
                             H[PN][i] = Hn;
-                            if (i & 1)
+                            if ((i + PH) & 1)
                                 cm = O::max3(cm, Hn, hp);
                             else
                                 hp = Hn;
                         }
                     }
                 }
-                if (K & 1) cm = O::max2(cm, hp);
+                if (K & 1) {
+                    if (!STEADY)
+                        cm = O::max2(cm, hp);
+                    else if (PH == 0)
+                        hp_pend = hp;
+                }
                 h_last = H[PN][K - 1];
                 e_out = E;
             };
+            using SteadyT = std::true_type;
+            using GenericT = std::false_type;
             using I0 = std::integral_constant<int, 0>;
             using I1 = std::integral_constant<int, 1>;
             // m - bestp and m - cm are >= 0 in both halves, so the plain 32-bit subtractions are exact (FMA pipe);
@@ -275,7 +290,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
                 const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
                 const int j = s - lig;
                 if (j >= 0 && j < L) {
-                    column(parity, j, h_in, e_in);
+                    column(parity, GenericT{}, j, h_in, e_in);
                     bookkeeping((uint32_t)s & ~1u);
                 }
                 h_up_prev = h_in;
@@ -302,16 +317,16 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
             }
             for (; s + 1 < L_steady; s += 2) {  // steps s and s+1: every lane has a column
                 if (!REV && (((uint32_t)s) & cb_mask) == 0 && valid) checkpoint(s);
-                {
-                    const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1, G), h_in = lane0 ? 0u : h_sh;
-                    const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
-                    column(I0{}, s - lig, h_in, e_in);
+                {   // lane 0 receives zeros from "above": a multiply on the FMA pipe, not a SEL on the ALU pipe
+                    const uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G) * nz_lane;
+                    const uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G) * nz_lane;
+                    column(I0{}, SteadyT{}, s - lig, h_in, e_in);
                     h_up_prev = h_in;
                 }
                 {
-                    const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1, G), h_in = lane0 ? 0u : h_sh;
-                    const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
-                    column(I1{}, s + 1 - lig, h_in, e_in);
+                    const uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G) * nz_lane;
+                    const uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G) * nz_lane;
+                    column(I1{}, SteadyT{}, s + 1 - lig, h_in, e_in);
                     h_up_prev = h_in;
                 }
                 bookkeeping((uint32_t)s);
@@ -357,7 +372,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
                     const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
                     const int j = st - lig;
                     if (j >= 0 && j < L) {
-                        column(parity, j, h_in, e_in);
+                        column(parity, GenericT{}, j, h_in, e_in);
                         if (lig == wl_lo && st >= fs_lo && st <= se_lo) {
                             int irow = K;
 #pragma unroll
