@@ -50,7 +50,17 @@ while time.time() < t_end:
     tb = [bytes(t) for t in targets]
     sb = [bytes(s) for s in seqs]
     sc = O.Scoring(wm.weights, wm.mapping.index_map, go, ge)
+    # which integer types may answer: the from_i8 / _i16 / _i32 chains, or one standalone StripedProfile<T, N, S>
+    policy = [None, None, None, (16, 32, False), (32, 32, False), (8, 8, False), (8, 8, True), (16, 16, False),
+              (16, 16, True)][int(rng.integers(0, 9))]
+    standalone = policy is not None and policy[0] == policy[1]
+    first_bits = policy[0] if policy else 8
+    if standalone:
+        n_lanes = lanes[{8: 0, 16: 1, 32: 2}[policy[0]]]
+        lanes = (n_lanes, n_lanes, n_lanes)
     prof = CudaProfiles(tb, wm, go, ge, lanes=lanes, profiled_is_query=pq)
+    if policy:
+        prof.set_width_policy(*policy)
     src = SeqSrc.Reference(sb) if pq else SeqSrc.Query(sb)
     g_score = prof.sw_score_batch(sb)
     g_align = prof.sw_align_batch(src)
@@ -61,22 +71,32 @@ while time.time() < t_end:
     def check(ij):
         i, j = ij
         t, s = tb[j], sb[i]
-        rc, score, _tier = O.sw_score_from(t, s, sc, lanes=lanes)
+        if standalone:
+            bits, signed, nl, inv = policy[0], not policy[2], lanes[0], not pq
+            rc, score = O.striped_score(t, s, sc, bits, nl, signed=signed)
+            r_al = O.striped_align(t, s, sc, bits, nl, signed=signed, streamed_is_query=inv)
+            r_rg = O.striped_score_ranges(t, s, sc, bits, nl, signed=signed, streamed_is_query=inv)
+            r_3p = O.striped_align_3pass(t, s, sc, bits, nl, signed=signed, streamed_is_query=inv)[:2]
+        else:
+            rc, score, _tier = O.sw_score_from(t, s, sc, lanes=lanes, first_bits=first_bits)
+            r_al = O.sw_align_from(t, s, sc, lanes=lanes, first_bits=first_bits, streamed_is_query=not pq)[:2]
+            r_rg = O.sw_score_ranges_from(t, s, sc, lanes=lanes, first_bits=first_bits, streamed_is_query=not pq)[:4]
+            r_3p = O.sw_align_3pass_from(t, s, sc, lanes=lanes, first_bits=first_bits, streamed_is_query=not pq)[:2]
         g = g_score[i][j]
         assert g.status.value == rc and (rc != 0 or g.unwrap() == score), ("score", i, j, g, rc, score)
-        rc, aln, _ = O.sw_align_from(t, s, sc, lanes=lanes, streamed_is_query=not pq)
+        rc, aln = r_al
         g = g_align[i][j]
         assert g.status.value == rc, ("align", i, j, g, rc)
         if rc == 0:
             a = g.unwrap()
             assert (a.score, a.ref_range, a.query_range, a.states) == (aln.score, aln.ref_range, aln.query_range, aln.cigar), ("align", i, j, a, aln)
-        rc, score, rr, qr, _ = O.sw_score_ranges_from(t, s, sc, lanes=lanes, streamed_is_query=not pq)
+        rc, score, rr, qr = r_rg
         g = g_rng[i][j]
         assert g.status.value == rc, ("ranges", i, j, g, rc)
         if rc == 0:
             a = g.unwrap()
             assert (a.score, a.ref_range, a.query_range) == (score, rr, qr), ("ranges", i, j, a, score, rr, qr)
-        rc, aln, _, _ = O.sw_align_3pass_from(t, s, sc, lanes=lanes, streamed_is_query=not pq)
+        rc, aln = r_3p
         g = g_3p[i][j]
         assert g.status.value == rc, ("3pass", i, j, g, rc)
         if rc == 0:
@@ -92,6 +112,6 @@ while time.time() < t_end:
         print(repr(e.args[0])[:2000])
         sys.exit(1)
     cases += 1
-    print(f"case {cases}: {'BLOSUM62' if protein else 'DNA'} ({ma},{mi},{go},{ge}) lanes {lanes} pq {pq} targets {[len(t) for t in tb]} reads {len(sb)} max {max(len(s) for s in sb)} ok",
+    print(f"case {cases}: {'BLOSUM62' if protein else 'DNA'} ({ma},{mi},{go},{ge}) lanes {lanes} policy {policy} pq {pq} targets {[len(t) for t in tb]} reads {len(sb)} max {max(len(s) for s in sb)} ok",
           flush=True)
 print(f"soak ok: {cases} cases, {pairs_checked} pairs x 4 entry points, seed {seed}")
