@@ -1750,7 +1750,7 @@ int run_3pass_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         if (work[0] > 0) {
             CU(ctx, d.tp_blob.reserve(work[1] + 16));
             t.blob = d.tp_blob.as<uint8_t>();
-            tp_dp_kernel<<<(uint32_t)((work[0] + 63) / 64), 64, 0, d.stream>>>(t, (uint32_t)work[0]);
+            tp_dp_kernel<<<(uint32_t)((work[0] + kTpThreads - 1) / kTpThreads), kTpThreads, 0, d.stream>>>(t, (uint32_t)work[0]);
             CU(ctx, cudaGetLastError());
             ctx->last_launches++;
         }
