@@ -43,3 +43,10 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 src = open(os.path.join(root, f), errors="replace").read()
                 assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+def test_rust_sys_crate_binds_every_declared_symbol():
+    # the -sys crate cannot be compiled here (no rustc): at least keep its extern block in step with the header
+    text = open(os.path.join(ROOT, "rust", "zoe-cuda-sys", "src", "lib.rs")).read()
+    bound = sorted(set(re.findall(r"pub fn (zoe_cuda_[a-z0-9_]+)", text)))
+    assert bound == declared_symbols()
