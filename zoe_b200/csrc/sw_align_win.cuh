@@ -455,6 +455,7 @@ struct ClassifyParams {
     int K;
     int cb_log2;
     uint32_t slack, nblk;
+    int maxw, go, ge;              // largest weight and the (positive) gap penalties: bound the walk's column-only moves
     int all_exact;
     uint32_t *hist;
     int pin_stage;                 // 1: select the ambiguous pairs for the pin sweep; 2: every mapped pair (ranges);
@@ -537,7 +538,17 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
     }
     uint32_t r_hi, c_hi;
     end_bounds(e.r_end, e.c_end, t.K, n, t.coff[cj + 1] - t.coff[cj], r_hi, c_hi);
-    const uint32_t ws = win_start(r_hi, c_hi, t.slack, t.cb_log2);
+    // The walk follows one alignment of score S over n_r <= r_hi + 1 rows; its column-only moves I satisfy
+    // S <= n_r * maxw - go - (I - 1) * ge (one gap run is the cheapest way to spend them), so I + 1 columns of slack are
+    // enough whenever that is less than the configured slack (a mapped 150-nt read: 2 instead of 16).  Were the bound
+    // ever too tight the walk would reach the window's left edge and the pair would go to the literal kernel.
+    uint32_t slack = t.slack;
+    if (t.ge > 0) {
+        const long long num = (long long)(r_hi + 1) * t.maxw - t.go - (long long)e.best;
+        const long long imax = num >= 0 ? 1 + num / t.ge : 0;
+        if (imax + 1 < (long long)slack) slack = (uint32_t)(imax + 1);
+    }
+    const uint32_t ws = win_start(r_hi, c_hi, slack, t.cb_log2);
     t.ends[gid].aux = ws;
     atomicAdd(&t.hist[cj * t.nblk + (ws >> t.cb_log2)], 1u);
 }

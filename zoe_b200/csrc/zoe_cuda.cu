@@ -1257,6 +1257,9 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             cp.K = k->K;
             cp.cb_log2 = cb_log2;
             cp.slack = ctx->win_slack;
+            cp.maxw = std::max(ctx->max_weight, 0);
+            cp.go = ctx->go;
+            cp.ge = ctx->ge;
             cp.nblk = nblk;
             cp.all_exact = all_exact ? 1 : 0;
             cp.tp = ctx->tp;
@@ -1571,6 +1574,9 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
             cp.K = k->K;
             cp.cb_log2 = cb_log2;
             cp.slack = ctx->win_slack;
+            cp.maxw = std::max(ctx->max_weight, 0);
+            cp.go = ctx->go;
+            cp.ge = ctx->ge;
             cp.nblk = nblk;
             cp.all_exact = 0;
             cp.tp = ctx->tp;
