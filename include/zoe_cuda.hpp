@@ -16,6 +16,7 @@
 #pragma once
 #include <cstdint>
 #include <stdexcept>
+#include <optional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -63,6 +64,12 @@ struct Alignment {
         for (const Ciglet &c : states) s += std::to_string(c.inc) + c.op;
         return s;
     }
+};
+
+// zoe's ScoreAndRanges<u32> (src/alignment/types/output.rs): score + 0-based half-open ranges
+struct ScoreAndRanges {
+    uint32_t score = 0;
+    std::pair<uint32_t, uint32_t> ref_range{0, 0}, query_range{0, 0};
 };
 
 enum class SeqSrc { Query, Reference };
@@ -125,6 +132,27 @@ class CudaProfiles {
     // Tuning only (never changes results): 0 auto, 1 full-matrix direction bits, 2 checkpointed window.
     void set_align_options(int mode, int checkpoint_log2 = 6, int slack = 16) {
         check(zoe_cuda_set_align_options(ctx_, mode, checkpoint_log2, slack));
+    }
+
+    // Upper bound on the device scratch of one align / ranges / 3-pass call (0 = automatic); results never depend on it.
+    void set_memory_budget(uint64_t scratch_bytes) { check(zoe_cuda_set_memory_budget(ctx_, scratch_bytes)); }
+
+    // out[i * n_profiled + j] == profiles[j].sw_score_ranges_from_i8(SeqSrc::X(&seqs[i])) (profile_set.rs:313-322)
+    std::vector<MaybeAligned<ScoreAndRanges>> sw_score_ranges_batch(const std::vector<std::string> &seqs) {
+        std::vector<uint8_t> buf;
+        std::vector<uint64_t> off;
+        pack(seqs, buf, off);
+        size_t pairs = seqs.size() * targets_.size();
+        std::vector<uint32_t> score(pairs + 1), rs(pairs + 1), re(pairs + 1), qs(pairs + 1), qe(pairs + 1);
+        std::vector<uint8_t> status(pairs + 1), tier(pairs + 1);
+        check(zoe_cuda_sw_score_ranges_batch(ctx_, buf.data(), off.data(), seqs.size(), score.data(), status.data(),
+                                             tier.data(), rs.data(), re.data(), qs.data(), qe.data()));
+        std::vector<MaybeAligned<ScoreAndRanges>> out(pairs);
+        for (size_t k = 0; k < pairs; ++k) {
+            out[k].status = static_cast<Status>(status[k]);
+            if (out[k].is_some()) out[k].value = ScoreAndRanges{score[k], {rs[k], re[k]}, {qs[k], qe[k]}};
+        }
+        return out;
     }
 
     std::vector<MaybeAligned<uint32_t>> sw_score_batch(const std::vector<std::string> &seqs) {
@@ -232,6 +260,37 @@ class CudaProfiles {
     std::vector<std::string> targets_;
     SeqSrc streamed_are_;
 };
+
+// sneaky_snake(reference, query, threshold) -> Option<bool> (src/alignment/sneaky_snake.rs:78-131) for pair i =
+// (references[i], queries[i]); std::nullopt = zoe's None.
+inline std::vector<std::optional<bool>> sneaky_snake_batch(const std::vector<std::string> &references,
+                                                           const std::vector<std::string> &queries, float threshold,
+                                                           int n_devices = 1) {
+    if (references.size() != queries.size()) throw std::invalid_argument("references and queries must pair up");
+    zoe_cuda_ctx *ctx = nullptr;
+    int rc = zoe_cuda_create(&ctx, nullptr, n_devices);
+    if (rc) throw CudaError(rc, "zoe_cuda_create failed (no usable CUDA device; there is no CPU fallback)");
+    auto pack = [](const std::vector<std::string> &v, std::vector<uint8_t> &buf, std::vector<uint64_t> &off) {
+        off.assign(1, 0);
+        for (const std::string &x : v) {
+            buf.insert(buf.end(), x.begin(), x.end());
+            off.push_back(buf.size());
+        }
+        if (buf.empty()) buf.push_back(0);
+    };
+    std::vector<uint8_t> rb, qb, out(references.size() + 1);
+    std::vector<uint64_t> ro, qo;
+    pack(references, rb, ro);
+    pack(queries, qb, qo);
+    rc = zoe_cuda_sneaky_snake_batch(ctx, rb.data(), ro.data(), qb.data(), qo.data(), references.size(), threshold, out.data());
+    std::string msg = rc ? zoe_cuda_last_error(ctx) : "";
+    zoe_cuda_destroy(ctx);
+    if (rc) throw CudaError(rc, msg);
+    std::vector<std::optional<bool>> res(references.size());
+    for (size_t i = 0; i < res.size(); ++i)
+        if (out[i] != ZOE_CUDA_SNAKE_NONE) res[i] = out[i] == ZOE_CUDA_SNAKE_TRUE;
+    return res;
+}
 
 }  // namespace cuda
 }  // namespace zoe

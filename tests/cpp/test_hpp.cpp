@@ -36,6 +36,14 @@ int main() {
     auto a3 = prof.sw_align_3pass_batch({"ATGCATCGATCGATCGATCGATCGATCGATGC", "GGCCACAGGATTGAG"});
     CHECK(a3[0].unwrap().score == 26 && a3[0].unwrap().ref_range.first == 14 && a3[0].unwrap().ref_range.second == 31);
     CHECK(a3[3].unwrap().score == 27 && a3[3].unwrap().cigar() == "5M1D4M");
+    // doc profile_set.rs:293-310: sw_score_ranges_from_i8 -> score 26, query 0..15, ref 14..31
+    auto r = prof.sw_score_ranges_batch({"ATGCATCGATCGATCGATCGATCGATCGATGC"});
+    CHECK(r[0].unwrap().score == 26 && r[0].unwrap().query_range.second == 15 && r[0].unwrap().ref_range.first == 14);
+    prof.set_memory_budget(1 << 20);
+    CHECK(prof.sw_align_batch({"ATGCATCGATCGATCGATCGATCGATCGATGC"})[0].unwrap().cigar() == "6M2D9M3S");
+    // doc sneaky_snake.rs:54-62
+    auto sn = sneaky_snake_batch({"GGTGCAGAGCTC", "AAAA"}, {"GGTGAGAGTTGT", "AAAAAAAA"}, 0.25f);
+    CHECK(sn[0].has_value() && *sn[0] == true && !sn[1].has_value());
     // sw/test.rs:81-84 and an Unmapped pair
     auto w25 = WeightMatrix::new_dna_matrix(2, -5);
     auto p2 = CudaProfiles::new_with_w256({std::string(100, 'A')}, w25, -10, -1);
