@@ -188,6 +188,12 @@ impl CudaProfiles {
         self.check(unsafe { sys::zoe_cuda_set_align_options(self.ctx, mode, checkpoint_log2, slack) }, 0, 0)
     }
 
+    /// Upper bound on the device scratch of one align / ranges / 3-pass call (0 = automatic): larger batches are
+    /// processed in chunks of streamed sequences.  Never changes results.
+    pub fn set_memory_budget(&self, scratch_bytes: u64) -> Result<(), CudaError> {
+        self.check(unsafe { sys::zoe_cuda_set_memory_budget(self.ctx, scratch_bytes) }, 0, 0)
+    }
+
     /// The SeqSrc this context's batches correspond to (alignment/mod.rs:157-162).
     pub fn seq_src<'a>(&self, seq: &'a [u8]) -> SeqSrc<&'a [u8]> {
         if self.profiled_is_query { SeqSrc::Reference(seq) } else { SeqSrc::Query(seq) }
@@ -212,6 +218,30 @@ impl Drop for CudaProfiles {
     fn drop(&mut self) {
         unsafe { sys::zoe_cuda_destroy(self.ctx) }
     }
+}
+
+/// `out[i] == zoe::alignment::sneaky_snake(references[i], queries[i], threshold)`
+/// (src/alignment/sneaky_snake.rs:78-131) on the given devices.
+pub fn sneaky_snake_batch(references: &[&[u8]], queries: &[&[u8]], threshold: f32, devices: &[i32]) -> Result<Vec<Option<bool>>, CudaError> {
+    assert_eq!(references.len(), queries.len(), "references and queries must pair up");
+    let mut ctx = std::ptr::null_mut();
+    let rc = unsafe { sys::zoe_cuda_create(&mut ctx, devices.as_ptr(), devices.len() as i32) };
+    if rc != 0 {
+        return Err(CudaError::Cuda { code: rc, message: "no usable CUDA device".into() });
+    }
+    let (rb, ro) = pack(references);
+    let (qb, qo) = pack(queries);
+    let mut out = vec![0u8; references.len().max(1)];
+    let rc = unsafe {
+        sys::zoe_cuda_sneaky_snake_batch(ctx, rb.as_ptr(), ro.as_ptr(), qb.as_ptr(), qo.as_ptr(), references.len() as u64,
+                                         threshold, out.as_mut_ptr())
+    };
+    let message = if rc != 0 { unsafe { CStr::from_ptr(sys::zoe_cuda_last_error(ctx)) }.to_string_lossy().into_owned() } else { String::new() };
+    unsafe { sys::zoe_cuda_destroy(ctx) };
+    if rc != 0 {
+        return Err(CudaError::Cuda { code: rc, message });
+    }
+    Ok(out[..references.len()].iter().map(|&v| match v { 0 => Some(false), 1 => Some(true), _ => None }).collect())
 }
 
 fn maybe(status: u8, score: u32) -> MaybeAligned<u32> {
