@@ -1,21 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- SW GCUPS of the B200 path on BASELINE.json's configurations.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--mode M] [--impl reference]
 
-One "step" = one pass of the hot path over one batch of synthetic input.  The default workload is
-BASELINE.json configs[1]: 1M x 150-nt reads vs 8 influenza-A-length segments, score only
-(2.04e12 cells per GPU per step).  Multi-GPU: one process per GPU (torchrun), each rank scores
-its own 1M-read shard, no collective on the data path ("weak": per-GPU work is fixed).
+One "step" = one pass of the hot path over one batch of synthetic input.  The headline workload is BASELINE.json
+configs[1]: ONE fixed set of 1M x 150-nt reads (seed 3) vs 8 influenza-A-length segments, score only (2.04e12 cells per
+step).  With N GPUs (one process per GPU under torchrun) rank r scores the contiguous shard
+``zoe_b200.dist.shard_range(1_000_000, r, N)`` of that same set -- "scaling": "strong"; no collective on the data path;
+the per-rank result checksums are summed (off the clock) and must equal the N = 1 checksum.
 
-`value`  = GCUPS with the batch already resident in HBM (CUDA events on the library's stream).
-`e2e`    = GCUPS through the host-buffer C-ABI call (pinned host -> device copies and the
-           device -> host result copies inside the timed region).
-`--config 1..5` selects another BASELINE.json configuration (3 = align with device traceback and CIGARs, 4 = long
-reads, 5 = protein); `--mode score|align|ranges|3pass` overrides the entry point (ranges = sw_score_ranges, 3pass =
-sw_align_from_i8_3pass).
-`--impl reference` times the CPU restatement of zoe's striped path (oracle/zoe_sw_cpu.cpp) on all
-host threads; zoe itself (Rust nightly) cannot be built in this image.
+`value`  = whole-job GCUPS with the shard already resident in HBM (CUDA events on the library's stream, max over ranks).
+`e2e`    = whole-job GCUPS through the host-buffer C-ABI call (pinned host -> device copies and the device -> host
+           result copies inside the timed region, max over ranks).
+`legs`   = the other half of the metric and the other configurations, timed by the same code in the same run:
+           "align" (cfg 3: zoe_cuda_sw_align_batch, device traceback + CIGARs; at N = 1 checked pair by pair against the
+           vectorised CPU restatement of sw_simd_align on the WHOLE set), and at N = 1 also "cfg1", "cfg4" (a stated
+           slice), "cfg5".  `--legs none` skips them, `--config C` benches one configuration alone.
+`--impl reference` times the CPU restatement of zoe's striped path (oracle/zoe_sw_cpu.cpp) on all host threads; zoe
+itself (Rust nightly) cannot be built in this image.
 """
 from __future__ import annotations
 
@@ -37,6 +39,10 @@ METRIC = "sw_gcups"
 UNIT = "GCUPS"
 DPX_INSTR_PER_CELL = 2.25  # 4.5 DPX/ALU instructions per packed cell pair (DESIGN.md "score kernel")
 
+# Result checksums of the default workloads at N = 1 (sum of scores [+ ranges + CIGAR words], mod 2^64).  A sharded
+# run must reproduce them: the results do not depend on how the reads are split over GPUs.
+EXPECTED_CHECKSUM = {("cfg2", "score", 1_000_000): 268486591}
+
 
 def env_int(name, default):
     try:
@@ -45,36 +51,49 @@ def env_int(name, default):
         return default
 
 
-def make_workload(config: int, n_override: int | None, rank: int):
-    """Returns (name, matrix, gap_open, gap_extend, targets, (buf, offs), mode)."""
+def make_workload(config: int, n_override: int | None):
+    """Returns (key, name, matrix, gap_open, gap_extend, targets, (buf, offs), mode).  The data depend on the
+    configuration only -- never on the rank: every rank generates the same set and takes its shard of it."""
     from zoe_b200 import BLOSUM_62, WeightMatrix, synth
 
     dna = WeightMatrix.new_dna_matrix(2, -5, b"N")
     if config == 1:
         n = n_override or 10_000
-        t, r = synth.config1(ROOT, n_reads=n, seed=1 + 1000 * rank)
-        return (f"cfg1: {n} x 150nt reads vs 1704nt HA, score", dna, -10, -1, t, synth.fixed_len_batch(r), "score")
+        t, r = synth.config1(ROOT, n_reads=n, seed=1)
+        return ("cfg1", f"cfg1: {n} x 150nt reads vs 1704nt HA, score", dna, -10, -1, t, synth.fixed_len_batch(r), "score")
     if config == 2:
         n = n_override or 1_000_000
-        t, r = synth.config2(n_reads=n, seed_reads=3 + 1000 * rank)
-        return (f"cfg2: {n} x 150nt reads vs 8 flu-A-length segments (13588nt), score-only", dna, -10, -1, t,
+        t, r = synth.config2(n_reads=n, seed_reads=3)
+        return ("cfg2", f"cfg2: {n} x 150nt reads vs 8 flu-A-length segments (13588nt), score-only", dna, -10, -1, t,
                 synth.fixed_len_batch(r), "score")
     if config == 3:
         n = n_override or 1_000_000
-        t, r = synth.config3(ROOT, n_reads=n, seed=4 + 1000 * rank)
-        return (f"cfg3: {n} x 150nt reads vs 1704nt HA, align with traceback", dna, -10, -1, t,
+        t, r = synth.config3(ROOT, n_reads=n, seed=4)
+        return ("cfg3", f"cfg3: {n} x 150nt reads vs 1704nt HA, align with traceback", dna, -10, -1, t,
                 synth.fixed_len_batch(r), "align")
     if config == 4:
         n = n_override or 100_000
-        t, r = synth.config4(n_reads=n, seed_reads=6 + 1000 * rank)
-        return (f"cfg4: {n} x 1-5kb ONT-like reads vs 29903nt genome, score-only (long-row path)", dna, -10, -1, t,
+        t, r = synth.config4(n_reads=n, seed_reads=6)
+        return ("cfg4", f"cfg4: {n} x 1-5kb ONT-like reads vs 29903nt genome, score-only (long-row path)", dna, -10, -1, t,
                 synth.pack(r), "score")
     if config == 5:
         n = n_override or 1_000_000
-        t, q = synth.config5(n_queries=n, seed_queries=8 + 1000 * rank)
-        return (f"cfg5: {n} x 300aa queries vs 566aa target, BLOSUM62, score-only", BLOSUM_62, -10, -1, t,
+        t, q = synth.config5(n_queries=n, seed_queries=8)
+        return ("cfg5", f"cfg5: {n} x 300aa queries vs 566aa target, BLOSUM62, score-only", BLOSUM_62, -10, -1, t,
                 synth.fixed_len_batch(q), "score")
-    raise SystemExit(f"config {config} is not a bench workload yet")
+    raise SystemExit(f"config {config} is not a bench workload")
+
+
+def shared_config(name: str, n_total: int, n_prof: int, mode: str, in_bytes: int):
+    """The `config` object, identical in both arms (b200 / reference) for the same command line."""
+    return {
+        "workload": name, "sequences": n_total, "profiled": n_prof, "mode": mode,
+        "sharding": "one fixed set; rank r takes the contiguous index range shard_range(n, r, n_gpus); no collective",
+        "l2": ("inputs_exceed_l2" if in_bytes > 126e6 else
+               "inputs_smaller_than_l2 (ALU-bound kernel; every sequence byte is read once per step)"),
+        "orientation": "profile = reference side, reads streamed (SeqSrc::Query)", "lanes": "w256",
+        "reference_arm_sample": "the CPU arm times a bounded prefix of this workload per step (GCUPS is a rate)",
+    }
 
 
 class ClockSampler:
@@ -127,6 +146,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# CPU side (oracle/): the reported baseline and the parity checker.  Never inside a timed GPU region.
+# ------------------------------------------------------------------------------------------------------------------
 def cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads, width_bits=256):
     from oracle import cpu_baseline as CB
     from zoe_b200 import synth
@@ -136,6 +158,20 @@ def cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads, width_bi
     t0 = time.perf_counter()
     res = CB.score_batch(pbuf, poff, buf[: int(o[-1])], o, matrix.weights, matrix.mapping.index_map, go, ge,
                          width_bits=width_bits, n_threads=threads)
+    dt = time.perf_counter() - t0
+    cells = int(o[-1]) * int(poff[-1])
+    return cells / dt / 1e9, dt, res
+
+
+def cpu_align_run(matrix, go, ge, targets, buf, offs, n_sample, threads, width_bits=256):
+    from oracle import cpu_baseline as CB
+    from zoe_b200 import synth
+
+    pbuf, poff = synth.pack([np.asarray(t, dtype=np.uint8) for t in targets])
+    o = offs[: n_sample + 1]
+    t0 = time.perf_counter()
+    res = CB.align_batch(pbuf, poff, buf[: int(o[-1])], o, matrix.weights, matrix.mapping.index_map, go, ge,
+                         width_bits=width_bits, n_threads=threads, streamed_is_query=True)
     dt = time.perf_counter() - t0
     cells = int(o[-1]) * int(poff[-1])
     return cells / dt / 1e9, dt, res
@@ -152,6 +188,13 @@ def run_threaded(check_range, n_items):
         return sum(ex.map(lambda sp: check_range(*sp), spans)), threads
 
 
+def sized_sample(n_total, probe_fn, seconds):
+    """Largest prefix of the workload the CPU port gets through in about `seconds` (probe: 2000 sequences)."""
+    probe = min(n_total, 2000)
+    _, dt0, _ = probe_fn(probe)
+    return int(min(n_total, max(probe, probe * seconds / max(dt0, 1e-3))))
+
+
 def run_reference(args):
     """`--impl reference`: the CPU restatement on all host threads, rank 0 only."""
     rank = env_int("RANK", 0)
@@ -159,35 +202,369 @@ def run_reference(args):
         return
     from oracle import cpu_baseline as CB
 
-    name, matrix, go, ge, targets, (buf, offs), mode = make_workload(args.config, args.n, 0)
+    key, name, matrix, go, ge, targets, (buf, offs), mode = make_workload(args.config, args.n)
+    if args.mode:
+        mode = args.mode
+        name += f" [mode {mode}]"
     threads = CB.hardware_threads()
     n_total = len(offs) - 1
-    # calibrate a bounded sample: ~4 s of CPU work per step
-    probe = min(n_total, 2000)
-    g0, dt0, _ = cpu_port_run(matrix, go, ge, targets, buf, offs, probe, threads)
-    n_sample = int(min(n_total, max(probe, probe * 4.0 / max(dt0, 1e-3))))
+    n_prof = len(targets)
+    align = mode in ("align", "3pass", "ranges")
+    runner = cpu_align_run if align else cpu_port_run
+    # a bounded sample: ~4 s of CPU work per step
+    n_sample = sized_sample(n_total, lambda k: runner(matrix, go, ge, targets, buf, offs, k, threads), 4.0)
     for _ in range(args.warmup):
-        cpu_port_run(matrix, go, ge, targets, buf, offs, min(n_sample, probe), threads)
+        runner(matrix, go, ge, targets, buf, offs, min(n_sample, 2000), threads)
     times = []
     for _ in range(args.steps):
-        g, dt, _ = cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads)
+        g, dt, _ = runner(matrix, go, ge, targets, buf, offs, n_sample, threads)
         times.append(dt)
     prof_total = sum(len(t) for t in targets)
     cells = int(offs[n_sample]) * prof_total
     value = cells * len(times) / sum(times) / 1e9
+    what = ("sw_simd_align + to_alignment + invert" if align else "sw_simd_score") + " + i8->i16->i32 escalation"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "i8/i16/i32 (zoe tiers, w256 lanes)", "data": "synthetic",
-        "config": {"workload": name, "sample": f"first {n_sample} sequences of the workload per step",
-                   "orientation": "profile = reference side, reads streamed"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "i8/i16/i32 (zoe tiers, w256 lanes)", "data": "synthetic",
+        "config": shared_config(name, n_total, n_prof, mode, int(buf.nbytes + offs.nbytes)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n_sample} sequences x {prof_total} profiled residues per step, {CB.isa()}, "
-                                   "C++ restatement of zoe's striped sw_simd_score + i8->i16->i32 escalation "
+                         "sample": f"first {n_sample} sequences x {prof_total} profiled residues per step, {CB.isa()}, "
+                                   f"C++ restatement of zoe's striped {what} "
                                    "(zoe itself needs nightly Rust: not buildable here)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# one leg = one configuration + mode, timed device-resident and end to end on this rank's shard
+# ------------------------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide state of a bench run (ranks, barrier, reductions from zoe_b200.dist)."""
+
+    def __init__(self, args):
+        import torch
+        from zoe_b200 import dist as zdist
+
+        self.torch = torch
+        self.zdist = zdist
+        self.rank, self.world, self.local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        self.distributed = self.world > 1
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: zoe_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.distributed:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        self.in_process_devices = args.gpus if (not self.distributed and args.gpus > 1) else 1
+        self.n_gpus = self.world if self.distributed else self.in_process_devices
+        self.device = torch.device("cuda", self.local_rank)
+
+    def barrier(self):
+        if self.distributed:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        return self.zdist.max_over_ranks(x, device=self.device)
+
+    def sum_over_ranks(self, x: float) -> float:
+        return self.zdist.sum_over_ranks(x, device=self.device)
+
+    def sum_u64_over_ranks(self, x: int) -> int:
+        return self.zdist.sum_u64_over_ranks(x, device=self.device)
+
+
+def pinned(torch, arr: np.ndarray):
+    t = torch.from_numpy(arr).pin_memory()
+    return t, t.numpy()
+
+
+def run_leg(ctx: Ctx, config: int, mode_override, n_override, steps: int, warmup: int, cpu: bool, cpu_seconds: float,
+            align_opts=None, sample_clocks: bool = False, full_parity: bool = True):
+    """Times one configuration on this rank's shard; returns the record rank 0 prints (None on the other ranks)."""
+    from zoe_b200 import CudaProfiles
+
+    torch = ctx.torch
+    key, name, matrix, go, ge, targets, (buf_all, offs_all), mode = make_workload(config, n_override)
+    if mode_override:
+        mode = mode_override
+        name += f" [mode {mode}]"
+    n_total = len(offs_all) - 1
+    n_prof = len(targets)
+    prof_total = sum(len(t) for t in targets)
+    total_cells = int(offs_all[-1]) * prof_total
+
+    # ---- this rank's shard: contiguous index range of the one fixed set ----
+    # (an in-process multi-device context shards inside the library by the same rule)
+    _, buf, offs = ctx.zdist.shard_batch(buf_all, offs_all, ctx.rank if ctx.distributed else 0,
+                                         ctx.world if ctx.distributed else 1)
+    n = len(offs) - 1
+    pairs = n * n_prof
+
+    if ctx.in_process_devices > 1:
+        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, n_devices=ctx.in_process_devices)
+    else:
+        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, devices=[ctx.local_rank])
+    if align_opts:
+        prof.set_align_options(*[int(x) for x in align_opts.split(",")])
+
+    # pinned host buffers for the end-to-end leg
+    t_buf, h_buf = pinned(torch, buf)
+    t_offs, h_offs_i = pinned(torch, offs.view(np.int64))
+    h_offs = h_offs_i.view(np.uint64)
+    keep = [t_buf, t_offs]
+    outs = {}
+    for k in ("score", "ref_start", "ref_end", "query_start", "query_end"):
+        if k == "score" or mode != "score":
+            t, a = pinned(torch, np.zeros(max(pairs, 1), dtype=np.int32))
+            keep.append(t)
+            outs[k] = a.view(np.uint32)
+    for k in ("status", "tier", "hazard"):
+        if k != "hazard" or mode in ("align", "3pass"):
+            t, a = pinned(torch, np.zeros(max(pairs, 1), dtype=np.uint8))
+            keep.append(t)
+            outs[k] = a
+    if mode in ("align", "3pass"):
+        cap = pairs * 8 + 1024
+        t, a = pinned(torch, np.zeros(pairs + 1, dtype=np.int64))
+        keep.append(t)
+        outs["cigar_off"] = a.view(np.uint64)
+        t, a = pinned(torch, np.zeros(cap, dtype=np.int32))
+        keep.append(t)
+        outs["cigar"] = a.view(np.uint32)
+
+    stream = torch.cuda.ExternalStream(prof.stream_handle(0), device=ctx.device)
+    run_staged = {"score": prof.run_score_staged, "align": prof.run_align_staged, "ranges": prof.run_ranges_staged,
+                  "3pass": prof.run_3pass_staged}[mode]
+
+    def e2e_call():
+        if mode == "score":
+            prof.sw_score_into(h_buf, h_offs, outs["score"], outs["status"], outs["tier"])
+        elif mode == "ranges":
+            prof.ranges_into(h_buf, h_offs, outs)
+        else:
+            prof.align_into(h_buf, h_offs, outs, three_pass=(mode == "3pass"))
+
+    # ---------------- device-resident leg (`value`) ----------------
+    prof.stage(h_buf, h_offs)
+    sampler = ClockSampler(ctx.local_rank) if (sample_clocks and ctx.rank == 0) else None
+    if sampler:
+        sampler.start()
+    for _ in range(warmup):
+        run_staged()
+    ctx.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dp_ms, launches = [], 0
+    t_region0 = time.time()
+    ev0.record(stream)
+    for _ in range(steps):
+        run_staged()
+        tm = prof.last_timing()
+        dp_ms.append(tm["dp_kernel_ms"])
+        launches += tm["kernel_launches"]
+    ev1.record(stream)
+    ctx.barrier()
+    if sampler:
+        sampler.window(t_region0, time.time())
+    clocks = sampler.stop() if sampler else None
+    dev_ms = ctx.max_over_ranks(ev0.elapsed_time(ev1))
+    stats = prof.last_stats()
+    value = total_cells * steps / (dev_ms * 1e-3) / 1e9
+
+    # ---------------- end-to-end leg (`e2e`): host buffers in, host results out ----------------
+    for _ in range(min(warmup, 2)):
+        e2e_call()
+    ctx.barrier()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev2.record(stream)
+    for _ in range(steps):
+        e2e_call()
+        launches += prof.last_timing()["kernel_launches"]
+    ev3.record(stream)
+    ctx.barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = ctx.max_over_ranks(max(ev2.elapsed_time(ev3), wall_ms))
+    e2e_stats = prof.last_stats()
+    n_words = int(outs["cigar_off"][pairs]) if mode in ("align", "3pass") else 0
+    d2h = {"score": pairs * 6, "ranges": pairs * 22}.get(mode, pairs * (5 * 4 + 3 + 8) + 8 + n_words * 4)
+    # additive checksum: the per-rank values sum to the N = 1 value
+    checksum = int(outs["score"][:pairs].sum(dtype=np.uint64))
+    if mode != "score":
+        for k in ("ref_start", "ref_end", "query_start", "query_end"):
+            checksum += int(outs[k][:pairs].sum(dtype=np.uint64))
+    if n_words:
+        checksum += int(outs["cigar"][:n_words].sum(dtype=np.uint64))
+    checksum = ctx.sum_u64_over_ranks(checksum & 0xFFFFFFFFFFFFFFFF)
+    want = EXPECTED_CHECKSUM.get((key, mode, n_total))
+    e2e = {"value": total_cells * steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": int(ctx.sum_over_ranks(float(h_buf.nbytes + h_offs.nbytes))),
+           "d2h_bytes_per_step": int(ctx.sum_over_ranks(float(d2h))),
+           "ms_per_step": e2e_ms / steps, "result_checksum": checksum,
+           "checksum_expected_n1": want, "checksum_matches_n1": (checksum == want) if want is not None else None}
+
+    # ---------------- roofline of the dominant kernel (this rank's launches) ----------------
+    dpx_g, _ = prof.dpx_peak(0)  # G lane-instr/s, measured live on this GPU
+    peak_gcups = dpx_g / DPX_INSTR_PER_CELL
+    cells_rank = int(offs[-1]) * prof_total
+    dp_mean = float(np.mean(dp_ms)) if dp_ms and np.mean(dp_ms) > 0 else float("nan")
+    kernel_gcups = cells_rank / (dp_mean * 1e-3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    in_bytes = float(h_buf.nbytes + h_offs.nbytes + pairs * 4)
+    maxlen = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
+    if mode == "score":
+        if matrix.S > 8 and max(len(t) for t in targets) <= 1024 and 64 <= maxlen <= 1024:
+            kname, instr = "sw_score_rows_stream_kernel (profiled sequence in registers, shared table)", "4.5 ALU + 2 FMA-pipe"
+        elif maxlen > 1024:
+            kname, instr = "sw_score_long_kernel (chunked rows, boundary rows through L2)", "4.5 ALU + 1 FMA-pipe"
+        else:
+            kname, instr = "sw_score_kernel (two column streams, ping-pong register sets)", "4.5 ALU + 1 FMA-pipe"
+        frac_of = "the kernel alone"
+    elif mode in ("ranges", "3pass"):
+        kname = "sw_align_scan_kernel forward (+ pin sweep) and its REV instantiation (score + end / start cell, no traceback matrix)"
+        instr = "4.5 ALU + 1 FMA-pipe per cell pair plus per-column bookkeeping; the reverse pass covers the truncated matrix"
+        if mode == "3pass":
+            kname += "; pass 3 = tp_classify / tp_dp kernels (no-gaps shortcut, banded box alignment)"
+        frac_of = "all DP kernels of the step (forward scan, pin sweep, reverse scan)"
+    else:
+        kname = "sw_align_scan_kernel + sw_align_winfill_kernel (checkpointed window; DESIGN.md 4.3)"
+        instr = "4.5 ALU per cell pair in the scan, 9.5 ALU + 11 FMA-pipe in the window fill"
+        ck = (n / 2) * sum((len(t) - 1) // 64 for t in targets) * 40 * 8 * 4
+        fl = (pairs / 2) * 216 * 8 * 8 * 4
+        in_bytes += float(ck + fl)
+        frac_of = "the DP kernels of the step (scan + pin + window fill), not the whole pipeline -- see `frac_step`"
+    traffic, traffic_source = None, None
+    try:  # measured DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"cfg{config}/{mode}")
+        if tr and n_override is None and ctx.n_gpus == 1:
+            traffic, traffic_source = tr["dram_read_bytes"] + tr["dram_write_bytes"], tr["source"]
+    except Exception:
+        pass
+    roofline = {
+        "bound": "alu", "achieved": kernel_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
+        "frac_of": frac_of, "frac_step": value / ctx.n_gpus / peak_gcups,
+        "traffic": traffic, "traffic_source": traffic_source,
+        "note": ("integer max-plus (DPX on the ALU pipe) bound, not hbm/tensor: peak = live-measured "
+                 "VIADDMNMX.S16x2 issue rate (%.0f G lane-instr/s) / %.2f ALU instr per cell (4.5 per packed s16x2 cell "
+                 "pair: the score recurrence); kernel = %s, %s per cell pair; avg of %d steps on rank 0's shard, CUDA events "
+                 "on the library stream" % (dpx_g, DPX_INSTR_PER_CELL, kname, instr, len(dp_ms))),
+        "hbm": {"algorithmic_bytes_per_launch": in_bytes, "achieved_gbs": in_bytes / (dp_mean * 1e-3) / 1e9,
+                "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "frac": in_bytes / (dp_mean * 1e-3) / 1e9 / hbm_peak},
+    }
+
+    # ---------------- CPU baseline + parity (rank 0, N = 1 only) ----------------
+    cpu_rec, parity = None, None
+    if cpu and ctx.rank == 0 and ctx.n_gpus == 1:
+        from oracle import cpu_baseline as CB
+        threads = CB.hardware_threads()
+        if mode == "score":
+            full = full_parity and total_cells <= 4e11  # cfg 1 / 5: the whole set (SURVEY 8(d)); cfg 2 / 4: a sample
+            n_sample = n if full else sized_sample(
+                n, lambda k: cpu_port_run(matrix, go, ge, targets, buf, offs, k, threads), cpu_seconds)
+            g, dt, (c_score, c_status, c_tier) = cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads)
+            lazy, rows = CB.last_lazy_stats()
+            cpu_rec = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": f"first {n_sample} of {n} sequences x all {n_prof} profiled ({dt:.1f} s, {CB.isa()}, w256 "
+                                 f"lanes i8x32/i16x16/i32x8; lazy-F revisits {lazy / max(rows, 1):.1f} vectors per DP row)"}
+            g_score = outs["score"].reshape(n, n_prof)[:n_sample]
+            g_status = outs["status"].reshape(n, n_prof)[:n_sample]
+            g_tier = outs["tier"].reshape(n, n_prof)[:n_sample]
+            some = c_status == 0
+            mism = int((g_status != c_status).sum() + (g_score[some] != c_score[some]).sum()
+                       + (g_tier[some] != c_tier[some]).sum())
+            parity = {"checked_pairs": int(n_sample * n_prof), "of_pairs": pairs, "mismatches": mism,
+                      "against": "vectorised CPU port of sw_simd_score (oracle/zoe_sw_cpu.cpp)"}
+        elif mode == "align":
+            n_sample = n if full_parity else sized_sample(
+                n, lambda k: cpu_align_run(matrix, go, ge, targets, buf, offs, k, threads), cpu_seconds)
+            g, dt, want_res = cpu_align_run(matrix, go, ge, targets, buf, offs, n_sample, threads)
+            t1 = time.perf_counter()
+            mism = CB.compare_alignments(outs, want_res, n_sample * n_prof)
+            cpu_rec = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": f"first {n_sample} of {n} sequences ({dt:.1f} s, {CB.isa()}, w256 lanes): vectorised C++ "
+                                 "restatement of sw_simd_align + to_alignment + invert + i8->i16->i32 escalation"}
+            parity = {"checked_pairs": int(n_sample * n_prof), "of_pairs": pairs, "mismatches": mism,
+                      "compare_s": round(time.perf_counter() - t1, 2),
+                      "against": "vectorised CPU port of sw_simd_align (oracle/zoe_sw_cpu.cpp; itself pinned to "
+                                 "oracle/zoe_sw_oracle.c in tests/): status, score, tier, ranges, CIGAR"}
+        else:  # ranges / 3pass: the plain-C oracle on a sample
+            from oracle import oracle as O
+            sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
+            n_sample = min(n, 20000)
+            t0 = time.perf_counter()
+
+            def check_range(lo_, hi_):
+                bad = 0
+                for i in range(lo_, hi_):
+                    s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
+                    for j, tg in enumerate(targets):
+                        k = i * n_prof + j
+                        if mode == "3pass":
+                            rc, w, _, _ = O.sw_align_3pass_from(bytes(tg), s_i, sc, streamed_is_query=True)
+                            ok = int(outs["status"][k]) == rc
+                            if ok and rc == 0:
+                                lo_w, hi_w = int(outs["cigar_off"][k]), int(outs["cigar_off"][k + 1])
+                                cig = "".join(f"{int(x) >> 4}{'MID?S'[int(x) & 15]}" for x in outs["cigar"][lo_w:hi_w])
+                                ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
+                                      int(outs["query_start"][k]), int(outs["query_end"][k]), cig) == \
+                                     (w.score, w.ref_range[0], w.ref_range[1], w.query_range[0], w.query_range[1], w.cigar)
+                        else:
+                            rc, score, rr, qr, _ = O.sw_score_ranges_from(bytes(tg), s_i, sc, streamed_is_query=True)
+                            ok = int(outs["status"][k]) == rc
+                            if ok and rc == 0:
+                                ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
+                                      int(outs["query_start"][k]), int(outs["query_end"][k])) == (score, rr[0], rr[1], qr[0], qr[1])
+                        bad += 0 if ok else 1
+                return bad
+
+            mism, oracle_threads = run_threaded(check_range, n_sample)
+            dt = time.perf_counter() - t0
+            cpu_rec = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": oracle_threads,
+                       "kind": "port",
+                       "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of "
+                                 f"{'sw_align_3pass' if mode == '3pass' else 'sw_simd_score_ranges'} + escalation ({dt:.1f} s); "
+                                 "not vectorised -- a checker, not a tuned baseline"}
+            parity = {"checked_pairs": n_sample * n_prof, "of_pairs": pairs, "mismatches": mism,
+                      "against": "oracle/zoe_sw_oracle.c"}
+
+    rec = None
+    if ctx.rank == 0:
+        rec = {
+            "value": value, "unit": UNIT, "ms_per_step": dev_ms / steps, "steps": steps, "warmup": warmup,
+            "config": shared_config(name, n_total, n_prof, mode, int(buf_all.nbytes + offs_all.nbytes)),
+            "sequences_per_rank": n, "cells_per_step": total_cells,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu_rec, "parity": parity, "tiers": stats,
+            "hazard_pairs": int(e2e_stats.get("hazard", 0)),
+        }
+    prof.close()
+    del keep
+    return rec
+
+
+def compact(rec):
+    """An extra leg's record inside the headline line: the same keys, minus the long prose."""
+    if rec is None:
+        return None
+    out = {k: rec[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "sequences_per_rank", "cells_per_step",
+                               "gpu_launches", "cpu_baseline", "parity", "tiers", "hazard_pairs")}
+    out["workload"] = rec["config"]["workload"]
+    out["mode"] = rec["config"]["mode"]
+    out["e2e"] = rec["e2e"]
+    r = rec["roofline"]
+    out["roofline"] = {k: r[k] for k in ("bound", "achieved", "peak", "unit", "frac", "frac_of", "frac_step", "traffic")}
+    return out
 
 
 def main():
@@ -195,336 +572,82 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", type=int, default=2)
-    ap.add_argument("--n", type=int, default=None, help="override the number of streamed sequences per GPU")
+    ap.add_argument("--config", type=int, default=None, help="bench ONE configuration (1..5) alone; default: cfg 2 + legs")
+    ap.add_argument("--n", type=int, default=None, help="override the number of streamed sequences of the whole job")
     ap.add_argument("--mode", default=None, choices=["score", "align", "ranges", "3pass"],
                     help="override the workload's mode (ranges = sw_score_ranges: score + alignment ranges, no traceback matrix; "
                          "3pass = sw_align_from_i8_3pass: ranges + banded alignment of the bounding box)")
     ap.add_argument("--align-opts", default=None, help="mode,checkpoint_log2,slack for zoe_cuda_set_align_options (tuning)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--legs", default="auto", help="auto | none | comma list of align,cfg1,cfg4,cfg5,w512")
+    ap.add_argument("--leg-steps", type=int, default=5)
+    ap.add_argument("--parity", default="full", choices=["full", "sample"],
+                    help="full: cfg 1 / 3 / 5 are checked on the whole set (SURVEY 8(d)); sample: a bounded prefix")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    headline_alone = args.config is not None
+    if args.config is None:
+        args.config = 2
 
     if args.impl == "reference":
         run_reference(args)
         return
 
-    import torch
+    ctx = Ctx(args)
+    cpu = not args.no_cpu_baseline
+    full = args.parity == "full"
+    head = run_leg(ctx, args.config, args.mode, args.n, args.steps, args.warmup, cpu, 12.0, args.align_opts,
+                   sample_clocks=True, full_parity=full)
 
-    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    distributed = world > 1
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: zoe_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if distributed:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    in_process_devices = args.gpus if (not distributed and args.gpus > 1) else 1
+    legs = {}
+    want = []
+    if args.legs == "auto":
+        if not headline_alone and args.n is None:
+            want = ["align", "cfg5", "cfg4", "cfg1", "w512"] if ctx.n_gpus == 1 else ["align"]
+    elif args.legs != "none":
+        want = [x for x in args.legs.split(",") if x]
+    for leg in want:
+        ls, lw = args.leg_steps, 3
+        if leg == "align":
+            legs["align"] = compact(run_leg(ctx, 3, "align", None, ls, lw, cpu, 6.0, args.align_opts, full_parity=full))
+        elif leg == "cfg5":
+            legs["cfg5"] = compact(run_leg(ctx, 5, None, None, ls, lw, cpu, 6.0, full_parity=full))
+        elif leg == "cfg4":
+            r = run_leg(ctx, 4, None, 20_000, 3, 3, cpu, 5.0, full_parity=full)
+            if r:
+                r["config"]["workload"] += " [the first 20000 reads of the 100k-read set]"
+            legs["cfg4"] = compact(r)
+        elif leg == "cfg1":
+            legs["cfg1"] = compact(run_leg(ctx, 1, None, None, max(ls, 20), lw, cpu, 2.0, full_parity=full))
+        elif leg == "w512" and cpu and ctx.rank == 0 and ctx.n_gpus == 1:
+            # the score-only CPU baseline with zoe's w512 preset (i8 x 64; sw/mod.rs:285-286) beside w256
+            from oracle import cpu_baseline as CB
+            key, name, matrix, go, ge, targets, (buf, offs), _ = make_workload(2, 200_000)
+            threads = CB.hardware_threads()
+            n_s = sized_sample(len(offs) - 1, lambda k: cpu_port_run(matrix, go, ge, targets, buf, offs, k, threads, 512), 5.0)
+            g, dt, _ = cpu_port_run(matrix, go, ge, targets, buf, offs, n_s, threads, 512)
+            legs["cpu_w512"] = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"cfg2, first {n_s} sequences x 8 profiled, score-only, w512 lanes i8x64/i16x32/i32x16 "
+                                          f"({dt:.1f} s, {CB.isa()})"}
 
-    from zoe_b200 import CudaProfiles
-
-    name, matrix, go, ge, targets, (buf, offs), mode = make_workload(args.config, args.n, rank)
-    if args.mode:
-        mode = args.mode
-        name += f" [mode {mode}]"
-    if in_process_devices > 1:
-        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, n_devices=in_process_devices)
-    else:
-        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], matrix, go, ge, devices=[local_rank])
-    if args.align_opts:
-        prof.set_align_options(*[int(x) for x in args.align_opts.split(",")])
-    n = len(offs) - 1
-    n_prof = len(targets)
-    prof_total = sum(len(t) for t in targets)
-    cells_per_step = int(offs[-1]) * prof_total  # per process
-
-    # pinned host buffers for the end-to-end leg
-    t_buf = torch.from_numpy(buf).pin_memory()
-    t_offs = torch.from_numpy(offs.view(np.int64)).pin_memory()
-    h_buf, h_offs = t_buf.numpy(), t_offs.numpy().view(np.uint64)
-    t_score = torch.empty(n * n_prof, dtype=torch.int32).pin_memory()
-    t_status = torch.empty(n * n_prof, dtype=torch.uint8).pin_memory()
-    t_tier = torch.empty(n * n_prof, dtype=torch.uint8).pin_memory()
-    h_score, h_status, h_tier = t_score.numpy().view(np.uint32), t_status.numpy(), t_tier.numpy()
-
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if not distributed:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if not distributed:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    stream = torch.cuda.ExternalStream(prof.stream_handle(0), device=torch.device("cuda", local_rank))
-    run_staged = {"score": prof.run_score_staged, "align": prof.run_align_staged, "ranges": prof.run_ranges_staged,
-                  "3pass": prof.run_3pass_staged}[mode]
-
-    # ---------------- device-resident leg (`value`) ----------------
-    prof.stage(h_buf, h_offs)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
-        run_staged()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dp_ms, launches = [], 0
-    t_region0 = time.time()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        run_staged()
-        tm = prof.last_timing()
-        dp_ms.append(tm["dp_kernel_ms"])
-        launches += tm["kernel_launches"]
-    ev1.record(stream)
-    barrier()
-    if rank == 0:
-        sampler.window(t_region0, time.time())
-    clocks = sampler.stop() if rank == 0 else None
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    stats = prof.last_stats()
-    total_cells = sum_over_ranks(float(cells_per_step))
-    value = total_cells * args.steps / (dev_ms * 1e-3) / 1e9
-
-    # ---------------- end-to-end leg (`e2e`): host buffers in, host results out ----------------
-    e2e = None
-    if mode == "score":
-        for _ in range(min(args.warmup, 2)):
-            prof.sw_score_into(h_buf, h_offs, h_score, h_status, h_tier)
-        barrier()
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev2.record(stream)
-        for _ in range(args.steps):
-            prof.sw_score_into(h_buf, h_offs, h_score, h_status, h_tier)
-            launches += prof.last_timing()["kernel_launches"]
-        ev3.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), wall_ms))
-        e2e = {"value": total_cells * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(h_buf.nbytes + h_offs.nbytes),
-               "d2h_bytes_per_step": int(h_score.nbytes + h_status.nbytes + h_tier.nbytes),
-               "ms_per_step": e2e_ms / args.steps, "result_checksum": int(h_score.sum(dtype=np.uint64))}
-
-    if mode == "ranges":
-        t_out = {k: torch.empty(n * n_prof, dtype=torch.int32).pin_memory() for k in
-                 ("score", "ref_start", "ref_end", "query_start", "query_end")}
-        t_b = {k: torch.empty(n * n_prof, dtype=torch.uint8).pin_memory() for k in ("status", "tier")}
-        outs = {k: v.numpy().view(np.uint32) for k, v in t_out.items()}
-        outs.update({k: v.numpy() for k, v in t_b.items()})
-        for _ in range(min(args.warmup, 2)):
-            prof.ranges_into(h_buf, h_offs, outs)
-        barrier()
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev2.record(stream)
-        for _ in range(args.steps):
-            prof.ranges_into(h_buf, h_offs, outs)
-            launches += prof.last_timing()["kernel_launches"]
-        ev3.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), wall_ms))
-        e2e = {"value": total_cells * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(h_buf.nbytes + h_offs.nbytes),
-               "d2h_bytes_per_step": int(n * n_prof * (5 * 4 + 2)),
-               "ms_per_step": e2e_ms / args.steps,
-               "result_checksum": int(outs["score"].sum(dtype=np.uint64)) ^ int(outs["ref_start"].sum(dtype=np.uint64))}
-
-    if mode in ("align", "3pass"):
-        three_pass = mode == "3pass"
-        cap = n * n_prof * 8 + 1024
-        t_out = {k: torch.empty(n * n_prof, dtype=torch.int32).pin_memory() for k in
-                 ("score", "ref_start", "ref_end", "query_start", "query_end")}
-        t_b = {k: torch.empty(n * n_prof, dtype=torch.uint8).pin_memory() for k in ("status", "tier", "hazard")}
-        t_off = torch.empty(n * n_prof + 1, dtype=torch.int64).pin_memory()
-        t_cig = torch.empty(cap, dtype=torch.int32).pin_memory()
-        outs = {k: v.numpy().view(np.uint32) for k, v in t_out.items()}
-        outs.update({k: v.numpy() for k, v in t_b.items()})
-        outs["cigar_off"] = t_off.numpy().view(np.uint64)
-        outs["cigar"] = t_cig.numpy().view(np.uint32)
-        for _ in range(min(args.warmup, 2)):
-            prof.align_into(h_buf, h_offs, outs, three_pass=three_pass)
-        barrier()
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev2.record(stream)
-        for _ in range(args.steps):
-            prof.align_into(h_buf, h_offs, outs, three_pass=three_pass)
-            launches += prof.last_timing()["kernel_launches"]
-        ev3.record(stream)
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        e2e_ms = max_over_ranks(max(ev2.elapsed_time(ev3), wall_ms))
-        n_words = int(outs["cigar_off"][n * n_prof])
-        e2e = {"value": total_cells * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(h_buf.nbytes + h_offs.nbytes),
-               "d2h_bytes_per_step": int(n * n_prof * (5 * 4 + 3 + 8) + 8 + n_words * 4),
-               "ms_per_step": e2e_ms / args.steps,
-               "result_checksum": int(outs["score"].sum(dtype=np.uint64)) ^ int(outs["cigar"][:n_words].sum(dtype=np.uint64))}
-
-    # ---------------- roofline of the dominant kernel ----------------
-    dpx_g, _ = prof.dpx_peak(0)  # G lane-instr/s, measured live on this GPU
-    peak_gcups = dpx_g / DPX_INSTR_PER_CELL
-    kernel_gcups = cells_per_step / (float(np.mean(dp_ms)) * 1e-3) / 1e9
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    in_bytes = float(h_buf.nbytes + h_offs.nbytes + n * n_prof * 4)
-    maxlen = int(np.max(np.diff(offs.astype(np.int64)))) if n else 0
-    if mode == "score":
-        if matrix.S > 8 and max(len(t) for t in targets) <= 1024 and 64 <= maxlen <= 1024:
-            kname, instr = "sw_score_rows_kernel (profiled sequence in registers, shared table)", "4.5 ALU + 2 FMA-pipe"
-        elif maxlen > 1024:
-            kname, instr = "sw_score_long_kernel (chunked rows, boundary rows through L2)", "4.5 ALU + 1 FMA-pipe"
-        else:
-            kname, instr = "sw_score_kernel (two column streams, ping-pong register sets)", "4.5 ALU + 1 FMA-pipe"
-    elif mode in ("ranges", "3pass"):
-        kname = "sw_align_scan_kernel forward (+ pin sweep) and its REV instantiation (score + end / start cell, no traceback matrix)"
-        instr = "4.5 ALU + 1 FMA-pipe per cell pair plus per-column bookkeeping; the reverse pass covers the truncated matrix"
-        if mode == "3pass":
-            kname += "; pass 3 = tp_classify / tp_dp kernels (no-gaps shortcut, banded box alignment)"
-    else:
-        # checkpointed-window pipeline: checkpoints (2K+2 words x 8 lanes per 64 columns per read pair) plus
-        # ~5 bits per cell of direction flags for the window of each mapped pair (about 150+16+32+8+10 columns)
-        kname = "sw_align_scan_kernel + sw_align_winfill_kernel (checkpointed window; DESIGN.md 4.3)"
-        instr = "4.5 ALU per cell pair in the scan, 9.5 ALU + 11 FMA-pipe in the window fill"
-        ck = (n / 2) * sum((len(t) - 1) // 64 for t in targets) * 40 * 8 * 4
-        fl = (n * n_prof / 2) * 216 * 8 * 8 * 4
-        in_bytes += float(ck + fl)
-    traffic, traffic_source = None, None
-    try:  # measured DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"cfg{args.config}/{mode}")
-        if tr and args.n is None:
-            traffic, traffic_source = tr["dram_read_bytes"] + tr["dram_write_bytes"], tr["source"]
-    except Exception:
-        pass
-    roofline = {
-        "bound": "alu", "achieved": kernel_gcups, "peak": peak_gcups, "unit": "GCUPS", "frac": kernel_gcups / peak_gcups,
-        "traffic": traffic, "traffic_source": traffic_source,
-        "note": ("integer max-plus (DPX on the ALU pipe) bound, not hbm/tensor: peak = live-measured "
-                 "VIADDMNMX.S16x2 issue rate (%.0f G lane-instr/s) / %.2f ALU instr per cell (4.5 per packed s16x2 cell "
-                 "pair: the score recurrence); kernel = %s, %s per cell pair; avg of %d steps, CUDA events on the "
-                 "library stream" % (dpx_g, DPX_INSTR_PER_CELL, kname, instr, len(dp_ms))),
-        "hbm": {"algorithmic_bytes_per_launch": in_bytes, "achieved_gbs": in_bytes / (float(np.mean(dp_ms)) * 1e-3) / 1e9,
-                "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                "frac": in_bytes / (float(np.mean(dp_ms)) * 1e-3) / 1e9 / hbm_peak},
-    }
-
-    # ---------------- CPU baseline + parity on a bounded sample (rank 0, N=1 only) ----------------
-    cpu = None
-    parity = None
-    if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "score":
-        from oracle import cpu_baseline as CB
-        threads = CB.hardware_threads()
-        probe = min(n, 2000)
-        g0, dt0, _ = cpu_port_run(matrix, go, ge, targets, buf, offs, probe, threads)
-        n_sample = int(min(n, max(probe, probe * 12.0 / max(dt0, 1e-3))))
-        g, dt, (c_score, c_status, c_tier) = cpu_port_run(matrix, go, ge, targets, buf, offs, n_sample, threads)
-        cpu = {"value": g, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {n_sample} sequences x all {n_prof} profiled ({dt:.1f} s, {CB.isa()}, w256 lanes)"}
-        g_score = h_score.reshape(n, n_prof)[:n_sample]
-        g_status = h_status.reshape(n, n_prof)[:n_sample]
-        g_tier = h_tier.reshape(n, n_prof)[:n_sample]
-        some = c_status == 0
-        mism = int((g_status != c_status).sum() + (g_score[some] != c_score[some]).sum()
-                   + (g_tier[some] != c_tier[some]).sum())
-        parity = {"checked_pairs": int(n_sample * n_prof), "mismatches": mism, "against": "cpu port (oracle/zoe_sw_cpu.cpp)"}
-
-    if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode == "ranges":
-        from oracle import oracle as O
-        sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
-        n_sample = min(n, 20000)
-        t0 = time.perf_counter()
-
-        def check_range(lo, hi):
-            bad = 0
-            for i in range(lo, hi):
-                s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
-                for j, tg in enumerate(targets):
-                    rc, score, rr, qr, _ = O.sw_score_ranges_from(bytes(tg), s_i, sc, streamed_is_query=True)
-                    k = i * n_prof + j
-                    ok = int(outs["status"][k]) == rc
-                    if ok and rc == 0:
-                        ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
-                              int(outs["query_start"][k]), int(outs["query_end"][k])) == (score, rr[0], rr[1], qr[0], qr[1])
-                    bad += 0 if ok else 1
-            return bad
-
-        mism, oracle_threads = run_threaded(check_range, n_sample)
-        dt = time.perf_counter() - t0
-        cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": oracle_threads, "kind": "port",
-               "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of sw_simd_score_ranges + escalation ({dt:.1f} s); "
-                         "not vectorised -- a checker, not a tuned baseline"}
-        parity = {"checked_pairs": n_sample * n_prof, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c (score, ranges)"}
-
-    if rank == 0 and world == 1 and in_process_devices == 1 and not args.no_cpu_baseline and mode in ("align", "3pass"):
-        from oracle import oracle as O
-        sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
-        n_sample = min(n, 20000)
-        t0 = time.perf_counter()
-
-        def check_range(lo, hi):
-            bad = 0
-            for i in range(lo, hi):
-                s_i = bytes(buf[int(offs[i]):int(offs[i + 1])])
-                for j, tg in enumerate(targets):
-                    if mode == "3pass":
-                        rc, want, _, _ = O.sw_align_3pass_from(bytes(tg), s_i, sc, streamed_is_query=True)
-                    else:
-                        rc, want, _ = O.sw_align_from(bytes(tg), s_i, sc, streamed_is_query=True)
-                    k = i * n_prof + j
-                    ok = int(outs["status"][k]) == rc
-                    if ok and rc == 0:
-                        lo_w, hi_w = int(outs["cigar_off"][k]), int(outs["cigar_off"][k + 1])
-                        cig = "".join(f"{int(w) >> 4}{'MID?S'[int(w) & 15]}" for w in outs["cigar"][lo_w:hi_w])
-                        ok = (int(outs["score"][k]), int(outs["ref_start"][k]), int(outs["ref_end"][k]),
-                              int(outs["query_start"][k]), int(outs["query_end"][k]), cig) == \
-                             (want.score, want.ref_range[0], want.ref_range[1], want.query_range[0], want.query_range[1], want.cigar)
-                    bad += 0 if ok else 1
-            return bad
-
-        mism, oracle_threads = run_threaded(check_range, n_sample)
-        dt = time.perf_counter() - t0
-        cpu = {"value": int(offs[n_sample]) * prof_total / dt / 1e9, "unit": UNIT, "cores": oracle_threads, "kind": "port",
-               "sample": f"first {n_sample} sequences, plain-C scalar-loop oracle of {'sw_align_3pass' if mode == '3pass' else 'sw_simd_align'} + escalation ({dt:.1f} s); "
-                         "not vectorised -- a checker, not a tuned baseline"}
-        parity = {"checked_pairs": n_sample * n_prof, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c (score, ranges, CIGAR)"}
-
-    if rank == 0:
-        n_gpus = world if distributed else in_process_devices
+    if ctx.rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": ctx.n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "s16x2 packed (s32 on overflow)", "data": "synthetic",
-            "config": {"workload": name, "sequences_per_gpu": n, "profiled": n_prof, "mode": mode,
-                       "cells_per_gpu_per_step": cells_per_step, "l2": "inputs_exceed_l2" if h_buf.nbytes > 126e6 else
-                       "inputs_smaller_than_l2 (compute-bound kernel; sequence bytes are read once)",
-                       "orientation": "profile = reference side, reads streamed (SeqSrc::Query)", "lanes": "w256"},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "parity": parity, "tiers": stats,
+            "config": head["config"], "sequences_per_rank": head["sequences_per_rank"],
+            "cells_per_step": head["cells_per_step"],
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "roofline": head["roofline"],
+            "cpu_baseline": head["cpu_baseline"], "parity": head["parity"], "tiers": head["tiers"],
         }
+        if legs:
+            line["legs"] = legs
+            if "align" in legs:
+                line["align"] = legs["align"]  # the "with traceback" half of the metric, also at top level
         print(json.dumps(line), flush=True)
-    prof.close()
-    if distributed:
-        dist.destroy_process_group()
+    if ctx.distributed:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":
