@@ -41,7 +41,9 @@ DPX_INSTR_PER_CELL = 2.25  # 4.5 DPX/ALU instructions per packed cell pair (DESI
 
 # Result checksums of the default workloads at N = 1 (sum of scores [+ ranges + CIGAR words], mod 2^64).  A sharded
 # run must reproduce them: the results do not depend on how the reads are split over GPUs.
-EXPECTED_CHECKSUM = {("cfg2", "score", 1_000_000): 268486591}
+EXPECTED_CHECKSUM = {("cfg2", "score", 1_000_000): 268486591, ("cfg3", "align", 1_000_000): 4405153473,
+                     ("cfg5", "score", 1_000_000): 767435248, ("cfg1", "score", 10_000): 1466752,
+                     ("cfg4", "score", 20_000): 23653328}
 
 
 def env_int(name, default):
@@ -51,9 +53,23 @@ def env_int(name, default):
         return default
 
 
+SCORING = None  # --scoring match,mismatch,gap_open,gap_extend (DNA configurations): e.g. 4,-2,-3,-1 = tie-heavy
+
+
 def make_workload(config: int, n_override: int | None):
     """Returns (key, name, matrix, gap_open, gap_extend, targets, (buf, offs), mode).  The data depend on the
     configuration only -- never on the rank: every rank generates the same set and takes its shard of it."""
+    w = _make_workload(config, n_override)
+    if SCORING and config != 5:
+        from zoe_b200 import WeightMatrix
+        ma, mi, go, ge = SCORING
+        key, name, _, _, _, t, batch, mode = w
+        return (key + f"/scoring{ma},{mi},{go},{ge}", name + f" [scoring match {ma} mismatch {mi} open {go} extend {ge}]",
+                WeightMatrix.new_dna_matrix(ma, mi, b"N"), go, ge, t, batch, mode)
+    return w
+
+
+def _make_workload(config: int, n_override: int | None):
     from zoe_b200 import BLOSUM_62, WeightMatrix, synth
 
     dna = WeightMatrix.new_dna_matrix(2, -5, b"N")
@@ -330,7 +346,7 @@ def run_leg(ctx: Ctx, config: int, mode_override, n_override, steps: int, warmup
             keep.append(t)
             outs[k] = a
     if mode in ("align", "3pass"):
-        cap = pairs * 8 + 1024
+        cap = pairs * (64 if SCORING else 8) + 1024  # tie-heavy scorings fragment the CIGARs
         t, a = pinned(torch, np.zeros(pairs + 1, dtype=np.int64))
         keep.append(t)
         outs["cigar_off"] = a.view(np.uint64)
@@ -584,7 +600,12 @@ def main():
     ap.add_argument("--leg-steps", type=int, default=5)
     ap.add_argument("--parity", default="full", choices=["full", "sample"],
                     help="full: cfg 1 / 3 / 5 are checked on the whole set (SURVEY 8(d)); sample: a bounded prefix")
+    ap.add_argument("--scoring", default=None, help="match,mismatch,gap_open,gap_extend for the DNA configurations "
+                                                    "(e.g. 4,-2,-3,-1: many E == H == F ties -> literal striped kernels)")
     args = ap.parse_args()
+    if args.scoring:
+        global SCORING
+        SCORING = tuple(int(v) for v in args.scoring.split(","))
     args.warmup = max(args.warmup, 0)
     headline_alone = args.config is not None
     if args.config is None:

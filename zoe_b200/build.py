@@ -13,6 +13,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
     "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-cudart", "shared",
+    "-split-compile", str(min(os.cpu_count() or 1, 16)),  # one translation unit, many kernels: optimise them in parallel
 ]
 
 

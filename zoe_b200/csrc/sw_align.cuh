@@ -342,13 +342,13 @@ __global__ void sw_traceback_kernel(const TraceParams t) {
         t.hazard[gid] = 1;
         atomicAdd(&t.counters[8], 1ULL);
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
-        t.hazard_list[slot] = (uint32_t)gid;
+        t.hazard_list[slot] = (uint32_t)gid | 0x80000000u;  // no exact end cell yet
         return;
     }
     if (e.best == 0 || n == 0) {
         t.score[gid] = 0;
         t.status[gid] = 2;  // Unmapped
-        t.tier[gid] = 8;
+        t.tier[gid] = t.tp.first;
         t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
         return;
     }
@@ -441,7 +441,9 @@ __global__ void sw_traceback_kernel(const TraceParams t) {
 // literal striped emulation: one warp per pair
 // ---------------------------------------------------------------------------------------------
 struct ExactParams {
-    const uint32_t *pair_ids;   // global pair ids
+    const uint32_t *pair_ids;   // the literal list: global pair ids (bit 31: "no exact end cell yet", ignored here)
+    const uint32_t *pos_list;   // optional: positions into pair_ids to process (else 0 .. n_pairs)
+    const uint32_t *n_pairs_dev;  // optional: device-side length of pos_list (else n_pairs)
     uint32_t n_pairs;
     const uint8_t *rseq;
     const uint64_t *roff;
@@ -483,8 +485,10 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
     const int lane = threadIdx.x & 31;
     constexpr unsigned FULL = 0xffffffffu;
 
-    for (uint32_t pi = slot; pi < x.n_pairs; pi += n_slots) {
-        const uint32_t gid = x.pair_ids[pi];
+    const uint32_t n_pairs = x.n_pairs_dev ? *x.n_pairs_dev : x.n_pairs;
+    for (uint32_t pq = slot; pq < n_pairs; pq += n_slots) {
+        const uint32_t pi = x.pos_list ? x.pos_list[pq] : pq;  // position in the literal list = CIGAR scratch row
+        const uint32_t gid = x.pair_ids[pi] & 0x7fffffffu;
         const uint32_t seq = gid / x.n_cseq, cj = gid % x.n_cseq;
         const uint8_t *R = x.rseq + x.roff[seq];
         const int n = (int)(x.roff[seq + 1] - x.roff[seq]);
@@ -659,7 +663,7 @@ __global__ void __launch_bounds__(128) sw_align_exact_kernel(const ExactParams x
         }
         __syncwarp();
 #ifdef ZOE_EXACT_PROFILE
-        if (lane == 0 && pi == 0)
+        if (lane == 0 && pq == 0)
             printf("exact profile: N %d nv %d rows %d main %lld lazy %lld publish+reduce %lld loop-total %lld cycles\n", N, nv, n,
                    t_main, t_lazy, t_pub, clock64() - t_all0);
 #endif
@@ -863,7 +867,7 @@ __global__ void cigar_gather_kernel(const uint32_t *scratch, uint32_t cig_cap, c
                                     const uint8_t *skip) {
     const uint32_t slot = blockIdx.x;
     if (slot >= n_slots) return;
-    const uint32_t gid = pair_of_slot ? pair_of_slot[slot] : slot_first_pair + slot;
+    const uint32_t gid = pair_of_slot ? (pair_of_slot[slot] & 0x7fffffffu) : slot_first_pair + slot;
     if (skip && skip[gid]) return;  // hazard pairs are gathered from the exact kernel's scratch
     const uint32_t cnt = count[gid];
     const uint64_t o = out_off[gid];

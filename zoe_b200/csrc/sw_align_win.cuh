@@ -445,6 +445,278 @@ __global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const
 }
 
 // ---------------------------------------------------------------------------------------------
+// pass A, two tasks per group: the forward scan above with TWO independent recurrences per thread.
+// ---------------------------------------------------------------------------------------------
+// With one profiled sequence per sweep (config 3) sw_align_scan_kernel carries one dependency chain per thread and
+// stalls on it (ncu: `wait` 1.9 cycles per issue, ALU pipe 83 %).  Here a group sweeps tasks 2t and 2t+1 side by side:
+// same column symbol, two score tables, two H / F register sets -- the instruction-level parallelism the two-stream score
+// kernel gets from its second profiled sequence.  Twice the shared memory per group, so 11 warps per SM instead of 16,
+// but 22 chains instead of 16.  Checkpoints, bookkeeping and the published (lane, step pair) are exactly those of the
+// one-task kernel, task by task, so the pin sweep, pass B and the walk do not change.
+template <int K>
+struct ScanChain {
+    uint32_t H[2][K], F[K];
+    uint32_t h_last, e_out, h_up_prev;
+    uint32_t bestp, firstp, lastp, cm, hp_pend;
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            H[0][i] = H[1][i] = 0;
+            F[i] = 0;
+        }
+        h_last = e_out = h_up_prev = 0;
+        bestp = firstp = lastp = cm = hp_pend = 0;
+    }
+};
+
+#define ZOE_SCAN_ROW(C, W)                                            \
+    {                                                                 \
+        const uint32_t x = O::max3(C##E, C.F[i], go_s) - go_s;        \
+        const uint32_t Hn = O::addmax(C##diag, W, x);                 \
+        C##diag = C.H[PO][i];                                         \
+        C##E = O::addmax(C##E, neg_ge, Hn);                           \
+        C.F[i] = O::addmax(C.F[i], neg_ge, Hn);                       \
+        C.H[PN][i] = Hn;                                              \
+        if ((i + PH) & 1)                                             \
+            C.cm = O::max3(C.cm, Hn, C##hp);                          \
+        else                                                          \
+            C##hp = Hn;                                               \
+    }
+
+template <int G, int K, bool CSM = true>
+__global__ void __launch_bounds__(K <= 13 ? 512 : 352) sw_align_scan2_kernel(const WinParams wp) {
+    using O = Ops<true>;
+    const ScoreParams &p = wp.s;
+    constexpr int K4 = (K + 3) / 4;
+    constexpr int CKW = 2 * K + 2;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    const int tid = threadIdx.x;
+    const int lig = tid % G;
+    const int group_in_block = tid / G;
+    const int groups_per_block = blockDim.x / G;
+
+    const TaskSmem sm0 = carve_and_stage<G, K4, 2>(smem, p, CSM);
+    const int tab_bytes = sm0.tab_bytes;
+    TaskSmem smA = sm0, smB = sm0;
+    smB.tab = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(sm0.tab) + tab_bytes);
+    const uint8_t *cc = CSM ? sm0.s_cc : p.ccodes;
+
+    uint32_t go_s = O::splat(p.go), neg_ge = O::splat(-p.ge);
+    const uint32_t cb_mask = (1u << wp.cb_log2) - 1u;
+    const bool lane0 = lig == 0;
+    uint32_t nz_lane = lane0 ? 0u : 1u;
+    const uint32_t one_s = O::splat(1);
+    uint32_t tabA_off = (uint32_t)group_in_block * (uint32_t)(2 * tab_bytes) + (uint32_t)lig * 16u;
+    uint32_t tabB_off = tabA_off + (uint32_t)tab_bytes;
+    asm volatile("" : "+r"(go_s), "+r"(neg_ge), "+r"(tabA_off), "+r"(tabB_off), "+r"(nz_lane));
+
+    const uint32_t n_duos = (p.n_tasks + 1) / 2;
+    const uint32_t total_groups = gridDim.x * groups_per_block;
+    const uint32_t trips = (n_duos + total_groups - 1) / total_groups;
+    const uint32_t first = blockIdx.x * groups_per_block + group_in_block;
+
+    for (uint32_t trip = 0; trip < trips; ++trip) {
+        const uint32_t duo = first + trip * total_groups;
+        uint32_t task[2] = {2 * duo, 2 * duo + 1};
+        bool valid[2];
+        uint32_t id_lo[2], id_hi[2];
+        uint64_t off_lo[2] = {0, 0}, off_hi[2] = {0, 0};
+        int len_lo[2] = {0, 0}, len_hi[2] = {0, 0};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            valid[t] = duo < n_duos && task[t] < p.n_tasks;
+            id_lo[t] = id_hi[t] = 0xffffffffu;
+            if (valid[t]) {
+                const uint32_t a = 2 * task[t], b = 2 * task[t] + 1;
+                id_lo[t] = wp.chunk_first + a;
+                id_hi[t] = (b < p.n_rseq) ? wp.chunk_first + b : 0xffffffffu;
+            }
+            if (id_lo[t] != 0xffffffffu) {
+                off_lo[t] = p.roff[id_lo[t]];
+                len_lo[t] = (int)(p.roff[id_lo[t] + 1] - off_lo[t]);
+            }
+            if (id_hi[t] != 0xffffffffu) {
+                off_hi[t] = p.roff[id_hi[t]];
+                len_hi[t] = (int)(p.roff[id_hi[t] + 1] - off_hi[t]);
+            }
+        }
+        build_task_table<G, K, true>(smA, p, lig, (int64_t)off_lo[0], len_lo[0], (int64_t)off_hi[0], len_hi[0]);
+        build_task_table<G, K, true>(smB, p, lig, (int64_t)off_lo[1], len_lo[1], (int64_t)off_hi[1], len_hi[1]);
+        uint32_t *ckA_task = wp.ckpt + (size_t)task[0] * wp.ckpt_task_stride;
+        uint32_t *ckB_task = wp.ckpt + (size_t)task[1] * wp.ckpt_task_stride;
+
+        for (uint32_t cj = 0; cj < p.n_cseq; ++cj) {
+            const uint32_t c0 = p.coff[cj];
+            const int L = (int)(p.coff[cj + 1] - c0);
+            const uint8_t *cs = cc + c0;
+            uint32_t *ckA = ckA_task + wp.ckpt_base[cj] + lig;
+            uint32_t *ckB = ckB_task + wp.ckpt_base[cj] + lig;
+
+            ScanChain<K> A, B;
+            A.reset();
+            B.reset();
+            const int nsteps = L + G - 1;
+
+            auto column2 = [&](auto parity, auto steady, const int j, const uint32_t ha_in, const uint32_t ea_in,
+                               const uint32_t hb_in, const uint32_t eb_in) {
+                constexpr int PO = decltype(parity)::value, PN = 1 - PO;
+                constexpr bool STEADY = decltype(steady)::value;
+                constexpr int PH = (STEADY && (K & 1)) ? PO : 0;
+                const uint32_t code_off = (uint32_t)cs[j] * (uint32_t)(K4 * G * 16);
+                const uint4 *tpA = reinterpret_cast<const uint4 *>(smem + tabA_off + code_off);
+                const uint4 *tpB = reinterpret_cast<const uint4 *>(smem + tabB_off + code_off);
+                uint32_t Adiag = A.h_up_prev, AE = ea_in, Ahp = A.hp_pend;
+                uint32_t Bdiag = B.h_up_prev, BE = eb_in, Bhp = B.hp_pend;
+#pragma unroll
+                for (int i4 = 0; i4 < K4; ++i4) {
+                    const uint4 wa4 = tpA[i4 * G], wb4 = tpB[i4 * G];
+                    const uint32_t wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w};
+                    const uint32_t wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = i4 * 4 + q;
+                        if (i < K) {
+                            ZOE_SCAN_ROW(A, wa[q])
+                            ZOE_SCAN_ROW(B, wb[q])
+                        }
+                    }
+                }
+                if (K & 1) {
+                    if (!STEADY) {
+                        A.cm = O::max2(A.cm, Ahp);
+                        B.cm = O::max2(B.cm, Bhp);
+                    } else if (PH == 0) {
+                        A.hp_pend = Ahp;
+                        B.hp_pend = Bhp;
+                    }
+                }
+                A.h_last = A.H[PN][K - 1];
+                A.e_out = AE;
+                B.h_last = B.H[PN][K - 1];
+                B.e_out = BE;
+            };
+            using SteadyT = std::true_type;
+            using GenericT = std::false_type;
+            using I0 = std::integral_constant<int, 0>;
+            using I1 = std::integral_constant<int, 1>;
+            auto bookkeeping = [&](ScanChain<K> &C, const uint32_t s_even) {
+                const uint32_t pp = (s_even >> 1) * 0x00010001u;
+                const uint32_t m = O::max2(C.cm, C.bestp);
+                const uint32_t inc = O::min2(m - C.bestp, one_s) * 0xffffu;
+                const uint32_t ge = (one_s - O::min2(m - C.cm, one_s)) * 0xffffu;
+                C.firstp = (C.firstp & ~inc) | (pp & inc);
+                C.lastp = (C.lastp & ~ge) | (pp & ge);
+                C.bestp = m;
+                C.cm = 0;
+            };
+            auto generic_step = [&](auto parity, const int s) {
+                const uint32_t ha = __shfl_up_sync(FULL, A.h_last, 1, G) * nz_lane, ea = __shfl_up_sync(FULL, A.e_out, 1, G) * nz_lane;
+                const uint32_t hb = __shfl_up_sync(FULL, B.h_last, 1, G) * nz_lane, eb = __shfl_up_sync(FULL, B.e_out, 1, G) * nz_lane;
+                const int j = s - lig;
+                if (j >= 0 && j < L) {
+                    column2(parity, GenericT{}, j, ha, ea, hb, eb);
+                    bookkeeping(A, (uint32_t)s & ~1u);
+                    bookkeeping(B, (uint32_t)s & ~1u);
+                }
+                A.h_up_prev = ha;
+                B.h_up_prev = hb;
+            };
+            auto checkpoint = [&](const ScanChain<K> &C, uint32_t *ck, const int s) {
+                uint32_t *dst = ck + (size_t)(((uint32_t)s >> wp.cb_log2) - 1) * (CKW * G);
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    dst[i * G] = C.H[0][i];
+                    dst[(K + i) * G] = C.F[i];
+                }
+                dst[(2 * K) * G] = C.e_out;
+                dst[(2 * K + 1) * G] = C.h_up_prev;
+            };
+
+            int s = 0;
+            const int s_steady = min(G, nsteps);
+            for (; s < s_steady; ++s) {
+                if (s & 1)
+                    generic_step(I1{}, s);
+                else
+                    generic_step(I0{}, s);
+            }
+            for (; s + 1 < L; s += 2) {
+                if ((((uint32_t)s) & cb_mask) == 0) {
+                    if (valid[0]) checkpoint(A, ckA, s);
+                    if (valid[1]) checkpoint(B, ckB, s);
+                }
+                {
+                    const uint32_t ha = __shfl_up_sync(FULL, A.h_last, 1, G) * nz_lane, ea = __shfl_up_sync(FULL, A.e_out, 1, G) * nz_lane;
+                    const uint32_t hb = __shfl_up_sync(FULL, B.h_last, 1, G) * nz_lane, eb = __shfl_up_sync(FULL, B.e_out, 1, G) * nz_lane;
+                    column2(I0{}, SteadyT{}, s - lig, ha, ea, hb, eb);
+                    A.h_up_prev = ha;
+                    B.h_up_prev = hb;
+                }
+                {
+                    const uint32_t ha = __shfl_up_sync(FULL, A.h_last, 1, G) * nz_lane, ea = __shfl_up_sync(FULL, A.e_out, 1, G) * nz_lane;
+                    const uint32_t hb = __shfl_up_sync(FULL, B.h_last, 1, G) * nz_lane, eb = __shfl_up_sync(FULL, B.e_out, 1, G) * nz_lane;
+                    column2(I1{}, SteadyT{}, s + 1 - lig, ha, ea, hb, eb);
+                    A.h_up_prev = ha;
+                    B.h_up_prev = hb;
+                }
+                bookkeeping(A, (uint32_t)s);
+                bookkeeping(B, (uint32_t)s);
+            }
+            for (; s < nsteps; ++s) {
+                if ((((uint32_t)s) & cb_mask) == 0 && s >= G && s < L) {
+                    if (valid[0]) checkpoint(A, ckA, s);
+                    if (valid[1]) checkpoint(B, ckB, s);
+                }
+                if (s & 1)
+                    generic_step(I1{}, s);
+                else
+                    generic_step(I0{}, s);
+            }
+
+            // ---- per task: the lowest lane holding the group's maximum wins; publish (lane, first / last step pair) ----
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t bestp = t == 0 ? A.bestp : B.bestp, firstp = t == 0 ? A.firstp : B.firstp,
+                               lastp = t == 0 ? A.lastp : B.lastp;
+                uint32_t key_lo = ((bestp & 0xffffu) << 8) | (uint32_t)(G - 1 - lig);
+                uint32_t key_hi = ((bestp >> 16) << 8) | (uint32_t)(G - 1 - lig);
+#pragma unroll
+                for (int d = G / 2; d >= 1; d >>= 1) {
+                    key_lo = max(key_lo, __shfl_xor_sync(FULL, key_lo, d, G));
+                    key_hi = max(key_hi, __shfl_xor_sync(FULL, key_hi, d, G));
+                }
+                const int wl_lo = G - 1 - (int)(key_lo & 0xffu), wl_hi = G - 1 - (int)(key_hi & 0xffu);
+                const uint32_t f_lo = __shfl_sync(FULL, firstp, wl_lo, G) & 0xffffu, l_lo = __shfl_sync(FULL, lastp, wl_lo, G) & 0xffffu;
+                const uint32_t f_hi = __shfl_sync(FULL, firstp, wl_hi, G) >> 16, l_hi = __shfl_sync(FULL, lastp, wl_hi, G) >> 16;
+                if (lig == 0 && valid[t]) {
+                    if (id_lo[t] != 0xffffffffu) {
+                        AlignEnd e;
+                        const int b = (int)(key_lo >> 8);
+                        e.best = (b >= p.ovf_thresh) ? -1 : b;
+                        e.r_end = (uint32_t)wl_lo;
+                        e.c_end = 2u * f_lo;
+                        e.aux = 2u * l_lo;
+                        wp.ends[(size_t)id_lo[t] * p.n_cseq + cj] = e;
+                    }
+                    if (id_hi[t] != 0xffffffffu) {
+                        AlignEnd e;
+                        const int b = (int)(key_hi >> 8);
+                        e.best = (b >= p.ovf_thresh) ? -1 : b;
+                        e.r_end = (uint32_t)wl_hi;
+                        e.c_end = 2u * f_hi;
+                        e.aux = 2u * l_hi;
+                        wp.ends[(size_t)id_hi[t] * p.n_cseq + cj] = e;
+                    }
+                }
+            }
+        }
+    }
+}
+#undef ZOE_SCAN_ROW
+
+// ---------------------------------------------------------------------------------------------
 // pairing: classify every pair of the chunk, counting-sort the mapped ones by (profiled, block)
 // ---------------------------------------------------------------------------------------------
 struct ClassifyParams {
@@ -505,14 +777,14 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
         t.hazard[gid] = 1;
         atomicAdd(&t.counters[8], 1ULL);
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
-        t.hazard_list[slot] = (uint32_t)gid;
+        t.hazard_list[slot] = (uint32_t)gid | 0x80000000u;  // no exact end cell yet
         t.ends[gid].aux = kNotBucketed;
         return;
     }
     if (e.best == 0 || n == 0) {
         t.score[gid] = 0;
         t.status[gid] = 2;  // Unmapped
-        t.tier[gid] = 8;
+        t.tier[gid] = t.tp.first;
         t.ref_start[gid] = t.ref_end[gid] = t.query_start[gid] = t.query_end[gid] = 0;
         t.ends[gid].aux = kNotBucketed;
         return;
@@ -531,7 +803,7 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
     t.tier[gid] = tier;
     if (t.all_exact) {
         unsigned long long slot = atomicAdd(&t.counters[5], 1ULL);
-        t.hazard_list[slot] = (uint32_t)gid;
+        t.hazard_list[slot] = (uint32_t)gid | 0x80000000u;  // pass A's (lane, step pair) is not an end cell
         t.hazard[gid] = 1;
         t.ends[gid].aux = kNotBucketed;
         return;

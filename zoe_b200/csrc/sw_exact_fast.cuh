@@ -1,0 +1,452 @@
+// sw_exact_fast.cuh -- throughput version of the literal striped emulation (sm_100a).
+//
+// Same contract as sw_align_exact_kernel (sw_align.cuh): zoe's sw_simd_align (src/alignment/sw/striped.rs:449-598) run
+// at the lane count N of the pair's score tier, flag for flag, so that CIGAR tie-breaks that depend on the striped lane
+// layout come out as zoe's.  The old kernel spends 2-5 ms per 150 x 1704 pair (one warp per pair, every access a
+// dependent load, flags of the whole matrix through global memory); a workload with a few per cent of tie hazards
+// (small weights, cheap gaps) then pays more for the literal pairs than for everything else.  Differences here:
+//
+//   * thread = SIMD lane, but a warp carries 32 / N pairs (N = 16: two, N = 8: four), and a CTA up to 24 pairs, each
+//     with its H row, E row, current flag row (and, for multi-sequence panels, its profiled symbol indices) in shared
+//     memory as 16-bit / 8-bit values: 6 bytes per profiled residue instead of 18;
+//   * one H buffer instead of zoe's load / store pair (row r-1's value is read into a register one step before it is
+//     overwritten), no max_row copy: the end cell is known from the canonical pass (H is layout independent), or, for
+//     the pairs that never had one (packed overflow), tracked per row;
+//   * the main loop is software pipelined: the loads of vector v+1 are issued before the stores of vector v;
+//   * only the flags the walk can reach leave the SM: rows 0..r_end, columns [c_lo, c_end] with c_lo from the score
+//     bound on column-only moves (the same bound the window pipeline uses) -- about 150 x 170 bytes instead of 150 x 1704;
+//   * the walk runs in a second kernel, one thread per pair, so its dependent loads overlap across thousands of pairs
+//     instead of stalling a DP warp.
+//
+// Values are true (un-offset) scores: zoe keeps x + T::MIN and saturates, which is a clamp at 0 here; saturation at MAX
+// cannot happen because the tier was chosen from the exact score.  Tiers 8 and 16 only (values < 65535 fit the 16-bit
+// rows) with N <= 32; everything else stays with sw_align_exact_kernel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "sw_align.cuh"
+
+namespace zoe_cuda {
+
+constexpr uint32_t kEndUnknown = 0x80000000u;  // hazard_list entry flag: the pair has no exact end cell yet
+
+struct ExactFastParams {
+    const uint32_t *list;         // positions into hazard_list of this launch's pairs
+    uint32_t list_count;          // pairs of this round
+    const uint32_t *hazard_list;  // global pair id | kEndUnknown
+    const uint8_t *rseq;
+    const uint64_t *roff;
+    const uint8_t *pbytes;        // profiled sequences, raw bytes
+    const uint32_t *coff;
+    uint32_t n_cseq;
+    const int8_t *weights;        // S*S zoe weights[ref_idx][query_idx]
+    int S;
+    const uint8_t *lut;
+    int go, ge;                   // positive
+    int maxw;
+    int N;                        // SIMD lanes of this tier (power of two, <= 32)
+    uint32_t vcap;                // shared-memory row capacity per pair (elements), >= nv * N for every profiled sequence
+    int invert;
+    AlignEnd *ends;               // in: exact end cell (known-end launches); out: exact end cell (FULL launches)
+    const uint32_t *score_in;     // exact score (decides the tier; checked against the recomputed value)
+    uint8_t *fbuf;                // [round slot][fcap] flag bytes, row stride wcap
+    uint64_t fcap;
+    uint32_t wcap;
+    // walk outputs (same arrays as TraceParams)
+    uint32_t *ref_start, *ref_end, *query_start, *query_end;
+    uint32_t *cig_scratch;        // [hazard_list position][cig_cap]
+    uint32_t *cig_count;
+    uint32_t cig_cap;
+    unsigned long long *counters; // [6] cigar overflow, [7] score mismatch (internal check)
+    uint32_t *retry_list;         // walks that left their flag window go back to sw_align_exact_kernel (hazard_list positions)
+    uint32_t *retry_count;
+};
+
+// Rows and columns of flags the walk of a pair can reach.  With the end cell known: rows 0..r_end; the walk follows
+// one alignment of score S over n_r = r_end + 1 rows, whose column-only moves I satisfy
+// S <= n_r * maxw - go - (I - 1) * ge (one gap run is the cheapest way to spend them), so it stays right of
+// c_end + 1 - (n_r + I + 1).  Unknown end: everything.
+__host__ __device__ inline void exact_window(bool end_known, uint32_t r_end, uint32_t c_end, uint32_t score, uint32_t n,
+                                             uint32_t m, int maxw, int go, int ge, uint32_t &n_rows, uint32_t &c_lo,
+                                             uint32_t &width) {
+    if (!end_known) {
+        n_rows = n;
+        c_lo = 0;
+        width = m;
+        return;
+    }
+    n_rows = r_end + 1;
+    c_lo = 0;
+    if (ge > 0) {
+        const long long num = (long long)n_rows * maxw - go - (long long)score;
+        const long long imax = num >= 0 ? 1 + num / ge : 0;
+        const long long need = (long long)n_rows + imax + 1;
+        if ((long long)c_end + 1 > need) c_lo = (uint32_t)((long long)c_end + 1 - need);
+    }
+    width = c_end - c_lo + 1;
+}
+
+// Shared memory per CTA: [groups x (H u16[vcap], E u16[vcap], flags u8[vcap], (pidx u8[vcap]))]
+//                        [shared pidx u8[vcap] when n_cseq == 1][weights (S+1) x (S+1) i8][lut 256]
+// The group stride is 2N bytes past a multiple of 128, so the 32 / N groups of a warp hit disjoint banks.
+__host__ __device__ inline size_t exact_fast_group_bytes(uint32_t vcap, bool pidx_shared, int N) {
+    return (((size_t)vcap * (pidx_shared ? 5 : 6) + 127) & ~(size_t)127) + (N < 32 ? 2 * (size_t)N : 0);
+}
+__host__ __device__ inline size_t exact_fast_fixed_bytes(uint32_t vcap, int S, bool pidx_shared) {
+    return (pidx_shared ? (size_t)vcap : 0) + (size_t)((S + 1) * (S + 1) + 15) / 16 * 16 + 256;
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParams x) {
+    extern __shared__ __align__(16) uint8_t xs[];
+    constexpr unsigned ALL = 0xffffffffu;
+    const int N = x.N;
+    const int lig = threadIdx.x & (N - 1);
+    const int group = threadIdx.x / N, groups = blockDim.x / N;
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (N == 32 ? ALL : ((1u << N) - 1u)) << (lane & ~(N - 1));
+    const bool pidx_shared = x.n_cseq == 1;
+    const uint32_t vcap = x.vcap;
+    const int S1 = x.S + 1;
+
+    uint8_t *gbase = xs + (size_t)group * exact_fast_group_bytes(vcap, pidx_shared, N);
+    uint16_t *hrow = reinterpret_cast<uint16_t *>(gbase);
+    uint16_t *es = hrow + vcap;
+    uint8_t *frow = reinterpret_cast<uint8_t *>(es + vcap);
+    uint8_t *fixed = xs + (size_t)groups * exact_fast_group_bytes(vcap, pidx_shared, N);
+    uint8_t *pidx = pidx_shared ? fixed : frow + vcap;
+    int8_t *wtab = reinterpret_cast<int8_t *>(fixed + (pidx_shared ? vcap : 0));
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(wtab) + ((S1 * S1 + 15) / 16) * 16;
+
+    // weights with one extra all-zero row / column: the profile pads residues beyond the sequence with weight 0
+    for (int i = threadIdx.x; i < S1 * S1; i += blockDim.x) {
+        const int a = i / S1, b = i % S1;
+        wtab[i] = (a < x.S && b < x.S) ? x.weights[a * x.S + b] : 0;
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = x.lut[i];
+    if (pidx_shared) {  // one profiled sequence: its striped symbol indices are the same for every pair of the CTA
+        const int m = (int)(x.coff[1] - x.coff[0]);
+        const int nv = (m + N - 1) / N;
+        for (int i = threadIdx.x; i < nv * N; i += blockDim.x) {
+            const int v = i / N, l = i % N, c = l * nv + v;
+            pidx[i] = c < m ? x.lut[x.pbytes[x.coff[0] + c]] : (uint8_t)x.S;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t total_groups = gridDim.x * groups;
+    const uint32_t trips = (x.list_count + total_groups - 1) / total_groups;
+    const uint32_t first = blockIdx.x * groups + group;
+
+    for (uint32_t trip = 0; trip < trips; ++trip) {
+        const uint32_t slot = first + trip * total_groups;  // round slot = index into this round's list
+        const bool valid = slot < x.list_count;
+        uint32_t pos = 0, gid = 0;
+        int n = 0, m = 0, nv = 0;
+        const uint8_t *R = x.rseq, *P = x.pbytes;
+        uint32_t want = 0, r_end_in = 0, c_end_in = 0;
+        if (valid) {
+            pos = x.list[slot];
+            gid = x.hazard_list[pos] & ~kEndUnknown;
+            const uint32_t seq = gid / x.n_cseq, cj = gid % x.n_cseq;
+            R = x.rseq + x.roff[seq];
+            n = (int)(x.roff[seq + 1] - x.roff[seq]);
+            P = x.pbytes + x.coff[cj];
+            m = (int)(x.coff[cj + 1] - x.coff[cj]);
+            nv = (m + N - 1) / N;
+            want = x.score_in[gid];
+            if (!FULL) {
+                const AlignEnd e = x.ends[gid];
+                r_end_in = e.r_end;
+                c_end_in = e.c_end;
+            }
+        }
+        uint32_t n_rows, c_lo, width;
+        exact_window(!FULL, r_end_in, c_end_in, want, (uint32_t)n, (uint32_t)m, x.maxw, x.go, x.ge, n_rows, c_lo, width);
+        if (!valid) n_rows = 0;
+        // loop bounds are warp-uniform (the groups of a warp advance in lock step, idle where they have nothing to do)
+        const int rows_w = (int)__reduce_max_sync(ALL, n_rows);
+        const int nv_w = (int)__reduce_max_sync(ALL, (unsigned)nv);
+
+        for (int i = lig; i < nv * N; i += N) {
+            hrow[i] = 0;
+            es[i] = 0;
+            if (!pidx_shared) {
+                const int v = i / N, l = i % N, c = l * nv + v;
+                pidx[i] = c < m ? s_lut[P[c]] : (uint8_t)x.S;
+            }
+        }
+        // first window column of this lane and its striped coordinates (the same for every row)
+        uint8_t *fdst = x.fbuf + (size_t)slot * x.fcap;
+        const int t0 = lig;  // window offsets t0, t0 + N, ...
+        int pv0 = 0, pl0 = 0;
+        if (valid && nv > 0) {
+            const int c0 = (int)c_lo + t0;
+            pl0 = c0 / nv;
+            pv0 = c0 - pl0 * nv;
+        }
+        __syncwarp();
+
+        int best = 0, r_best = n > 0 ? n - 1 : 0, c_best = m > 0 ? m - 1 : 0;  // FULL: zoe's defaults (striped.rs:476, 573)
+        const int go = x.go, ge = x.ge;
+
+        for (int r = 0; r < rows_w; ++r) {
+            const bool row_on = r < (int)n_rows;
+            const int8_t *wrow = wtab + (row_on ? (int)s_lut[R[r]] : x.S) * S1;
+            // H = store[nv-1].shift_elements_right(MIN): the final H of row r-1 at column l*nv - 1
+            int Hd = (row_on && lig > 0) ? (int)hrow[(nv - 1) * N + lig - 1] : 0;
+            __syncwarp();
+            int F = 0, rowmax = 0;
+            // software pipeline: the symbol index is fetched two vectors ahead, weight / E / previous H one vector ahead,
+            // all before vector v is stored -- no load sits on the F -> H -> F chain
+            int w_n = 0, E_n = 0, Hp_n = 0, pi_n = x.S;
+            if (row_on && nv > 0) {
+                w_n = wrow[pidx[lig]];
+                E_n = es[lig];
+                Hp_n = hrow[lig];
+                if (nv > 1) pi_n = pidx[N + lig];
+            }
+#pragma unroll 4
+            for (int v = 0; v < nv_w; ++v) {
+                const bool on = row_on && v < nv;
+                const int w = w_n, E = E_n, Hp = Hp_n;
+                const int idx = v * N + lig;
+                if (row_on && v + 1 < nv) {
+                    w_n = wrow[pi_n];
+                    E_n = es[idx + N];
+                    Hp_n = hrow[idx + N];
+                    if (v + 2 < nv) pi_n = pidx[idx + 2 * N];
+                }
+                if (on) {
+                    const int h = __vimax3_s32(Hd + w, E, F);             // saturating_add floors at MIN = 0 <= E, F
+                    const int ho = __viaddmax_s32(h, -go, 0);
+                    const int E2 = __viaddmax_s32(E, -ge, ho);
+                    const int F2 = __viaddmax_s32(F, -ge, ho);
+                    uint32_t fl = (uint32_t)(E == h) | ((uint32_t)(F == h) << 2) | ((uint32_t)(E2 > ho) << 1) |
+                                  ((uint32_t)(F2 > ho) << 3);
+                    if (h == 0) fl = 16u;
+                    rowmax = max(rowmax, h);
+                    hrow[idx] = (uint16_t)h;
+                    es[idx] = (uint16_t)E2;
+                    frow[idx] = (uint8_t)fl;
+                    F = F2;
+                    Hd = Hp;
+                }
+            }
+            // ---- lazy-F (striped.rs:528-553): every group runs its own (pass, vector) counters.  Within a pass F only
+            //      decays (F -= gap_extend per vector, independent of H) and every vector is visited once, so the
+            //      "does any lane still improve?" tests of U consecutive vectors are independent of each other: they are
+            //      evaluated together (U loads, U votes in flight) and the updates applied up to the first vector whose
+            //      vote fails -- the serial vote-per-vector loop was 90 % of the kernel's time on high-scoring rows ----
+            {
+                constexpr int U = 8;
+                bool live = row_on && nv > 0;
+                int pass = 0, v = 0;
+                int Fl = 0;
+                bool fresh = true;  // a new pass starts: F = F.shift_elements_right(MIN)
+                while (__any_sync(ALL, live)) {
+                    const int Fs = __shfl_up_sync(ALL, fresh ? F : 0, 1, N);
+                    if (live && fresh) {
+                        Fl = lig == 0 ? 0 : Fs;
+                        fresh = false;
+                    }
+                    const int cnt = live ? min(U, nv - v) : 0;
+                    int hh[U];
+                    unsigned votes[U];
+#pragma unroll
+                    for (int k = 0; k < U; ++k) hh[k] = k < cnt ? (int)hrow[(v + k) * N + lig] : 0;
+#pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        const int Fk = max(Fl - k * ge, 0);
+                        const bool trig = k < cnt && Fk > __viaddmax_s32(hh[k], -go, 0);
+                        votes[k] = __ballot_sync(ALL, trig) & gmask;
+                    }
+                    int stop = cnt;
+#pragma unroll
+                    for (int k = U - 1; k >= 0; --k)
+                        if (k < cnt && votes[k] == 0) stop = k;
+#pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        if (k < stop) {
+                            const int idx = (v + k) * N + lig;
+                            const int Fk = max(Fl - k * ge, 0);
+                            const int h2 = max(hh[k], Fk);
+                            hrow[idx] = (uint16_t)h2;
+                            uint32_t fl = frow[idx];
+                            if (Fk == h2) fl = (fl & 2u) | 4u;  // simd_correct_and_set_left
+                            const int ho = __viaddmax_s32(h2, -go, 0);
+                            if (max(Fk - ge, 0) > ho) fl |= 8u;
+                            if (h2 == 0) fl = 16u;
+                            frow[idx] = (uint8_t)fl;
+                        }
+                    }
+                    if (live) {
+                        Fl = max(Fl - stop * ge, 0);
+                        v += stop;
+                        if (stop < cnt) {
+                            live = false;  // break 'lazy_f
+                        } else if (v == nv) {
+                            v = 0;
+                            F = Fl;  // the next pass shifts what this one left
+                            fresh = true;
+                            if (++pass == N) live = false;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- row maximum; FULL: best cell so far = (max H, min r, min c) (striped.rs:555-583) ----
+            int rb = rowmax;
+            if (FULL || __any_sync(ALL, row_on && r == (int)r_end_in))
+                for (int d = N / 2; d >= 1; d >>= 1) rb = max(rb, __shfl_xor_sync(ALL, rb, d, N));
+            if (FULL) {
+                const bool improved = row_on && rb > best;
+                if (__any_sync(ALL, improved)) {
+                    int cmin = 0x7fffffff;
+                    if (improved) {
+                        for (int v = 0; v < nv; ++v)
+                            if ((int)hrow[v * N + lig] == rb) {
+                                const int c = lig * nv + v;
+                                if (c < m) cmin = c;
+                                break;
+                            }
+                    }
+                    for (int d = N / 2; d >= 1; d >>= 1) cmin = min(cmin, __shfl_xor_sync(ALL, cmin, d, N));
+                    if (improved) {
+                        best = rb;
+                        r_best = r;
+                        c_best = cmin != 0x7fffffff ? cmin : m - 1;
+                    }
+                }
+            } else if (row_on && r == (int)r_end_in && lig == 0) {
+                const int v = (int)c_end_in % nv, l = (int)c_end_in / nv;
+                if ((uint32_t)hrow[v * N + l] != want || (uint32_t)rb != want) atomicAdd(&x.counters[7], 1ULL);
+            }
+            // ---- publish the reachable part of the finished flag row ----
+            if (row_on) {
+                uint8_t *dst = fdst + (size_t)r * x.wcap;
+                int pv = pv0, pl = pl0;
+#pragma unroll 4
+                for (int t = t0; t < (int)width; t += N) {
+                    dst[t] = frow[pv * N + pl];
+                    pv += N;
+                    while (pv >= nv) {
+                        pv -= nv;
+                        ++pl;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (FULL && valid && lig == 0) {
+            if ((uint32_t)best != want) atomicAdd(&x.counters[7], 1ULL);
+            AlignEnd e;
+            e.best = best;
+            e.r_end = (uint32_t)r_best;
+            e.c_end = (uint32_t)c_best;
+            e.aux = kNotBucketed;
+            x.ends[gid] = e;
+        }
+        __syncwarp();
+    }
+}
+
+// zoe's walk (backtrack.rs:290-342) over the published flags: one thread per pair of the round.
+__global__ void sw_exact_walk_kernel(const ExactFastParams x, int full) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= x.list_count) return;
+    const uint32_t pos = x.list[slot];
+    const uint32_t gid = x.hazard_list[pos] & ~kEndUnknown;
+    const uint32_t seq = gid / x.n_cseq, cj = gid % x.n_cseq;
+    const uint32_t n = (uint32_t)(x.roff[seq + 1] - x.roff[seq]);
+    const uint32_t m = x.coff[cj + 1] - x.coff[cj];
+    const AlignEnd e = x.ends[gid];
+    uint32_t n_rows, c_lo, width;
+    exact_window(!full, e.r_end, e.c_end, x.score_in[gid], n, m, x.maxw, x.go, x.ge, n_rows, c_lo, width);
+    const uint8_t *fl = x.fbuf + (size_t)slot * x.fcap;
+    auto cell = [&](uint32_t rr, uint32_t cc) -> uint32_t { return fl[(size_t)rr * x.wcap + (cc - c_lo)]; };
+
+    CigarBack cg;
+    cg.init(x.cig_scratch + (size_t)pos * x.cig_cap, x.cig_cap);
+    const uint32_t OP_UP = x.invert ? 1u : 2u, OP_LEFT = x.invert ? 2u : 1u;
+    uint32_t r = e.r_end + 1, c = e.c_end + 1;
+    const uint32_t r_end1 = r, c_end1 = c;
+    cg.push(4u, x.invert ? (n - r_end1) : (m - c_end1));
+    uint32_t cur = cell(e.r_end, e.c_end);
+    int op = 0;
+    bool left_window = false;
+    while (!(cur & 16u) && r > 0 && c > 0) {
+        if (op == 1 && (cur & 2u)) {
+            r -= 1;
+        } else if (op == 2 && (cur & 8u)) {
+            c -= 1;
+        } else if (cur & 1u) {
+            op = 1;
+            r -= 1;
+        } else if (cur & 4u) {
+            op = 2;
+            c -= 1;
+        } else {
+            op = 3;
+            r -= 1;
+            c -= 1;
+        }
+        cg.push(op == 1 ? OP_UP : (op == 2 ? OP_LEFT : 0u), 1);
+        if (r == 0 || c == 0) break;  // zoe reads cell(max(r-1,0), max(c-1,0)) and then leaves the loop
+        if (c - 1 < c_lo) {
+            left_window = true;
+            break;
+        }
+        cur = cell(r - 1, c - 1);
+    }
+    if (left_window) {  // cannot happen while the score bound holds; kept as a safety net, not as a code path
+        x.retry_list[atomicAdd(x.retry_count, 1u)] = pos;
+        return;
+    }
+    cg.push(4u, x.invert ? r : c);
+    cg.flush();
+    if (cg.overflow) atomicAdd(&x.counters[6], 1ULL);
+    x.cig_count[gid] = cg.n;
+    if (x.invert) {
+        x.ref_start[gid] = c;
+        x.ref_end[gid] = c_end1;
+        x.query_start[gid] = r;
+        x.query_end[gid] = r_end1;
+    } else {
+        x.ref_start[gid] = r;
+        x.ref_end[gid] = r_end1;
+        x.query_start[gid] = c;
+        x.query_end[gid] = c_end1;
+    }
+}
+
+// Splits the literal list by what can run where: [0] tier 8, end known; [1] tier 16, end known; [2] tier 8, end unknown;
+// [3] tier 16, end unknown; [4] everything else that needs an alignment (tier 32, lane counts beyond a warp, rows that
+// do not fit shared memory) -> sw_align_exact_kernel.  Entries are positions into hazard_list (= the pair's row in the
+// literal kernels' CIGAR scratch).  Pairs beyond the widest allowed type need nothing.
+struct ExactPartitionParams {
+    const uint32_t *hazard_list;
+    uint32_t n;
+    const uint32_t *score;
+    TierPolicy tp;
+    int fast8, fast16;   // the fast kernel can take this tier
+    uint32_t *lists;     // 5 x n
+    uint32_t *counts;    // [5]
+};
+
+__global__ void exact_partition_kernel(const ExactPartitionParams q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.n) return;
+    const uint32_t ent = q.hazard_list[i];
+    const uint32_t gid = ent & ~kEndUnknown;
+    const uint8_t tier = tier_for(q.tp, q.score[gid]);
+    if (tier == 0) return;
+    int which = 4;
+    if (tier == 8 && q.fast8) which = (ent & kEndUnknown) ? 2 : 0;
+    if (tier == 16 && q.fast16) which = (ent & kEndUnknown) ? 3 : 1;
+    const uint32_t slot = atomicAdd(&q.counts[which], 1u);
+    q.lists[(size_t)which * q.n + slot] = i;
+}
+
+}  // namespace zoe_cuda

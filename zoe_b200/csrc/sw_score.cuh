@@ -155,14 +155,15 @@ struct TaskSmem {
 
 // Carves the dynamic shared memory, loads the LUT and the weights, stages the profiled symbol codes (one TMA bulk
 // copy per CTA) when `stage_cols`, and synchronises the CTA.  Must be called by every thread of the CTA.
-template <int G, int K4>
+// TPG = tables per group (2: the group sweeps two tasks side by side; `tab` is the first of the two, back to back).
+template <int G, int K4, int TPG = 1>
 __device__ __forceinline__ TaskSmem carve_and_stage(uint8_t *smem, const ScoreParams &p, bool stage_cols) {
     const int tid = threadIdx.x;
     const int group_in_block = tid / G, groups_per_block = blockDim.x / G;
     TaskSmem m;
     m.tab_bytes = p.n_csym * K4 * G * 16;
-    m.tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * m.tab_bytes);
-    m.s_lut = smem + (size_t)groups_per_block * m.tab_bytes;
+    m.tab = reinterpret_cast<uint4 *>(smem + (size_t)group_in_block * (TPG * m.tab_bytes));
+    m.s_lut = smem + (size_t)groups_per_block * (TPG * m.tab_bytes);
     m.s_wk = reinterpret_cast<int8_t *>(m.s_lut + 256);
     m.s_cc = reinterpret_cast<uint8_t *>(m.s_wk) + ((p.n_csym * p.S + 15) & ~15);
     for (int i = tid; i < 256; i += blockDim.x) m.s_lut[i] = p.lut[i];

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <chrono>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -22,8 +23,10 @@
 
 #include "sw_align.cuh"
 #include "sw_align_win.cuh"
+#include "sw_exact_fast.cuh"
 #include "sw_score.cuh"
 #include "sw_score_long.cuh"
+#include "sw_ends_long.cuh"
 #include "sw_score_rows.cuh"
 #include "sw_ranges.cuh"
 #include "sw_3pass.cuh"
@@ -84,7 +87,7 @@ struct Device {
     DevBuf rseq, roff, best, score, status, tier, wide_ids, counters;
     // align state
     DevBuf pbytes, ends, flags, flag_base, ref_start, ref_end, query_start, query_end, hazard, hazard_list;
-    DevBuf cig_scratch, cig_count, cig_off, cig_out, ex_hbuf, ex_fbuf, ex_cig, weights;
+    DevBuf cig_scratch, cig_count, cig_off, cig_out, ex_hbuf, ex_fbuf, ex_cig, weights, ex_lists, ex_counts, ex_fast_fbuf;
     // windowed align path (sw_align_win.cuh)
     DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems;
     DevBuf starts;  // ranges: reverse-pass results
@@ -112,6 +115,20 @@ struct KernelEntry {
     void (*scan_g)(const WinParams);     // pass A with the profiled symbol codes read from global memory (sets > 96 KB)
     void (*pin)(const WinParams);        // windowed align: exact best cell of the pairs whose maximum recurs
     void (*scan_rev)(const WinParams);   // ranges: reverse pass (score-rate scan + in-kernel pin)
+    void (*scan2)(const WinParams);      // pass A, two tasks per group (K <= 20), codes in shared memory / ...
+    void (*scan2_g)(const WinParams);    // ... codes from global memory
+};
+
+// the two-task pass A exists for K <= 20 (two H / F register sets per thread)
+template <int G, int K, bool ON>
+struct Scan2 {
+    static constexpr void (*smem())(const WinParams) { return sw_align_scan2_kernel<G, K, true>; }
+    static constexpr void (*gmem())(const WinParams) { return sw_align_scan2_kernel<G, K, false>; }
+};
+template <int G, int K>
+struct Scan2<G, K, false> {
+    static constexpr void (*smem())(const WinParams) { return nullptr; }
+    static constexpr void (*gmem())(const WinParams) { return nullptr; }
 };
 
 #define ZK(G, K) \
@@ -119,7 +136,8 @@ struct KernelEntry {
         G, K, sw_score_kernel<G, K, true, 1>, sw_score_kernel<G, K, false, 1>, sw_align_fill_kernel<G, K, true>, \
             sw_score_kernel<G, K, true, 2>, sw_align_scan_kernel<G, K>, sw_align_winfill_kernel<G, K>,     \
             sw_ends_kernel<G, K, true>, sw_ends_kernel<G, K, false>, sw_align_scan_kernel<G, K, false>,     \
-            sw_align_winfill_kernel<G, K, false>, sw_align_scan_kernel<G, K, true, true>                    \
+            sw_align_winfill_kernel<G, K, false>, sw_align_scan_kernel<G, K, true, true>,                   \
+            Scan2<G, K, (K <= 20)>::smem(), Scan2<G, K, (K <= 20)>::gmem()                                  \
     }
 
 // Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
@@ -136,10 +154,27 @@ constexpr int kMaxRowsSinglePass = 32 * 32;
 constexpr uint32_t kScanMaxCols = 131072 - 64;
 constexpr uint32_t kEndsMaxCols = (1u << 20) - 64;
 
+struct LaunchPlan {
+    int threads = 0, blocks_per_sm = 0;
+    size_t smem = 0;
+    int cols_in_smem = 0;
+};
+struct PlanKey {
+    const void *fn;
+    size_t cc_bytes;
+    int tabs_per_group;
+    bool operator<(const PlanKey &o) const {
+        if (fn != o.fn) return fn < o.fn;
+        if (cc_bytes != o.cc_bytes) return cc_bytes < o.cc_bytes;
+        return tabs_per_group < o.tabs_per_group;
+    }
+};
+
 }  // namespace
 
 struct zoe_cuda_ctx {
     std::vector<Device> devs;
+    std::map<PlanKey, LaunchPlan> plans;  // launch configurations, valid for the current scoring + profiled set
     // One extra stream + buffer set per GPU: zoe_cuda_sw_score_batch alternates sub-batches between devs[k] and alt[k]
     // so that the H2D copy of sub-batch i+1 and the D2H copy of sub-batch i-1 overlap the kernels of sub-batch i.
     std::vector<Device> alt;
@@ -254,10 +289,10 @@ __global__ void finalize_scores_kernel(const int32_t *best, uint64_t n, uint32_t
     if (i < n) {
         int32_t b = best[i];
         uint32_t s = (uint32_t)b;
-        uint8_t st = ZOE_CUDA_SOME, t = 8;
+        uint8_t st = ZOE_CUDA_SOME, t = tp.first;
         if (b <= 0) {
             s = 0;
-            st = ZOE_CUDA_UNMAPPED;  // Unmapped does not escalate: it is decided in the i8 tier
+            st = ZOE_CUDA_UNMAPPED;  // Unmapped does not escalate: it is decided in the first tier of the chain
             cun = 1;
         } else {
             t = tier_for(tp, s);
@@ -372,16 +407,11 @@ const KernelEntry *pick_score_kernel(uint32_t max_len, int n_csym) {
     return bestk;
 }
 
-struct LaunchPlan {
-    int threads = 0, blocks_per_sm = 0;
-    size_t smem = 0;
-    int cols_in_smem = 0;
-};
-
 constexpr size_t kColsSmemLimit = 96 * 1024;  // profiled symbol codes staged per CTA (leaves room for the task tables)
 
-size_t score_smem_bytes(const zoe_cuda_ctx *ctx, const KernelEntry &k, int threads, int cols_in_smem, size_t cc_bytes) {
-    size_t tab = (size_t)score_tab_bytes(ctx->n_csym, k.G, k.K) * (threads / k.G);
+size_t score_smem_bytes(const zoe_cuda_ctx *ctx, const KernelEntry &k, int threads, int cols_in_smem, size_t cc_bytes,
+                        int tabs_per_group = 1) {
+    size_t tab = (size_t)score_tab_bytes(ctx->n_csym, k.G, k.K) * (threads / k.G) * tabs_per_group;
     size_t s = tab + 256 + (((size_t)ctx->n_csym * ctx->S + 15) & ~(size_t)15);
     if (cols_in_smem) s += (cc_bytes + 15) & ~(size_t)15;
     return s;
@@ -389,8 +419,20 @@ size_t score_smem_bytes(const zoe_cuda_ctx *ctx, const KernelEntry &k, int threa
 
 // cc_bytes: symbol-code bytes the launch covers (default: the whole profiled set)
 template <class Fn>
-int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan, size_t cc_bytes = ~(size_t)0) {
+int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan, size_t cc_bytes = ~(size_t)0,
+                int tabs_per_group = 1) {
     if (cc_bytes == ~(size_t)0) cc_bytes = ctx->ccodes.size();
+    // occupancy queries and attribute changes cost tens of microseconds each: a plan is computed once per (kernel,
+    // profiled bytes) and reused until the scoring / profiled set changes (small batches are launch-bound otherwise)
+    const PlanKey key{(const void *)fn, cc_bytes, tabs_per_group};
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->plans.find(key);
+        if (it != ctx->plans.end()) {
+            *plan = it->second;
+            return 0;
+        }
+    }
     int best_warps = 0;
     LaunchPlan bp;
     cudaFuncAttributes fa{};
@@ -401,9 +443,9 @@ int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan
     for (int cols_in_smem = 1; cols_in_smem >= 0; --cols_in_smem) {
         if (cols_in_smem && cc_bytes > kColsSmemLimit) continue;
         static const int env_max_threads = getenv("ZOE_CUDA_MAX_THREADS") ? atoi(getenv("ZOE_CUDA_MAX_THREADS")) : 1024;
-        for (int threads : {512, 384, 256, 128, 64, 32}) {
+        for (int threads : {512, 448, 384, 352, 320, 288, 256, 224, 192, 160, 128, 96, 64, 32}) {
             if (threads < k.G || threads % k.G || threads > fa.maxThreadsPerBlock || threads > env_max_threads) continue;
-            size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem, cc_bytes);
+            size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem, cc_bytes, tabs_per_group);
             if (smem > 227 * 1024) continue;
             int nb = 0;
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -431,7 +473,27 @@ int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan
         return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no launch configuration fits shared memory (alphabet %d, G=%d K=%d)",
                     ctx->n_csym, k.G, k.K);
     *plan = bp;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->plans[key] = bp;
+    }
     return 0;
+}
+
+// Pass A of the windowed pipelines with two tasks per group (two dependency chains per thread).  MEASURED AND REJECTED on
+// cfg 3 (1M reads): 67.7 ms against 64.8 ms with the one-task kernel -- two score tables per group leave 11 warps per SM
+// instead of 16 (22 chains against 16), and the 168-register build spills.  Kept behind ZOE_CUDA_SCAN2 as a record.
+void pick_scan2(zoe_cuda_ctx *ctx, const KernelEntry &k, void (**scan_fn)(const WinParams), LaunchPlan *plan, int *tpg) {
+    static const bool off = getenv("ZOE_CUDA_SCAN2") == nullptr;
+    void (*fn2)(const WinParams) = plan->cols_in_smem ? k.scan2 : k.scan2_g;
+    if (off || !fn2) return;
+    LaunchPlan p2;
+    if (plan_launch(ctx, k, fn2, &p2, ~(size_t)0, 2) != 0) return;
+    if (p2.cols_in_smem != plan->cols_in_smem) return;
+    if (2 * p2.blocks_per_sm * p2.threads <= plan->blocks_per_sm * plan->threads) return;
+    *scan_fn = fn2;
+    *plan = p2;
+    *tpg = 2;
 }
 
 int upload_scoring_and_profiled(zoe_cuda_ctx *ctx) {
@@ -909,7 +971,7 @@ __global__ void apply_wide_scores_kernel(const uint32_t *list, uint32_t n, const
                                          uint8_t *status, uint8_t *tier, const TierPolicy tp) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t gid = list[i];
+    uint32_t gid = list[i] & 0x7fffffffu;
     if (status[gid] != 0xFF) return;
     int32_t b = best[gid];
     const uint8_t t = b > 0 ? tier_for(tp, (uint32_t)b) : tp.first;
@@ -973,6 +1035,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     const int NW = align_words_per_lane(k->K);
     const uint32_t n_prof = ctx->n_prof;
     const size_t pairs = (size_t)d.n_count * n_prof;
+    if (pairs >= 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "too many pairs for one align call");  // 31-bit pair ids
 
     // ---- which align pipeline? ----
     // The checkpointed-window pipeline pays when the profiled sequences are much longer than the walk can
@@ -1068,6 +1131,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         rc = plan_launch(ctx, *k, scan_fn, &plan);
         if (rc) return rc;
     }
+    int scan_tpg = 1;  // tasks a group sweeps side by side in pass A
+    if (use_window) pick_scan2(ctx, *k, &scan_fn, &plan, &scan_tpg);
     LaunchPlan plan_p;
     if (use_window) {
         rc = plan_launch(ctx, *k, k->winfill, &plan_b);
@@ -1160,21 +1225,135 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         t.hazard_list = d.hazard_list.as<uint32_t>();
         t.all_exact = all_exact ? 1 : 0;
         t.tp = ctx->tp;
-        // ---- literal striped emulation for hazard / overflow / gap_open == 0 pairs: list[first, first + count) ----
-        auto launch_exact = [&](uint32_t first, uint32_t count, uint32_t total_hint, cudaStream_t stream) -> int {
-            const uint32_t slots = (std::min<uint32_t>(std::max(count, 1u), (uint32_t)d.sm_count * 16) + 3u) & ~3u;  // whole blocks
+        // ---- literal striped emulation for hazard / overflow / gap_open == 0 pairs (the first n_exact entries of
+        //      hazard_list).  Tiers 8 / 16 with at most 32 lanes whose rows fit shared memory run in
+        //      sw_exact_fast_kernel + sw_exact_walk_kernel, in rounds sized by the scratch budget; the rest (tier 32,
+        //      64-lane presets, very long profiled sequences) in sw_align_exact_kernel. ----
+        auto launch_exact = [&](uint32_t n_exact, cudaStream_t stream) -> int {
+            const uint32_t n_rows_max = std::max<uint32_t>(ctx->staged_max_len, 1);
+            const uint64_t ex_budget = std::max<uint64_t>(std::min<uint64_t>(budget / 4, (uint64_t)4 << 30), (uint64_t)64 << 20);
+            CU(ctx, d.ex_cig.reserve((size_t)n_exact * cig_cap * sizeof(uint32_t)));
+            CU(ctx, d.ex_lists.reserve((size_t)5 * n_exact * sizeof(uint32_t)));
+            CU(ctx, d.ex_counts.reserve(8 * sizeof(uint32_t)));
+            CU(ctx, cudaMemsetAsync(d.ex_counts.p, 0, 8 * sizeof(uint32_t), stream));
+            // can the fast kernel hold a pair of this tier?  (lanes <= 32, one group's rows within the shared memory)
+            const bool pidx_shared = n_prof == 1;
+            auto fast_plan = [&](int N, uint32_t *vcap_out, int *groups_out, size_t *smem_out) -> bool {
+                if (N > 32 || getenv("ZOE_CUDA_EXACT_SLOW")) return false;
+                const uint32_t vcap = (((ctx->max_prof_len + N - 1) / N * N) + 31u) & ~31u;
+                const size_t gb = exact_fast_group_bytes(vcap, pidx_shared, N), fx = exact_fast_fixed_bytes(vcap, ctx->S, pidx_shared);
+                const size_t lim = 200 * 1024;
+                if (gb * (32 / N) + fx > lim) return false;
+                int groups = (int)std::min<size_t>((lim - fx) / gb, (size_t)(512 / N));
+                groups -= groups % (32 / N);  // whole warps
+                *vcap_out = vcap;
+                *groups_out = groups;
+                *smem_out = gb * groups + fx;
+                return groups > 0;
+            };
+            uint32_t vcap8 = 0, vcap16 = 0;
+            int groups8 = 0, groups16 = 0;
+            size_t smem8 = 0, smem16 = 0;
+            const bool fast8 = fast_plan(ctx->lanes[0], &vcap8, &groups8, &smem8);
+            const bool fast16 = fast_plan(ctx->lanes[1], &vcap16, &groups16, &smem16);
+            ExactPartitionParams q{};
+            q.hazard_list = d.hazard_list.as<uint32_t>();
+            q.n = n_exact;
+            q.score = t.score;
+            q.tp = ctx->tp;
+            q.fast8 = fast8;
+            q.fast16 = fast16;
+            q.lists = d.ex_lists.as<uint32_t>();
+            q.counts = d.ex_counts.as<uint32_t>();
+            exact_partition_kernel<<<(n_exact + 255) / 256, 256, 0, stream>>>(q);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+            uint32_t cnt[5] = {0, 0, 0, 0, 0};
+            CU(ctx, cudaMemcpyAsync(cnt, d.ex_counts.p, sizeof(cnt), cudaMemcpyDeviceToHost, stream));
+            CU(ctx, cudaStreamSynchronize(stream));
+            bool any_fast = false;
+            for (int which = 0; which < 4; ++which) {
+                if (cnt[which] == 0) continue;
+                any_fast = true;
+                const bool full = which >= 2;
+                const int N = (which & 1) ? ctx->lanes[1] : ctx->lanes[0];
+                const uint32_t vcap = (which & 1) ? vcap16 : vcap8;
+                const int groups = (which & 1) ? groups16 : groups8;
+                const size_t smem = (which & 1) ? smem16 : smem8;
+                // flag window capacity of one pair: the widest window any pair of this launch can have
+                uint32_t wcap = ctx->max_prof_len;
+                if (!full && ctx->ge > 0) {
+                    const uint64_t imax = 1 + ((uint64_t)n_rows_max * (uint64_t)std::max(ctx->max_weight, 0)) / (uint64_t)ctx->ge;
+                    wcap = (uint32_t)std::min<uint64_t>(wcap, (uint64_t)n_rows_max + imax + 2);
+                }
+                wcap = (wcap + 15u) & ~15u;
+                const uint64_t fcap = (uint64_t)n_rows_max * wcap;
+                const uint32_t round = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(cnt[which], ex_budget / fcap));
+                CU(ctx, d.ex_fast_fbuf.reserve((size_t)round * fcap));
+                ExactFastParams x{};
+                x.hazard_list = d.hazard_list.as<uint32_t>();
+                x.rseq = p.rseq;
+                x.roff = p.roff;
+                x.pbytes = d.pbytes.as<uint8_t>();
+                x.coff = p.coff;
+                x.n_cseq = n_prof;
+                x.weights = d.weights.as<int8_t>();
+                x.S = ctx->S;
+                x.lut = p.lut;
+                x.go = ctx->go;
+                x.ge = ctx->ge;
+                x.maxw = std::max(ctx->max_weight, 0);
+                x.N = N;
+                x.vcap = vcap;
+                x.invert = invert;
+                x.ends = d.ends.as<AlignEnd>();
+                x.score_in = t.score;
+                x.fbuf = d.ex_fast_fbuf.as<uint8_t>();
+                x.fcap = fcap;
+                x.wcap = wcap;
+                x.ref_start = t.ref_start;
+                x.ref_end = t.ref_end;
+                x.query_start = t.query_start;
+                x.query_end = t.query_end;
+                x.cig_scratch = d.ex_cig.as<uint32_t>();
+                x.cig_count = t.cig_count;
+                x.cig_cap = cig_cap;
+                x.counters = ctr;
+                x.retry_list = d.ex_lists.as<uint32_t>() + (size_t)4 * n_exact;
+                x.retry_count = d.ex_counts.as<uint32_t>() + 4;
+                auto fn = full ? sw_exact_fast_kernel<true> : sw_exact_fast_kernel<false>;
+                CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                for (uint32_t r0 = 0; r0 < cnt[which]; r0 += round) {
+                    x.list = d.ex_lists.as<uint32_t>() + (size_t)which * n_exact + r0;
+                    x.list_count = std::min<uint32_t>(round, cnt[which] - r0);
+                    const uint32_t blocks = std::min<uint32_t>((uint32_t)d.sm_count, (x.list_count + groups - 1) / groups);
+                    fn<<<blocks, groups * N, smem, stream>>>(x);
+                    CU(ctx, cudaGetLastError());
+                    sw_exact_walk_kernel<<<(x.list_count + 127) / 128, 128, 0, stream>>>(x, full ? 1 : 0);
+                    CU(ctx, cudaGetLastError());
+                    ctx->last_launches += 2;
+                }
+            }
+            uint32_t n_slow = cnt[4];
+            if (any_fast) {  // walks that left their window were appended to the slow list (none, unless the bound is wrong)
+                CU(ctx, cudaMemcpyAsync(&n_slow, d.ex_counts.as<uint32_t>() + 4, sizeof(n_slow), cudaMemcpyDeviceToHost, stream));
+                CU(ctx, cudaStreamSynchronize(stream));
+            }
+            if (n_slow == 0) return 0;
             const uint64_t vcap = ((uint64_t)ctx->max_prof_len + 64 + 3) & ~3ull;  // multiple of 4: rows stay word-aligned
-            const uint64_t fcap = (uint64_t)std::max<uint32_t>(ctx->staged_max_len, 1) * vcap;
-            // scratch: two disjoint slot regions (always both reserved, so nothing is reallocated while a launch on
-            // the second stream is in flight); the CIGAR rows of every listed pair must survive until the gather
-            const uint32_t region = (uint32_t)d.sm_count * 16 + 4;
-            const uint32_t slot_base = first ? region : 0;
-            CU(ctx, d.ex_hbuf.reserve((size_t)2 * region * 4 * vcap * sizeof(int32_t)));
-            CU(ctx, d.ex_fbuf.reserve((size_t)2 * region * fcap));
-            CU(ctx, d.ex_cig.reserve((size_t)std::max(total_hint, first + count) * cig_cap * sizeof(uint32_t)));
+            const uint64_t fcap = (uint64_t)n_rows_max * vcap;
+            // per-slot scratch of the literal kernel: the flag matrix and four H / E rows; as many slots as the budget
+            // allows (the kernel loops over the list), at least one block
+            uint32_t slots = std::min<uint32_t>(n_slow, (uint32_t)d.sm_count * 16);
+            slots = (uint32_t)std::min<uint64_t>(slots, std::max<uint64_t>(ex_budget / (fcap + 16 * vcap), 1));
+            slots = (slots + 3u) & ~3u;
+            CU(ctx, d.ex_hbuf.reserve((size_t)slots * 4 * vcap * sizeof(int32_t)));
+            CU(ctx, d.ex_fbuf.reserve((size_t)slots * fcap));
             ExactParams x{};
-            x.pair_ids = d.hazard_list.as<uint32_t>() + first;
-            x.n_pairs = count;
+            x.pair_ids = d.hazard_list.as<uint32_t>();
+            x.pos_list = d.ex_lists.as<uint32_t>() + (size_t)4 * n_exact;
+            x.n_pairs_dev = nullptr;
+            x.n_pairs = n_slow;
             x.rseq = p.rseq;
             x.roff = p.roff;
             x.pbytes = d.pbytes.as<uint8_t>();
@@ -1189,8 +1368,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             x.lanes16 = ctx->lanes[1];
             x.lanes32 = ctx->lanes[2];
             x.invert = invert;
-            x.hbuf = d.ex_hbuf.as<int32_t>() + (size_t)slot_base * 4 * vcap;
-            x.fbuf = d.ex_fbuf.as<uint8_t>() + (size_t)slot_base * fcap;
+            x.hbuf = d.ex_hbuf.as<int32_t>();
+            x.fbuf = d.ex_fbuf.as<uint8_t>();
             x.vcap = vcap;
             x.fcap = fcap;
             x.score_in = t.score;
@@ -1198,7 +1377,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             x.ref_end = t.ref_end;
             x.query_start = t.query_start;
             x.query_end = t.query_end;
-            x.cig_scratch = d.ex_cig.as<uint32_t>() + (size_t)first * cig_cap;
+            x.cig_scratch = d.ex_cig.as<uint32_t>();
             x.cig_count = t.cig_count;
             x.cig_cap = cig_cap;
             x.counters = ctr;
@@ -1245,7 +1424,11 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             wp.counters = ctr;
             const uint64_t max_items = (uint64_t)cpairs + n_keys + 2;
             CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
-            scan_fn<<<blocks, plan.threads, plan.smem, d.stream>>>(wp);
+            {
+                const uint32_t gpa = plan.threads / k->G, units = (p.n_tasks + scan_tpg - 1) / scan_tpg;
+                const uint32_t nba = std::min<uint32_t>((uint32_t)(d.sm_count * plan.blocks_per_sm), (units + gpa - 1) / gpa);
+                scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wp);
+            }
             CU(ctx, cudaGetLastError());
             ClassifyParams cp{};
             cp.ends = ap.ends;
@@ -1363,7 +1546,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             }
         }
         if (n_exact > 0) {
-            rc = launch_exact(0, n_exact, n_exact, d.stream);
+            rc = launch_exact(n_exact, d.stream);
             if (rc) return rc;
         }
         if (n_exact > 0) {
@@ -1430,16 +1613,212 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
 }
 
 // ---------------------------------------------------------------------------------------------
+// ranges pipeline for long streamed sequences (rows > kMaxRowsSinglePass) or key spaces too large for the bucketed
+// reverse pass: sw_ends_long_kernel forward (score + exact end cell) -> mapped pairs -> sw_ends_long_kernel<REV> ->
+// ranges_finalize_kernel.  zoe: sw_simd_score_ranges has no length limit (striped.rs:355-388).
+// ---------------------------------------------------------------------------------------------
+constexpr int kEndsLongK = 24;
+
+template <bool PACKED, bool REV>
+int launch_ends_long(zoe_cuda_ctx *ctx, Device &d, EndsLongParams lp, uint32_t n_tasks_bound, uint32_t max_rows) {
+    auto fn = sw_ends_long_kernel<kEndsLongK, PACKED, REV>;
+    const size_t tab_per_warp = (size_t)ctx->n_csym * (kEndsLongK / 4) * 32 * 16;
+    const size_t fixed = 256 + (((size_t)ctx->n_csym * ctx->S + 15) & ~(size_t)15);
+    const LaunchPlan *cached = nullptr;
+    const PlanKey key{(const void *)fn, ctx->ccodes.size(), 0};
+    LaunchPlan plan;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->plans.find(key);
+        if (it != ctx->plans.end()) {
+            plan = it->second;
+            cached = &plan;
+        }
+    }
+    if (!cached) {
+        int best_warps = 0;
+        cudaFuncAttributes fa{};
+        CU(ctx, cudaFuncGetAttributes(&fa, fn));
+        for (int cols_in_smem = 1; cols_in_smem >= 0 && best_warps == 0; --cols_in_smem) {
+            if (cols_in_smem && ctx->ccodes.size() > kColsSmemLimit) continue;
+            for (int threads : {384, 320, 256, 192, 128, 64, 32}) {
+                if (threads > fa.maxThreadsPerBlock) continue;
+                const size_t smem = tab_per_warp * (threads / 32) + fixed + (cols_in_smem ? ((ctx->ccodes.size() + 15) & ~(size_t)15) : 0);
+                if (smem > 227 * 1024) continue;
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                int nb = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, threads, smem) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                if (nb * threads / 32 > best_warps) {
+                    best_warps = nb * threads / 32;
+                    plan.threads = threads;
+                    plan.blocks_per_sm = nb;
+                    plan.smem = smem;
+                    plan.cols_in_smem = cols_in_smem;
+                }
+            }
+        }
+        if (!best_warps) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "long-row ends kernel does not fit shared memory (alphabet %d)", ctx->n_csym);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->plans[key] = plan;
+    }
+    if (n_tasks_bound == 0) return 0;
+    const uint32_t wpb = plan.threads / 32;
+    const uint32_t R = 32 * kEndsLongK;
+    const uint32_t chunk_cap = std::max<uint32_t>(1, (max_rows + R - 1) / R - 1);  // bottom rows of all chunks but the last
+    uint32_t blocks = std::min<uint32_t>((uint32_t)(d.sm_count * plan.blocks_per_sm), (n_tasks_bound + wpb - 1) / wpb);
+    // boundary rows: [warp slot][chunk][column] x 8 bytes, bounded by the scratch budget (fewer blocks if need be)
+    const uint64_t per_block = (uint64_t)wpb * chunk_cap * ctx->max_prof_len * sizeof(uint2);
+    uint64_t budget = ctx->flag_budget_bytes ? ctx->flag_budget_bytes : (uint64_t)(d.free_at_create * 0.4);
+    budget = std::min<uint64_t>(budget, (uint64_t)32 << 30);
+    blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(blocks, budget / std::max<uint64_t>(per_block, 1)));
+    CU(ctx, d.long_bnd.reserve((size_t)blocks * per_block));
+    CU(ctx, d.long_queue.reserve(sizeof(unsigned int)));
+    CU(ctx, cudaMemsetAsync(d.long_queue.p, 0, sizeof(unsigned int), d.stream));
+    lp.s.cols_in_smem = plan.cols_in_smem;
+    lp.boundary = d.long_bnd.as<uint2>();
+    lp.max_L = ctx->max_prof_len;
+    lp.chunk_cap = chunk_cap;
+    lp.queue = d.long_queue.as<unsigned int>();
+    CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    fn<<<blocks, plan.threads, plan.smem, d.stream>>>(lp);
+    CU(ctx, cudaGetLastError());
+    ctx->last_launches++;
+    return 0;
+}
+
+int run_ranges_long_on_device(zoe_cuda_ctx *ctx, Device &d) {
+    const uint32_t n_prof = ctx->n_prof;
+    const size_t pairs = (size_t)d.n_count * n_prof;
+    if (pairs >= 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "too many pairs for one ranges call");
+    // longest first: the two halves of a packed task have similar lengths, the queue hands out the big tasks first
+    std::vector<uint32_t> order(d.n_count);
+    for (uint64_t i = 0; i < d.n_count; ++i) order[i] = (uint32_t)i;
+    if (!ctx->staged_len.empty()) {
+        const uint32_t *len = ctx->staged_len.data() + d.n_first;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return len[a] > len[b]; });
+    }
+    CU(ctx, d.long_ids.reserve(order.size() * sizeof(uint32_t)));
+    CU(ctx, cudaMemcpyAsync(d.long_ids.p, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    CU(ctx, d.ends.reserve(pairs * sizeof(AlignEnd)));
+    CU(ctx, d.starts.reserve(pairs * sizeof(AlignEnd)));
+    for (DevBuf *b : {&d.ref_start, &d.ref_end, &d.query_start, &d.query_end, &d.score})
+        CU(ctx, b->reserve(pairs * sizeof(uint32_t)));
+    CU(ctx, d.status.reserve(pairs));
+    CU(ctx, d.tier.reserve(pairs));
+    CU(ctx, d.win_items.reserve((pairs + 2) * sizeof(uint32_t)));
+    CU(ctx, d.win_nitems.reserve(sizeof(uint32_t)));
+    CU(ctx, d.counters.reserve(16 * sizeof(unsigned long long)));
+    CU(ctx, cudaMemsetAsync(d.counters.p, 0, 16 * sizeof(unsigned long long), d.stream));
+    CU(ctx, cudaMemsetAsync(d.win_nitems.p, 0, sizeof(uint32_t), d.stream));
+    unsigned long long *ctr = d.counters.as<unsigned long long>();
+    // packed 16-bit lanes only when no pair can reach their limit and the step-pair indices fit 16 bits
+    const uint64_t bound = (uint64_t)std::min<uint32_t>(ctx->staged_max_len, ctx->max_prof_len) * (uint64_t)std::max(ctx->max_weight, 0);
+    const bool packed = bound < (uint64_t)(32767 - std::max(ctx->max_weight, 0) - 1 - ctx->go) && ctx->max_prof_len <= kScanMaxCols;
+
+    EndsLongParams lp{};
+    ScoreParams &p = lp.s;
+    p.rseq = d.rseq.as<uint8_t>();
+    p.roff = d.roff.as<uint64_t>();
+    p.task_ids = d.long_ids.as<uint32_t>();
+    p.n_rseq = (uint32_t)d.n_count;
+    p.n_tasks = packed ? (p.n_rseq + 1) / 2 : p.n_rseq;
+    p.ccodes = d.ccodes.as<uint8_t>();
+    p.coff = d.coff.as<uint32_t>();
+    p.n_cseq = n_prof;
+    p.ccodes_bytes = (uint32_t)ctx->ccodes.size();
+    p.wk = d.wk.as<int8_t>();
+    p.n_csym = ctx->n_csym;
+    p.S = ctx->S;
+    p.lut = d.lut.as<uint8_t>();
+    p.go = ctx->go;
+    p.ge = ctx->ge;
+    p.ovf_thresh = 0x7fffffff;  // packed lanes cannot overflow here (static bound above)
+    lp.out = d.ends.as<AlignEnd>();
+    lp.counters = ctr;
+    CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+    int rc = packed ? launch_ends_long<true, false>(ctx, d, lp, p.n_tasks, ctx->staged_max_len)
+                    : launch_ends_long<false, false>(ctx, d, lp, p.n_tasks, ctx->staged_max_len);
+    if (rc) return rc;
+
+    RangesLongParams rl{};
+    rl.ends = d.ends.as<AlignEnd>();
+    rl.roff = p.roff;
+    rl.order = d.long_ids.as<uint32_t>();
+    rl.n_seq = (uint32_t)d.n_count;
+    rl.n_cseq = n_prof;
+    rl.score = d.score.as<uint32_t>();
+    rl.status = d.status.as<uint8_t>();
+    rl.tier = d.tier.as<uint8_t>();
+    rl.ref_start = d.ref_start.as<uint32_t>();
+    rl.ref_end = d.ref_end.as<uint32_t>();
+    rl.query_start = d.query_start.as<uint32_t>();
+    rl.query_end = d.query_end.as<uint32_t>();
+    rl.items = d.win_items.as<uint32_t>();
+    rl.n_items = d.win_nitems.as<uint32_t>();
+    rl.tp = ctx->tp;
+    const uint32_t pb = (uint32_t)((pairs + 255) / 256);
+    ranges_long_classify_kernel<<<pb, 256, 0, d.stream>>>(rl);
+    CU(ctx, cudaGetLastError());
+
+    EndsLongParams lr = lp;
+    lr.s.task_ids = nullptr;
+    lr.items = d.win_items.as<uint32_t>();
+    lr.n_tasks_dev = d.win_nitems.as<uint32_t>();
+    lr.rev_in = d.ends.as<AlignEnd>();
+    lr.rev_maxw = std::max(ctx->max_weight, 0);
+    lr.out = d.starts.as<AlignEnd>();
+    rc = packed ? launch_ends_long<true, true>(ctx, d, lr, (uint32_t)pairs, ctx->staged_max_len)
+                : launch_ends_long<false, true>(ctx, d, lr, (uint32_t)pairs, ctx->staged_max_len);
+    if (rc) return rc;
+    CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+    d.timed_kernel = true;
+
+    RangesParams rp{};
+    rp.ends = d.ends.as<AlignEnd>();
+    rp.starts = d.starts.as<AlignEnd>();
+    rp.roff = p.roff;
+    rp.n_cseq = n_prof;
+    rp.chunk_first = 0;
+    rp.n_slots = (uint32_t)d.n_count;
+    rp.score = d.score.as<uint32_t>();
+    rp.status = d.status.as<uint8_t>();
+    rp.tier = d.tier.as<uint8_t>();
+    rp.ref_start = d.ref_start.as<uint32_t>();
+    rp.ref_end = d.ref_end.as<uint32_t>();
+    rp.query_start = d.query_start.as<uint32_t>();
+    rp.query_end = d.query_end.as<uint32_t>();
+    rp.counters = ctr;
+    rp.invert = ctx->profiled_is_query ? 0 : 1;
+    rp.tp = ctx->tp;
+    ranges_finalize_kernel<<<pb, 256, 0, d.stream>>>(rp);
+    CU(ctx, cudaGetLastError());
+    count_status_kernel<<<pb, 256, 0, d.stream>>>(d.tier.as<uint8_t>(), d.status.as<uint8_t>(), pairs, ctr);
+    CU(ctx, cudaGetLastError());
+    ctx->last_launches += 3;
+    unsigned long long mism = 0;
+    CU(ctx, cudaMemcpyAsync(&mism, ctr + 7, sizeof(mism), cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    if (mism) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: the long-row ranges passes disagreed on %llu pairs", mism);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // ranges pipeline (one device): forward ends -> bucket by (profiled, c_end) -> reverse ends -> ranges
 // ---------------------------------------------------------------------------------------------
 int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
     if (d.n_count == 0) return 0;
     CU(ctx, cudaSetDevice(d.id));
-    if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass)
-        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "streamed sequences longer than %d are not supported by the ranges path yet",
-                    kMaxRowsSinglePass);
-    if (ctx->max_prof_len > kEndsMaxCols)
-        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "profiled sequences longer than %u are not supported by the ranges path", kEndsMaxCols);
+    // long rows, or a (profiled, end column) key space too large for the bucketed reverse pass: the chunked-row pipeline
+    if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass || (uint64_t)ctx->n_prof * ctx->max_prof_len > (1ull << 27) ||
+        ctx->max_prof_len > kEndsMaxCols || getenv("ZOE_CUDA_RANGES_LONG"))
+        return run_ranges_long_on_device(ctx, d);
     const bool scan_ok = ctx->max_prof_len <= kScanMaxCols && !getenv("ZOE_CUDA_RANGES_SLOW");
     const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
     if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
@@ -1529,6 +1908,8 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
             rc2 = plan_launch(ctx, *k, scan_fn, &plan_a);
             if (rc2) return rc2;
         }
+        int scan_tpg = 1;
+        pick_scan2(ctx, *k, &scan_fn, &plan_a, &scan_tpg);
         rc2 = plan_launch(ctx, *k, k->pin, &plan_p);
         if (rc2) return rc2;
         CU(ctx, cudaFuncSetAttribute(scan_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_a.smem));
@@ -1560,8 +1941,8 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
             wp.items = d.win_items.as<uint32_t>();
             wp.n_items = d.win_nitems.as<uint32_t>();
             wp.counters = ctr;
-            const uint32_t gpa = plan_a.threads / k->G;
-            scan_fn<<<std::min<uint32_t>((uint32_t)(d.sm_count * plan_a.blocks_per_sm), (wp.s.n_tasks + gpa - 1) / gpa),
+            const uint32_t gpa = plan_a.threads / k->G, units = (wp.s.n_tasks + scan_tpg - 1) / scan_tpg;
+            scan_fn<<<std::min<uint32_t>((uint32_t)(d.sm_count * plan_a.blocks_per_sm), (units + gpa - 1) / gpa),
                       plan_a.threads, plan_a.smem, d.stream>>>(wp);
             CU(ctx, cudaGetLastError());
             ClassifyParams cp{};
@@ -1970,7 +2351,7 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
         for (DevBuf *b : {&d.ccodes, &d.coff, &d.wk, &d.lut, &d.corder, &d.ccodes_g, &d.coff_g, &d.corder_g, &d.rseq, &d.roff, &d.best, &d.score, &d.status, &d.tier,
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
-                          &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.weights, &d.tp_pair, &d.tp_off, &d.tp_cap, &d.tp_slot,
+                          &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.ex_lists, &d.ex_counts, &d.ex_fast_fbuf, &d.weights, &d.tp_pair, &d.tp_off, &d.tp_cap, &d.tp_slot,
                           &d.tp_blob, &d.tp_ctr, &d.sn_refs, &d.sn_roff, &d.sn_qry, &d.sn_qoff, &d.sn_out, &d.long_ids, &d.long_bnd,
                           &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.starts, &d.cig_bsum})
             b->release();
@@ -2002,6 +2383,7 @@ int zoe_cuda_set_scoring(zoe_cuda_ctx *ctx, const int8_t *weights, int S, const 
     ctx->max_weight = *std::max_element(ctx->weights.begin(), ctx->weights.end());
     ctx->bias = std::max(0, -(int)*std::min_element(ctx->weights.begin(), ctx->weights.end()));
     refresh_tier_policy(ctx);
+    ctx->plans.clear();
     ctx->have_scoring = true;
     ctx->have_profiled = false;
     ctx->staged = false;
@@ -2060,6 +2442,7 @@ int zoe_cuda_set_profiled(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64
         if (len == 0) return fail(ctx, ZOE_CUDA_E_EMPTY_SEQUENCE, "profiled sequence %u is empty", j);
         max_len = std::max<uint32_t>(max_len, (uint32_t)len);
     }
+    ctx->plans.clear();
     ctx->n_prof = n;
     ctx->max_prof_len = max_len;
     ctx->prof_bytes.assign(concat + offsets[0], concat + offsets[n]);
@@ -2168,8 +2551,11 @@ int zoe_cuda_run_align_staged(zoe_cuda_ctx *ctx) {
         CU(ctx, cudaSetDevice(d.id));
         CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
     }
-    // generous device-side CIGAR capacity: 8 words per pair (typical CIGARs have <= 5 entries)
-    int rc = for_each_device(ctx, [&](Device &d) { return run_align_on_device(ctx, d, (uint64_t)d.n_count * ctx->n_prof * 8 + 1024); });
+    // generous device-side CIGAR capacity: 64 words per pair, at most 1 GB (typical CIGARs have <= 5 entries; cheap gaps
+    // fragment them).  Nothing is fetched by this entry point: words beyond the capacity are dropped, not an error.
+    int rc = for_each_device(ctx, [&](Device &d) {
+        return run_align_on_device(ctx, d, std::min<uint64_t>((uint64_t)d.n_count * ctx->n_prof * 64 + 1024, (uint64_t)1 << 28));
+    });
     if (rc) return rc;
     rc = sync_and_time(ctx);
     if (rc) return rc;
