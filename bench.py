@@ -346,7 +346,8 @@ def run_leg(ctx: Ctx, config: int, mode_override, n_override, steps: int, warmup
             keep.append(t)
             outs[k] = a
     if mode in ("align", "3pass"):
-        cap = pairs * (64 if SCORING else 8) + 1024  # tie-heavy scorings fragment the CIGARs
+        # CIGAR words: <= 5 per short read; cheap gaps fragment them; long noisy reads need ~1 word per 15 bases
+        cap = pairs * (64 if SCORING else 8) + int(offs[-1]) * n_prof // 6 + 1024
         t, a = pinned(torch, np.zeros(pairs + 1, dtype=np.int64))
         keep.append(t)
         outs["cigar_off"] = a.view(np.uint64)
@@ -517,7 +518,9 @@ def run_leg(ctx: Ctx, config: int, mode_override, n_override, steps: int, warmup
         else:  # ranges / 3pass: the plain-C oracle on a sample
             from oracle import oracle as O
             sc = O.Scoring(matrix.weights, matrix.mapping.index_map, go, ge)
-            n_sample = min(n, 20000)
+            # the scalar-loop oracle does ~1 GCUPS on 16 threads: a prefix of at most 20000 sequences and ~2e10 cells
+            cum = np.cumsum(np.diff(offs.astype(np.int64))) * prof_total
+            n_sample = int(min(n, 20000, max(1, np.searchsorted(cum, 2e10) + 1)))
             t0 = time.perf_counter()
 
             def check_range(lo_, hi_):

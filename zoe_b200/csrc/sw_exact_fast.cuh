@@ -87,25 +87,35 @@ __host__ __device__ inline void exact_window(bool end_known, uint32_t r_end, uin
     width = c_end - c_lo + 1;
 }
 
-// Shared memory per CTA: [groups x (H u16[vcap], E u16[vcap], flags u8[vcap], (pidx u8[vcap]))]
+// Shared memory per CTA: [groups x (H u16[vcap], E u16[vcap], flags u8[vcap], (pidx u8[vcap]), F per lane i32[N])]
 //                        [shared pidx u8[vcap] when n_cseq == 1][weights (S+1) x (S+1) i8][lut 256]
 // The group stride is 2N bytes past a multiple of 128, so the 32 / N groups of a warp hit disjoint banks.
 __host__ __device__ inline size_t exact_fast_group_bytes(uint32_t vcap, bool pidx_shared, int N) {
-    return (((size_t)vcap * (pidx_shared ? 5 : 6) + 127) & ~(size_t)127) + (N < 32 ? 2 * (size_t)N : 0);
+    return (((size_t)vcap * (pidx_shared ? 5 : 6) + 4 + 4 * (size_t)N + 127) & ~(size_t)127) + (N < 32 ? 2 * (size_t)N : 0);
 }
 __host__ __device__ inline size_t exact_fast_fixed_bytes(uint32_t vcap, int S, bool pidx_shared) {
     return (pidx_shared ? (size_t)vcap : 0) + (size_t)((S + 1) * (S + 1) + 15) / 16 * 16 + 256;
 }
 
-template <bool FULL>
+// Lane-major row layout: element (vector v, SIMD lane l) of a row lives at l * nvp + v, nvp = vectors per lane padded to
+// twice an odd number -- the lanes of a warp then hit distinct banks in the main loop (thread = lane, same v), and one
+// lane's vectors are contiguous for the lazy-F pass (threads = consecutive v of ONE lane).
+__host__ __device__ inline int exact_fast_nvp(int nv) {
+    int p = nv + (nv & 1);
+    if (((p >> 1) & 1) == 0) p += 2;
+    return p;
+}
+
+// N (SIMD lanes of the tier: 8, 16 or 32) is a template parameter: index arithmetic by shifts, constant shuffle widths.
+template <bool FULL, int N>
 __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParams x) {
     extern __shared__ __align__(16) uint8_t xs[];
     constexpr unsigned ALL = 0xffffffffu;
-    const int N = x.N;
     const int lig = threadIdx.x & (N - 1);
     const int group = threadIdx.x / N, groups = blockDim.x / N;
     const int lane = threadIdx.x & 31;
-    const unsigned gmask = (N == 32 ? ALL : ((1u << N) - 1u)) << (lane & ~(N - 1));
+    const int gbase_lane = lane & ~(N - 1);  // first warp lane of this group
+    const unsigned gmask = (N == 32 ? ALL : ((1u << N) - 1u)) << gbase_lane;
     const bool pidx_shared = x.n_cseq == 1;
     const uint32_t vcap = x.vcap;
     const int S1 = x.S + 1;
@@ -116,6 +126,7 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
     uint8_t *frow = reinterpret_cast<uint8_t *>(es + vcap);
     uint8_t *fixed = xs + (size_t)groups * exact_fast_group_bytes(vcap, pidx_shared, N);
     uint8_t *pidx = pidx_shared ? fixed : frow + vcap;
+    int *fsh = reinterpret_cast<int *>(gbase + (((size_t)vcap * (pidx_shared ? 5 : 6) + 3) & ~(size_t)3));  // lazy-F: F per lane
     int8_t *wtab = reinterpret_cast<int8_t *>(fixed + (pidx_shared ? vcap : 0));
     uint8_t *s_lut = reinterpret_cast<uint8_t *>(wtab) + ((S1 * S1 + 15) / 16) * 16;
 
@@ -127,10 +138,10 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = x.lut[i];
     if (pidx_shared) {  // one profiled sequence: its striped symbol indices are the same for every pair of the CTA
         const int m = (int)(x.coff[1] - x.coff[0]);
-        const int nv = (m + N - 1) / N;
-        for (int i = threadIdx.x; i < nv * N; i += blockDim.x) {
-            const int v = i / N, l = i % N, c = l * nv + v;
-            pidx[i] = c < m ? x.lut[x.pbytes[x.coff[0] + c]] : (uint8_t)x.S;
+        const int nv = (m + N - 1) / N, nvp = exact_fast_nvp(nv);
+        for (int i = threadIdx.x; i < nvp * N; i += blockDim.x) {
+            const int l = i / nvp, v = i % nvp, c = l * nv + v;
+            pidx[i] = (v < nv && c < m) ? x.lut[x.pbytes[x.coff[0] + c]] : (uint8_t)x.S;
         }
     }
     __syncthreads();
@@ -162,6 +173,7 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
                 c_end_in = e.c_end;
             }
         }
+        const int nvp = exact_fast_nvp(nv);
         uint32_t n_rows, c_lo, width;
         exact_window(!FULL, r_end_in, c_end_in, want, (uint32_t)n, (uint32_t)m, x.maxw, x.go, x.ge, n_rows, c_lo, width);
         if (!valid) n_rows = 0;
@@ -169,14 +181,15 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
         const int rows_w = (int)__reduce_max_sync(ALL, n_rows);
         const int nv_w = (int)__reduce_max_sync(ALL, (unsigned)nv);
 
-        for (int i = lig; i < nv * N; i += N) {
-            hrow[i] = 0;
-            es[i] = 0;
-            if (!pidx_shared) {
-                const int v = i / N, l = i % N, c = l * nv + v;
-                pidx[i] = c < m ? s_lut[P[c]] : (uint8_t)x.S;
+        if (valid)
+            for (int i = lig; i < nvp * N; i += N) {
+                hrow[i] = 0;
+                es[i] = 0;
+                if (!pidx_shared) {
+                    const int l = i / nvp, v = i % nvp, c = l * nv + v;
+                    pidx[i] = (v < nv && c < m) ? s_lut[P[c]] : (uint8_t)x.S;
+                }
             }
-        }
         // first window column of this lane and its striped coordinates (the same for every row)
         uint8_t *fdst = x.fbuf + (size_t)slot * x.fcap;
         const int t0 = lig;  // window offsets t0, t0 + N, ...
@@ -190,33 +203,34 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
 
         int best = 0, r_best = n > 0 ? n - 1 : 0, c_best = m > 0 ? m - 1 : 0;  // FULL: zoe's defaults (striped.rs:476, 573)
         const int go = x.go, ge = x.ge;
+        const int mybase = lig * nvp;  // this lane's segment of every row
 
         for (int r = 0; r < rows_w; ++r) {
             const bool row_on = r < (int)n_rows;
             const int8_t *wrow = wtab + (row_on ? (int)s_lut[R[r]] : x.S) * S1;
             // H = store[nv-1].shift_elements_right(MIN): the final H of row r-1 at column l*nv - 1
-            int Hd = (row_on && lig > 0) ? (int)hrow[(nv - 1) * N + lig - 1] : 0;
+            int Hd = (row_on && lig > 0) ? (int)hrow[mybase - nvp + nv - 1] : 0;
             __syncwarp();
             int F = 0, rowmax = 0;
             // software pipeline: the symbol index is fetched two vectors ahead, weight / E / previous H one vector ahead,
             // all before vector v is stored -- no load sits on the F -> H -> F chain
             int w_n = 0, E_n = 0, Hp_n = 0, pi_n = x.S;
             if (row_on && nv > 0) {
-                w_n = wrow[pidx[lig]];
-                E_n = es[lig];
-                Hp_n = hrow[lig];
-                if (nv > 1) pi_n = pidx[N + lig];
+                w_n = wrow[pidx[mybase]];
+                E_n = es[mybase];
+                Hp_n = hrow[mybase];
+                pi_n = pidx[mybase + 1];  // padded: always readable
             }
 #pragma unroll 4
             for (int v = 0; v < nv_w; ++v) {
                 const bool on = row_on && v < nv;
                 const int w = w_n, E = E_n, Hp = Hp_n;
-                const int idx = v * N + lig;
+                const int idx = mybase + v;
                 if (row_on && v + 1 < nv) {
                     w_n = wrow[pi_n];
-                    E_n = es[idx + N];
-                    Hp_n = hrow[idx + N];
-                    if (v + 2 < nv) pi_n = pidx[idx + 2 * N];
+                    E_n = es[idx + 1];
+                    Hp_n = hrow[idx + 1];
+                    pi_n = pidx[idx + 2];  // nvp >= nv + 1 keeps idx + 2 inside the lane's padded segment
                 }
                 if (on) {
                     const int h = __vimax3_s32(Hd + w, E, F);             // saturating_add floors at MIN = 0 <= E, F
@@ -234,62 +248,70 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
                     Hd = Hp;
                 }
             }
-            // ---- lazy-F (striped.rs:528-553): every group runs its own (pass, vector) counters.  Within a pass F only
-            //      decays (F -= gap_extend per vector, independent of H) and every vector is visited once, so the
-            //      "does any lane still improve?" tests of U consecutive vectors are independent of each other: they are
-            //      evaluated together (U loads, U votes in flight) and the updates applied up to the first vector whose
-            //      vote fails -- the serial vote-per-vector loop was 90 % of the kernel's time on high-scoring rows ----
+            __syncwarp();
+            // ---- lazy-F (striped.rs:528-553).  Within a pass, lane L's F only decays: F_L(v) = max(F_L(0) - v * ge, 0),
+            //      independent of H, and every vector is visited once.  So every (lane, vector) test
+            //      "F_L(v) > H - gap_open" of a pass is known up front, a lane whose F enters the pass at 0 can never
+            //      pass it, and the only coupling is the stopping rule: the pass ends at the first vector where NO lane
+            //      passes.  The work of a pass is therefore spread over the group's threads by VECTOR (thread t takes
+            //      v = t, t + N, ...) for the few lanes with F > 0 only -- typically one or two of N -- instead of every
+            //      lane walking every vector:  1) test, 2) stop = first vector nobody passes (min over threads),
+            //      3) update the cells before `stop` that zoe would change.  A cell changes iff F >= H there:
+            //      H = max(H, F); LEFT corrected / set where F == H; LEFT_EXT where F - ge > H - go; STOP where H == MIN. ----
             {
-                constexpr int U = 8;
                 bool live = row_on && nv > 0;
-                int pass = 0, v = 0;
-                int Fl = 0;
-                bool fresh = true;  // a new pass starts: F = F.shift_elements_right(MIN)
+                int pass = 0;
                 while (__any_sync(ALL, live)) {
-                    const int Fs = __shfl_up_sync(ALL, fresh ? F : 0, 1, N);
-                    if (live && fresh) {
-                        Fl = lig == 0 ? 0 : Fs;
-                        fresh = false;
-                    }
-                    const int cnt = live ? min(U, nv - v) : 0;
-                    int hh[U];
-                    unsigned votes[U];
-#pragma unroll
-                    for (int k = 0; k < U; ++k) hh[k] = k < cnt ? (int)hrow[(v + k) * N + lig] : 0;
-#pragma unroll
-                    for (int k = 0; k < U; ++k) {
-                        const int Fk = max(Fl - k * ge, 0);
-                        const bool trig = k < cnt && Fk > __viaddmax_s32(hh[k], -go, 0);
-                        votes[k] = __ballot_sync(ALL, trig) & gmask;
-                    }
-                    int stop = cnt;
-#pragma unroll
-                    for (int k = U - 1; k >= 0; --k)
-                        if (k < cnt && votes[k] == 0) stop = k;
-#pragma unroll
-                    for (int k = 0; k < U; ++k) {
-                        if (k < stop) {
-                            const int idx = (v + k) * N + lig;
-                            const int Fk = max(Fl - k * ge, 0);
-                            const int h2 = max(hh[k], Fk);
-                            hrow[idx] = (uint16_t)h2;
-                            uint32_t fl = frow[idx];
-                            if (Fk == h2) fl = (fl & 2u) | 4u;  // simd_correct_and_set_left
-                            const int ho = __viaddmax_s32(h2, -go, 0);
-                            if (max(Fk - ge, 0) > ho) fl |= 8u;
-                            if (h2 == 0) fl = 16u;
-                            frow[idx] = (uint8_t)fl;
+                    // F = F.shift_elements_right(MIN); every thread of the group can read every lane's F
+                    const int Fs = __shfl_up_sync(ALL, F, 1, N);
+                    const int Fl = lig == 0 ? 0 : Fs;
+                    fsh[lig] = Fl;
+                    const unsigned act = (__ballot_sync(ALL, live && Fl > 0) & gmask) >> gbase_lane;  // lanes that can still improve cells
+                    __syncwarp();
+                    // 1) + 2) own vectors in ascending order: the first one where no active lane passes the test
+                    int stop = nv;
+                    if (live) {
+                        for (int v = lig; v < nv; v += N) {
+                            bool hit = false;
+                            for (unsigned a = act; a && !hit; a &= a - 1) {
+                                const int L = __ffs(a) - 1;
+                                hit = max(fsh[L] - v * ge, 0) > __viaddmax_s32((int)hrow[L * nvp + v], -go, 0);
+                            }
+                            if (!hit) {
+                                stop = v;
+                                break;
+                            }
                         }
                     }
+                    for (int d = N / 2; d >= 1; d >>= 1) stop = min(stop, __shfl_xor_sync(ALL, stop, d, N));
+                    // 3) update the visited cells of the active lanes
                     if (live) {
-                        Fl = max(Fl - stop * ge, 0);
-                        v += stop;
-                        if (stop < cnt) {
-                            live = false;  // break 'lazy_f
-                        } else if (v == nv) {
-                            v = 0;
-                            F = Fl;  // the next pass shifts what this one left
-                            fresh = true;
+                        for (unsigned a = act; a; a &= a - 1) {
+                            const int L = __ffs(a) - 1;
+                            const int FL = fsh[L];
+                            const int lb = L * nvp;
+                            for (int v = lig; v < stop; v += N) {
+                                const int Fk = max(FL - v * ge, 0);
+                                const int h = hrow[lb + v];
+                                if (Fk >= h) {
+                                    uint32_t fl = frow[lb + v];
+                                    fl = (fl & 2u) | 4u;  // simd_correct_and_set_left (F == max(H, F))
+                                    if (max(Fk - ge, 0) > __viaddmax_s32(Fk, -go, 0)) fl |= 8u;
+                                    if (Fk == 0) fl = 16u;
+                                    hrow[lb + v] = (uint16_t)Fk;
+                                    frow[lb + v] = (uint8_t)fl;
+                                } else if (max(Fk - ge, 0) > __viaddmax_s32(h, -go, 0)) {
+                                    frow[lb + v] |= 8u;   // F < H, but F - ge still beats H - go: LEFT_EXT
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (live) {
+                        if (stop < nv || act == 0) {
+                            live = false;  // break 'lazy_f (no active lane: the very first test fails)
+                        } else {
+                            F = max(Fl - nv * ge, 0);  // what this pass leaves; the next pass shifts it
                             if (++pass == N) live = false;
                         }
                     }
@@ -306,7 +328,7 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
                     int cmin = 0x7fffffff;
                     if (improved) {
                         for (int v = 0; v < nv; ++v)
-                            if ((int)hrow[v * N + lig] == rb) {
+                            if ((int)hrow[mybase + v] == rb) {
                                 const int c = lig * nv + v;
                                 if (c < m) cmin = c;
                                 break;
@@ -321,7 +343,7 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
                 }
             } else if (row_on && r == (int)r_end_in && lig == 0) {
                 const int v = (int)c_end_in % nv, l = (int)c_end_in / nv;
-                if ((uint32_t)hrow[v * N + l] != want || (uint32_t)rb != want) atomicAdd(&x.counters[7], 1ULL);
+                if ((uint32_t)hrow[l * nvp + v] != want || (uint32_t)rb != want) atomicAdd(&x.counters[7], 1ULL);
             }
             // ---- publish the reachable part of the finished flag row ----
             if (row_on) {
@@ -329,7 +351,7 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
                 int pv = pv0, pl = pl0;
 #pragma unroll 4
                 for (int t = t0; t < (int)width; t += N) {
-                    dst[t] = frow[pv * N + pl];
+                    dst[t] = frow[pl * nvp + pv];
                     pv += N;
                     while (pv >= nv) {
                         pv -= nv;

@@ -93,7 +93,7 @@ struct Device {
     DevBuf starts;  // ranges: reverse-pass results
     DevBuf cig_bsum;  // CIGAR scan: per-block sums
     DevBuf sn_refs, sn_roff, sn_qry, sn_qoff, sn_out;  // SneakySnake filter batch (sneaky_snake.cuh)
-    DevBuf tp_pair, tp_off, tp_cap, tp_slot, tp_blob, tp_ctr;  // 3-pass alignment: DP work list + scratch (sw_3pass.cuh)
+    DevBuf tp_pair, tp_off, tp_cap, tp_slot, tp_blob, tp_ctr, tp_cigoff, tp_bw, tp_list, tp_cig;  // 3-pass: DP work lists + scratch (sw_3pass.cuh)
     uint64_t cig_total = 0;
     // long-row score path
     DevBuf long_ids, long_bnd, long_queue;
@@ -222,7 +222,8 @@ struct zoe_cuda_ctx {
     uint64_t flag_budget_bytes = 0;  // 0 = auto (a fraction of free device memory)
     int align_mode = 0;              // 0 = auto, 1 = full-matrix flags, 2 = checkpointed window
     int win_cb_log2 = 6;             // checkpoint spacing (columns), log2 (64: measured best on cfg 3, 70.3 vs 73.6 ms at 128)
-    uint32_t win_slack = 16;         // columns kept left of the shortest possible walk
+    uint32_t win_slack = 16;         // columns kept left of the shortest possible walk ...
+    bool win_slack_set = false;      // ... when the caller set it (zoe_cuda_set_align_options); else chosen per scoring
     // measurements
     float last_total_ms = 0.f, last_dp_ms = 0.f;
     std::atomic<uint32_t> last_launches{0};
@@ -1044,7 +1045,13 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     while ((1 << cb_log2) < k->G) ++cb_log2;  // a checkpoint is a step boundary with every lane active
     const uint32_t CB = 1u << cb_log2;
     // window capacity in columns: the walk's reach + the distance to the previous checkpoint + the lane skew
-    const uint32_t wmax = std::min<uint32_t>(ctx->max_prof_len, std::max<uint32_t>(ctx->staged_max_len, 1) + ctx->win_slack + CB) + k->G;
+    // Columns kept left of the shortest possible walk.  Unless the caller chose one: 16, or 128 when gaps are cheap next
+    // to a match (open + extend <= 2 x the largest weight) -- unrelated reads then align as long gappy chains, and a walk
+    // that leaves its window costs a literal-kernel run (tie-heavy scoring 4/-2/-3/-1, 200k reads: 38 % of the walks
+    // left a 16-column slack, 0.08 % a 128-column one; 141 -> 95 ms).
+    const uint32_t win_slack = ctx->win_slack_set ? ctx->win_slack
+                                                  : ((ctx->go + ctx->ge <= 2 * std::max(ctx->max_weight, 0)) ? 128u : 16u);
+    const uint32_t wmax = std::min<uint32_t>(ctx->max_prof_len, std::max<uint32_t>(ctx->staged_max_len, 1) + win_slack + CB) + k->G;
     if (ctx->max_prof_len > kEndsMaxCols)
         return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "profiled sequences longer than %u are not supported by the align path", kEndsMaxCols);
     const bool window_ok = ctx->go != 0 && ctx->max_prof_len <= kScanMaxCols;
@@ -1239,8 +1246,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             // can the fast kernel hold a pair of this tier?  (lanes <= 32, one group's rows within the shared memory)
             const bool pidx_shared = n_prof == 1;
             auto fast_plan = [&](int N, uint32_t *vcap_out, int *groups_out, size_t *smem_out) -> bool {
-                if (N > 32 || getenv("ZOE_CUDA_EXACT_SLOW")) return false;
-                const uint32_t vcap = (((ctx->max_prof_len + N - 1) / N * N) + 31u) & ~31u;
+                if ((N != 8 && N != 16 && N != 32) || getenv("ZOE_CUDA_EXACT_SLOW")) return false;
+                const uint32_t vcap = ((uint32_t)N * (uint32_t)exact_fast_nvp((int)((ctx->max_prof_len + N - 1) / N)) + 31u) & ~31u;
                 const size_t gb = exact_fast_group_bytes(vcap, pidx_shared, N), fx = exact_fast_fixed_bytes(vcap, ctx->S, pidx_shared);
                 const size_t lim = 200 * 1024;
                 if (gb * (32 / N) + fx > lim) return false;
@@ -1321,7 +1328,14 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                 x.counters = ctr;
                 x.retry_list = d.ex_lists.as<uint32_t>() + (size_t)4 * n_exact;
                 x.retry_count = d.ex_counts.as<uint32_t>() + 4;
-                auto fn = full ? sw_exact_fast_kernel<true> : sw_exact_fast_kernel<false>;
+                void (*fn)(const ExactFastParams) = nullptr;
+                switch (N) {
+                    case 8: fn = full ? sw_exact_fast_kernel<true, 8> : sw_exact_fast_kernel<false, 8>; break;
+                    case 16: fn = full ? sw_exact_fast_kernel<true, 16> : sw_exact_fast_kernel<false, 16>; break;
+                    case 32: fn = full ? sw_exact_fast_kernel<true, 32> : sw_exact_fast_kernel<false, 32>; break;
+                    default: break;
+                }
+                if (!fn) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: no literal kernel for %d lanes", N);
                 CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 for (uint32_t r0 = 0; r0 < cnt[which]; r0 += round) {
                     x.list = d.ex_lists.as<uint32_t>() + (size_t)which * n_exact + r0;
@@ -1412,7 +1426,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             wp.ckpt_base = d.ckpt_base.as<uint64_t>();
             wp.ckpt_task_stride = ckpt_task_stride;
             wp.cb_log2 = cb_log2;
-            wp.slack = ctx->win_slack;
+            wp.slack = win_slack;
             wp.nblk = nblk;
             wp.hist = d.win_hist.as<uint32_t>();
             wp.bucket_start = d.win_bucket.as<uint32_t>();
@@ -1439,7 +1453,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             cp.n_slots = cn;
             cp.K = k->K;
             cp.cb_log2 = cb_log2;
-            cp.slack = ctx->win_slack;
+            cp.slack = win_slack;
             cp.maxw = std::max(ctx->max_weight, 0);
             cp.go = ctx->go;
             cp.ge = ctx->ge;
@@ -1507,7 +1521,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             tw.wflags = wp.flags;
             tw.win_task_stride = win_task_stride;
             tw.cb_log2 = cb_log2;
-            tw.slack = ctx->win_slack;
+            tw.slack = win_slack;
             sw_traceback_win_kernel<<<(uint32_t)((max_items + 127) / 128), 128, 0, d.stream>>>(tw);
             CU(ctx, cudaGetLastError());
             ctx->last_launches += 4;
@@ -2086,7 +2100,10 @@ int run_3pass_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     CU(ctx, d.tp_pair.reserve(chunk_pairs * sizeof(uint32_t)));
     CU(ctx, d.tp_cap.reserve(chunk_pairs * sizeof(uint32_t)));
     CU(ctx, d.tp_slot.reserve(chunk_pairs * sizeof(uint32_t)));
-    CU(ctx, d.tp_off.reserve(chunk_pairs * sizeof(unsigned long long)));
+    CU(ctx, d.tp_bw.reserve(2 * chunk_pairs * sizeof(uint32_t)));
+    CU(ctx, d.tp_list.reserve(2 * chunk_pairs * sizeof(uint32_t)));
+    CU(ctx, d.tp_off.reserve(2 * chunk_pairs * sizeof(unsigned long long)));
+    CU(ctx, d.tp_cigoff.reserve(chunk_pairs * sizeof(unsigned long long)));
     CU(ctx, d.tp_ctr.reserve(16 * sizeof(unsigned long long)));
     CU(ctx, cudaMemsetAsync(d.tp_ctr.p, 0, 16 * sizeof(unsigned long long), d.stream));
     unsigned long long *ctr = d.tp_ctr.as<unsigned long long>();
@@ -2113,33 +2130,82 @@ int run_3pass_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     t.dp_pair = d.tp_pair.as<uint32_t>();
     t.dp_cap = d.tp_cap.as<uint32_t>();
     t.dp_slot = d.tp_slot.as<uint32_t>();
+    t.dp_bw = d.tp_bw.as<uint32_t>();
     t.dp_off = d.tp_off.as<unsigned long long>();
+    t.dp_cig_off = d.tp_cigoff.as<unsigned long long>();
     t.ctr = ctr;
 
     unsigned long long n_nogaps = 0;
     for (uint64_t p0 = 0; p0 < pairs;) {
         uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_pairs, pairs - p0);
-        unsigned long long work[6] = {0, 0, 0, 0, 0, 0};  // [0] DP pairs, [1] scratch bytes, [5] no-gaps pairs
+        unsigned long long work[13] = {0};  // [0] DP pairs, [1] round-0 scratch, [2] CIGAR bytes, [5] no-gaps pairs, [12] widest large row
+        uint32_t *lists[2] = {d.tp_list.as<uint32_t>(), d.tp_list.as<uint32_t>() + chunk_pairs};
+        uint32_t *bws[2] = {d.tp_bw.as<uint32_t>(), d.tp_bw.as<uint32_t>() + chunk_pairs};
+        unsigned long long *offs[2] = {d.tp_off.as<unsigned long long>(), d.tp_off.as<unsigned long long>() + chunk_pairs};
         for (;;) {
             t.pair_first = p0;
             t.n_pairs = cn;
+            t.next_list = lists[0];  // the classification lists round 0
+            t.dp_bw = bws[0];
+            t.dp_off = offs[0];
             CU(ctx, cudaMemsetAsync(ctr, 0, 6 * sizeof(unsigned long long), d.stream));
+            CU(ctx, cudaMemsetAsync(ctr + 12, 0, sizeof(unsigned long long), d.stream));
             tp_classify_kernel<<<(cn + 255) / 256, 256, 0, d.stream>>>(t);
             CU(ctx, cudaGetLastError());
             ctx->last_launches++;
             CU(ctx, cudaMemcpyAsync(work, ctr, sizeof(work), cudaMemcpyDeviceToHost, d.stream));
             CU(ctx, cudaStreamSynchronize(d.stream));
-            if (work[1] <= budget || cn == 1) break;
-            cn = std::max<uint32_t>(1, cn / 2);  // the boxes of this chunk need more scratch than the budget: split it
+            if (work[1] + work[2] <= budget || cn == 1) break;
+            cn = std::max<uint32_t>(1, cn / 2);  // this chunk needs more scratch than the budget: split it
             chunk_pairs = cn;
         }
         n_nogaps += work[5];
         if (work[0] > 0) {
-            CU(ctx, d.tp_blob.reserve(work[1] + 16));
-            t.blob = d.tp_blob.as<uint8_t>();
-            tp_dp_kernel<<<(uint32_t)((work[0] + kTpThreads - 1) / kTpThreads), kTpThreads, 0, d.stream>>>(t, (uint32_t)work[0]);
-            CU(ctx, cudaGetLastError());
-            ctx->last_launches++;
+            // rounds: every unresolved pair tries its current band width; failures come back with twice the width
+            CU(ctx, d.tp_cig.reserve(work[2] + 16));
+            t.cig_blob = d.tp_cig.as<uint8_t>();
+            uint32_t n_round = (uint32_t)work[0];
+            unsigned long long bytes = work[1], wide = work[12];
+            int cur = 0;
+            for (int round = 0; n_round > 0; ++round) {
+                if (round > 64) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: 3-pass band rounds do not terminate");
+                CU(ctx, d.tp_blob.reserve(bytes + 16));
+                t.blob = d.tp_blob.as<uint8_t>();
+                t.list = lists[cur];
+                t.next_list = lists[cur ^ 1];
+                t.dp_bw = bws[cur];
+                t.dp_off = offs[cur];
+                t.dp_bw_next = bws[cur ^ 1];
+                t.dp_off_next = offs[cur ^ 1];
+                // large boxes (wide bands, big scalar boxes): one warp per pair, two int rows per warp in shared memory
+                uint32_t wcap = 0, warps = 0;
+                if (wide > 0 && !getenv("ZOE_CUDA_TP_THREAD")) {
+                    wcap = (uint32_t)std::min<unsigned long long>((wide + 2 + 31) & ~31ull, 24 * 1024);  // <= 192 KB per warp
+                    warps = (uint32_t)std::min<size_t>(16, (200 * 1024) / ((size_t)wcap * 8));
+                    if (warps == 0) wcap = 0;
+                }
+                t.warp_wcap = wcap;
+                CU(ctx, cudaMemsetAsync(ctr + 3, 0, 2 * sizeof(unsigned long long), d.stream));
+                CU(ctx, cudaMemsetAsync(ctr + 12, 0, sizeof(unsigned long long), d.stream));
+                tp_dp_kernel<<<(n_round + kTpThreads - 1) / kTpThreads, kTpThreads, 0, d.stream>>>(t, n_round);
+                CU(ctx, cudaGetLastError());
+                ctx->last_launches++;
+                if (wcap) {
+                    const size_t smem = (size_t)warps * wcap * 8;
+                    CU(ctx, cudaFuncSetAttribute(tp_band_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    const uint32_t nb = std::min<uint32_t>((n_round + warps - 1) / warps, (uint32_t)d.sm_count * 8);
+                    tp_band_warp_kernel<<<nb, warps * 32, smem, d.stream>>>(t, n_round, wcap);
+                    CU(ctx, cudaGetLastError());
+                    ctx->last_launches++;
+                }
+                unsigned long long nxt[10] = {0};
+                CU(ctx, cudaMemcpyAsync(nxt, ctr + 3, sizeof(nxt), cudaMemcpyDeviceToHost, d.stream));
+                CU(ctx, cudaStreamSynchronize(d.stream));
+                n_round = (uint32_t)nxt[0];
+                bytes = nxt[1];
+                wide = nxt[9];
+                cur ^= 1;
+            }
         }
         // CIGAR compaction, chained through the device-side running base ctr[9]
         if (cn >= (1u << 16)) {
@@ -2352,7 +2418,7 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
                           &d.wide_ids, &d.counters, &d.pbytes, &d.ends, &d.flags, &d.flag_base, &d.ref_start, &d.ref_end,
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.ex_lists, &d.ex_counts, &d.ex_fast_fbuf, &d.weights, &d.tp_pair, &d.tp_off, &d.tp_cap, &d.tp_slot,
-                          &d.tp_blob, &d.tp_ctr, &d.sn_refs, &d.sn_roff, &d.sn_qry, &d.sn_qoff, &d.sn_out, &d.long_ids, &d.long_bnd,
+                          &d.tp_blob, &d.tp_ctr, &d.tp_cigoff, &d.tp_bw, &d.tp_list, &d.tp_cig, &d.sn_refs, &d.sn_roff, &d.sn_qry, &d.sn_qoff, &d.sn_out, &d.long_ids, &d.long_bnd,
                           &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.starts, &d.cig_bsum})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -2419,6 +2485,7 @@ int zoe_cuda_set_align_options(zoe_cuda_ctx *ctx, int mode, int checkpoint_log2,
     ctx->align_mode = mode;
     ctx->win_cb_log2 = checkpoint_log2;
     ctx->win_slack = (uint32_t)slack;
+    ctx->win_slack_set = true;
     return 0;
 }
 
