@@ -106,7 +106,11 @@ int zoe_cuda_sw_score_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
  * if the CIGARs do not fit the call returns ZOE_CUDA_E_CIGAR_CAP and writes the needed
  * capacity to cigar_off[0] (nothing else is valid).
  *   hazard  (may be NULL) 1 where the pair went through the literal striped-emulation kernel
- *           because its traceback met an E/F tie whose resolution depends on the lane layout. */
+ *           because its traceback met an E/F tie whose resolution depends on the lane layout.
+ * Streamed sequences of any length, as zoe's function: those beyond 1024 residues (one pass of the register-resident
+ * kernels) are scored by the chunked-row kernels and aligned by the literal striped kernels, pair by pair -- correct
+ * but slow, like the O(mn) memory zoe warns about (striped.rs:410-413); the 3-pass entry point below is the one meant
+ * for long reads.  A batch that mixes both kinds is split internally and returned in the caller's order. */
 int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
                             uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
                             uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,
@@ -118,7 +122,8 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
  * sw_simd_score_ends / sw_simd_score_ends_reverse, striped.rs:153-336).  ref_end / query_end are what
  * StripedProfile::sw_score_ends reports (profile.rs:456-460).  Ranges follow zoe's output after make_alignment, i.e.
  * swapped when profiled_is_query == 0 (src/alignment/mod.rs:176-190); they are 0 when status != ZOE_CUDA_SOME.
- * Streamed sequences up to 1024 residues. */
+ * Streamed sequences of any length: batches with a sequence beyond 1024 residues take the chunked-row kernels
+ * (sw_ends_long_kernel, forward and reverse). */
 int zoe_cuda_sw_score_ranges_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
                                    uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
                                    uint32_t *query_start, uint32_t *query_end);
@@ -130,7 +135,8 @@ int zoe_cuda_sw_score_ranges_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_co
  * |ref_len - query_len| + 1 doubled until the banded score matches, else sw_scalar_align on the box
  * (src/alignment/sw/scalar.rs:173-271).  Outputs as zoe_cuda_sw_align_batch (the score is the pass-1 score; the CIGAR
  * carries zoe's soft clips; SeqSrc::Query results are invert()ed).  The CIGAR can differ from sw_align's in equal-score
- * ties, exactly as zoe's two functions differ.  Streamed sequences up to 1024 residues, alphabets up to 32 symbols. */
+ * ties, exactly as zoe's two functions differ.  Streamed sequences of any length (band-sized scratch: a 5 kb x 5 kb
+ * box costs rows x (2 bw + 1) flag bytes, not rows x columns); alphabets up to 32 symbols. */
 int zoe_cuda_sw_align_3pass_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, const uint64_t *offsets, uint64_t n,
                                   uint32_t *score, uint8_t *status, uint8_t *tier, uint32_t *ref_start, uint32_t *ref_end,
                                   uint32_t *query_start, uint32_t *query_end, uint32_t *cigar, uint64_t *cigar_off,

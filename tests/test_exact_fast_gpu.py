@@ -56,6 +56,21 @@ def test_hazard_heavy_reads_window_pipeline(go, ge, lanes):
     assert stats["hazard"] > 15, stats  # the workload does exercise the literal path
 
 
+@pytest.mark.parametrize("lanes", [(32, 16, 8), (16, 8, 4)])
+def test_cta_per_pair_kernel_on_every_hazard_pair(lanes):
+    # the latency kernel (one CTA per pair, F by a max-plus scan) forced onto whole hazard lists
+    ha = synth.golden_ha(ROOT)
+    reads = hazard_reads(700, 19, [ha])
+    for go, ge in ((-3, -1), (-2, -2), (-10, -1)):
+        stats, mism, _ = run_and_compare([ha], reads, W42, go, ge, lanes=lanes, env={"ZOE_CUDA_EXACT_CTA": "1"})
+        assert mism == 0, (go, ge, stats)
+    rng = np.random.default_rng(20)
+    targets = [synth.random_dna(rng, 700), synth.random_dna(rng, 333), synth.random_dna(rng, 64)]
+    stats, mism, _ = run_and_compare(targets, hazard_reads(300, 21, targets[:2]), W42, 0, 0, lanes=lanes,
+                                     env={"ZOE_CUDA_EXACT_CTA": "1"})
+    assert mism == 0, stats
+
+
 def test_fast_and_slow_literal_kernels_agree():
     ha = synth.golden_ha(ROOT)
     reads = hazard_reads(800, 12, [ha])

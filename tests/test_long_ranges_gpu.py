@@ -107,3 +107,17 @@ def test_3pass_warp_kernel_scalar_fallback_and_wide_bands():
     reads = [chimera, shifted] + ont_reads(rng, g, 3, 1100, 1600)
     stats = check_3pass([g], reads, WeightMatrix.new_dna_matrix(2, -5, b"N"), go=-3, ge=-1)
     assert stats["tp_band_attempts"] > stats["tp_banded"]
+
+
+def test_sw_align_batch_takes_long_and_mixed_batches():
+    # one long read must not fail the whole zoe_cuda_sw_align_batch call; zoe's sw_simd_align has no limit
+    from test_align_gpu import check_align
+    rng = np.random.default_rng(27)
+    g = synth.random_dna(rng, 2200)
+    long_reads = ont_reads(rng, g, 3, 1030, 1500)
+    short_reads = ont_reads(rng, g, 6, 30, 400)
+    check_align([g], long_reads, W25)                                   # all long
+    check_align([g, g[300:900].copy()], [short_reads[0], long_reads[0], short_reads[1], short_reads[2], long_reads[1]], W25)
+    check_align([g], [long_reads[2], short_reads[3]], W42, go=-3, ge=-1, profiled_is_query=True)
+    s = golden("CY137594.txt")
+    check_align([s], [s], W25)                                          # sw/test.rs:264-280, aligned on the GPU

@@ -374,6 +374,177 @@ __global__ void __launch_bounds__(512) sw_exact_fast_kernel(const ExactFastParam
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One CTA per pair: the latency version, for short literal lists (a lone hazard pair in a 125k-read shard kept the whole
+// GPU waiting 1.9 ms for one warp).  Warp L owns SIMD lane L; its nv vectors are spread over the warp's 32 threads in
+// chunks of 32 consecutive vectors.  The only dependency inside a lane's main pass, F, is a max-plus prefix scan:
+//     F(v) = max(0, max_{v' < v} (sat(H0(v') - go) - (v - v' - 1) * ge)),   H0 = max(Hdiag + w, E, 0)
+// (a gap opened from a cell that F itself produced never beats extending that gap: gap_open >= gap_extend), so a row
+// costs a few five-step warp scans instead of nv serial steps.  H rows are double buffered (the main pass reads row r-1,
+// writes row r); the lazy-F pass is the cell-parallel one of sw_exact_fast_kernel with the stopping rule taken over the
+// whole CTA.  Values and flags are those of the serial loops; the same walk kernel follows.  End cell known only.
+// Shared memory (lane-major, as above): H x 2 and E as u16, flags, symbol indices and "some lane passes here" marks as
+// u8, the F leaving every lane, two control words, weights, byte -> symbol map.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t exact_cta_smem_bytes(uint32_t vcap, int S, int N) {
+    return (((size_t)vcap * 9 + 3) & ~(size_t)3) + 4 * (size_t)N + 64 + (size_t)((S + 1) * (S + 1) + 15) / 16 * 16 + 256;
+}
+
+template <int N>
+__global__ void __launch_bounds__(N * 32) sw_exact_cta_kernel(const ExactFastParams x) {
+    extern __shared__ __align__(16) uint8_t xs[];
+    constexpr unsigned ALL = 0xffffffffu;
+    constexpr int NEG = -(1 << 29);
+    const int tid = threadIdx.x, lane = tid & 31, L = tid >> 5;  // L = the SIMD lane this warp owns
+    const uint32_t vcap = x.vcap;
+    const int S1 = x.S + 1;
+    uint16_t *hbuf0 = reinterpret_cast<uint16_t *>(xs);
+    uint16_t *hbuf1 = hbuf0 + vcap;
+    uint16_t *es = hbuf1 + vcap;
+    uint8_t *frow = reinterpret_cast<uint8_t *>(es + vcap);
+    uint8_t *pidx = frow + vcap;
+    uint8_t *anyhit = pidx + vcap;
+    int *fsh = reinterpret_cast<int *>(xs + (((size_t)vcap * 9 + 3) & ~(size_t)3));  // F leaving each lane's segment
+    int *ctl = fsh + N;                                                               // [0] stop, [1] some lane is active
+    int8_t *wtab = reinterpret_cast<int8_t *>(ctl + 16);
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(wtab) + ((S1 * S1 + 15) / 16) * 16;
+    for (int i = tid; i < S1 * S1; i += blockDim.x) {
+        const int a = i / S1, b = i % S1;
+        wtab[i] = (a < x.S && b < x.S) ? x.weights[a * x.S + b] : 0;
+    }
+    for (int i = tid; i < 256; i += blockDim.x) s_lut[i] = x.lut[i];
+    __syncthreads();
+
+    for (uint32_t slot = blockIdx.x; slot < x.list_count; slot += gridDim.x) {
+        const uint32_t pos = x.list[slot];
+        const uint32_t gid = x.hazard_list[pos] & ~kEndUnknown;
+        const uint32_t seq = gid / x.n_cseq, cj = gid % x.n_cseq;
+        const uint8_t *R = x.rseq + x.roff[seq];
+        const int n = (int)(x.roff[seq + 1] - x.roff[seq]);
+        const uint8_t *P = x.pbytes + x.coff[cj];
+        const int m = (int)(x.coff[cj + 1] - x.coff[cj]);
+        const int nv = (m + N - 1) / N, nvp = exact_fast_nvp(nv);
+        const uint32_t want = x.score_in[gid];
+        const AlignEnd e_in = x.ends[gid];
+        uint32_t n_rows, c_lo, width;
+        exact_window(true, e_in.r_end, e_in.c_end, want, (uint32_t)n, (uint32_t)m, x.maxw, x.go, x.ge, n_rows, c_lo, width);
+        __syncthreads();
+        for (int i = tid; i < nvp * N; i += blockDim.x) {
+            const int l = i / nvp, v = i % nvp, c = l * nv + v;
+            hbuf0[i] = 0;
+            hbuf1[i] = 0;
+            es[i] = 0;
+            pidx[i] = (v < nv && c < m) ? s_lut[P[c]] : (uint8_t)x.S;
+        }
+        __syncthreads();
+        uint8_t *fdst = x.fbuf + (size_t)slot * x.fcap;
+        const int go = x.go, ge = x.ge;
+        const int lb = L * nvp;
+        uint16_t *hprev = hbuf0, *hcur = hbuf1;
+
+        for (int r = 0; r < (int)n_rows; ++r) {
+            const int8_t *wrow = wtab + (int)s_lut[R[r]] * S1;
+            // ---- main pass of lane L: chunks of 32 vectors, F by a max-plus scan ----
+            int carry = 0;  // F entering the chunk's first vector (F starts the row at MIN = 0)
+            for (int v0 = 0; v0 < nv; v0 += 32) {
+                const int v = v0 + lane;
+                const bool on = v < nv;
+                int h0 = NEG, E = 0;
+                if (on) {
+                    // H = store[v-1] of row r-1; vector 0 takes the last vector of lane L-1 (shift_elements_right)
+                    const int Hd = v > 0 ? (int)hprev[lb + v - 1] : (L > 0 ? (int)hprev[lb - nvp + nv - 1] : 0);
+                    E = es[lb + v];
+                    h0 = max(max(Hd + (int)wrow[pidx[lb + v]], E), 0);
+                }
+                int X = on ? max(h0 - go, 0) : NEG;  // what this vector hands to the next one: sat(H0 - go)
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const int y = __shfl_up_sync(ALL, X, sft);
+                    if (lane >= sft) X = max(X, y - sft * ge);
+                }
+                const int Xprev = __shfl_up_sync(ALL, X, 1);
+                const int F = max(max(lane > 0 ? Xprev : NEG, carry - lane * ge), 0);
+                carry = max(max(__shfl_sync(ALL, X, 31), carry - 32 * ge), 0);
+                if (on) {
+                    const int h = max(h0, F);
+                    const int ho = __viaddmax_s32(h, -go, 0);
+                    const int E2 = __viaddmax_s32(E, -ge, ho);
+                    const int F2 = __viaddmax_s32(F, -ge, ho);
+                    uint32_t fl = (uint32_t)(E == h) | ((uint32_t)(F == h) << 2) | ((uint32_t)(E2 > ho) << 1) |
+                                  ((uint32_t)(F2 > ho) << 3);
+                    if (h == 0) fl = 16u;
+                    hcur[lb + v] = (uint16_t)h;
+                    es[lb + v] = (uint16_t)E2;
+                    frow[lb + v] = (uint8_t)fl;
+                    if (v == nv - 1) fsh[L] = F2;  // F leaving the lane's last vector
+                }
+            }
+            __syncthreads();
+            // ---- lazy-F (striped.rs:528-553): see sw_exact_fast_kernel; the stopping rule spans the whole CTA ----
+            for (int pass = 0; pass < N; ++pass) {
+                const int Fl = L > 0 ? fsh[L - 1] : 0;  // F.shift_elements_right(MIN)
+                const bool active = Fl > 0;
+                for (int i = tid; i < nv; i += blockDim.x) anyhit[i] = 0;
+                if (tid == 0) ctl[1] = 0;
+                __syncthreads();
+                if (active) {
+                    if (lane == 0) ctl[1] = 1;
+                    for (int v = lane; v < nv; v += 32)
+                        if (max(Fl - v * ge, 0) > __viaddmax_s32((int)hcur[lb + v], -go, 0)) anyhit[v] = 1;
+                }
+                __syncthreads();
+                if (ctl[1] == 0) break;  // no lane carries an F: the first test fails (uniform)
+                if (L == 0) {            // first vector where no lane passes
+                    int stop = nv;
+                    for (int v0 = 0; v0 < nv && stop == nv; v0 += 32) {
+                        const int v = v0 + lane;
+                        const unsigned miss = __ballot_sync(ALL, v < nv && anyhit[v] == 0);
+                        if (miss) stop = v0 + __ffs(miss) - 1;
+                    }
+                    if (lane == 0) ctl[0] = stop;
+                }
+                __syncthreads();
+                const int stop = ctl[0];
+                if (active) {
+                    for (int v = lane; v < stop; v += 32) {
+                        const int Fk = max(Fl - v * ge, 0);
+                        const int h = hcur[lb + v];
+                        if (Fk >= h) {
+                            uint32_t fl = frow[lb + v];
+                            fl = (fl & 2u) | 4u;  // simd_correct_and_set_left (F == max(H, F))
+                            if (max(Fk - ge, 0) > __viaddmax_s32(Fk, -go, 0)) fl |= 8u;
+                            if (Fk == 0) fl = 16u;
+                            hcur[lb + v] = (uint16_t)Fk;
+                            frow[lb + v] = (uint8_t)fl;
+                        } else if (max(Fk - ge, 0) > __viaddmax_s32(h, -go, 0)) {
+                            frow[lb + v] |= 8u;  // F < H, but F - ge still beats H - go: LEFT_EXT
+                        }
+                    }
+                }
+                __syncthreads();  // every warp has read fsh[L - 1] and ctl
+                if (stop < nv) break;
+                if (lane == 0) fsh[L] = max(Fl - nv * ge, 0);  // what this pass leaves; the next pass shifts it
+                __syncthreads();
+            }
+            __syncthreads();
+            // ---- consistency at the end row, then publish the reachable part of the finished flag row ----
+            if (r == (int)e_in.r_end && tid == 0) {
+                const int v = (int)e_in.c_end % nv, l = (int)e_in.c_end / nv;
+                if ((uint32_t)hcur[l * nvp + v] != want) atomicAdd(&x.counters[7], 1ULL);
+            }
+            uint8_t *dst = fdst + (size_t)r * x.wcap;
+            for (int t = tid; t < (int)width; t += blockDim.x) {
+                const int c = (int)c_lo + t, l = c / nv, v = c - l * nv;
+                dst[t] = frow[l * nvp + v];
+            }
+            uint16_t *sw = hprev;
+            hprev = hcur;
+            hcur = sw;
+            __syncthreads();
+        }
+    }
+}
+
 // zoe's walk (backtrack.rs:290-342) over the published flags: one thread per pair of the round.
 __global__ void sw_exact_walk_kernel(const ExactFastParams x, int full) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;

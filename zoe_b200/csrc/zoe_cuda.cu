@@ -1024,14 +1024,37 @@ __global__ void count_status_kernel(const uint8_t *tier, const uint8_t *status, 
     }
 }
 
+// Long-row align: every mapped pair of the chunk goes to the literal kernels, with the exact end cell the long-row
+// ranges pipeline found (status / score / tier are already final).
+__global__ void collect_mapped_kernel(const AlignEnd *ends, const uint8_t *status, uint32_t first_pair, uint32_t n_pairs,
+                                      int32_t *best_arr, uint8_t *hazard, uint32_t *cig_count, uint32_t *hazard_list,
+                                      unsigned long long *counters) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    const uint32_t gid = first_pair + k;
+    best_arr[gid] = ends[gid].best;
+    cig_count[gid] = 0;
+    const bool mapped = status[gid] == ZOE_CUDA_SOME;
+    hazard[gid] = mapped ? 1 : 0;
+    if (mapped) hazard_list[atomicAdd(&counters[5], 1ULL)] = gid;
+}
+
+int run_ranges_long_on_device(zoe_cuda_ctx *ctx, Device &d);
+
 int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) {
     d.cig_total = 0;
     if (d.n_count == 0) return 0;
     CU(ctx, cudaSetDevice(d.id));
-    if (ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass)
-        return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "streamed sequences longer than %d are not supported by the align path yet",
-                    kMaxRowsSinglePass);
-    const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
+    // Streamed sequences beyond one pass of the register-resident kernels: zoe's sw_simd_align takes any length (and
+    // documents its O(mn) memory as unsuitable for long pairs, striped.rs:410-413).  Here: score + exact end cell from the
+    // chunked-row pipeline, then the literal striped kernels for every mapped pair -- correct, not fast; the memory-light
+    // 3-pass alignment is the path meant for long reads.
+    const bool long_mode = ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass;
+    if (long_mode) {
+        int rc0 = run_ranges_long_on_device(ctx, d);
+        if (rc0) return rc0;
+    }
+    const KernelEntry *k = pick_score_kernel(std::min<uint32_t>(std::max<uint32_t>(ctx->staged_max_len, 1), kMaxRowsSinglePass), ctx->n_csym);
     if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
     const int NW = align_words_per_lane(k->K);
     const uint32_t n_prof = ctx->n_prof;
@@ -1057,6 +1080,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     const bool window_ok = ctx->go != 0 && ctx->max_prof_len <= kScanMaxCols;
     bool use_window = window_ok && (uint64_t)ctx->max_prof_len >= 2ull * wmax;
     if (ctx->align_mode == 1) use_window = false;
+    if (long_mode) use_window = false;
     if (ctx->align_mode == 2) use_window = window_ok;
     if (const char *e = getenv("ZOE_CUDA_ALIGN_MODE")) {
         if (!strcmp(e, "full")) use_window = false;
@@ -1084,12 +1108,13 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     uint64_t budget = ctx->flag_budget_bytes ? ctx->flag_budget_bytes : (uint64_t)(free_b * 0.55);
     budget = std::min<uint64_t>(budget, (uint64_t)48 << 30);
     // bytes per pass-A task (two sequences): full = all flags; window = checkpoints + one window per pair
-    const uint64_t per_task_bytes = use_window ? (ckpt_task_stride * 4 + (uint64_t)n_prof * win_task_stride * 4)
-                                               : task_stride * 4;
+    const uint32_t cig_cap = 2 * std::min<uint32_t>(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->max_prof_len) + 4;
+    const uint64_t per_task_bytes = long_mode ? (uint64_t)n_prof * cig_cap * 4 * 2 * 2  // the literal kernels' CIGAR rows only
+                                    : use_window ? (ckpt_task_stride * 4 + (uint64_t)n_prof * win_task_stride * 4)
+                                                 : task_stride * 4;
     uint64_t tasks_cap = std::max<uint64_t>(1, budget / std::max<uint64_t>(per_task_bytes, 1));
     uint64_t chunk_seqs = std::min<uint64_t>(d.n_count, tasks_cap * 2);
     if (chunk_seqs > 1) chunk_seqs &= ~1ULL;
-    const uint32_t cig_cap = 2 * std::min<uint32_t>(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->max_prof_len) + 4;
 
     CU(ctx, d.flag_base.reserve(n_prof * sizeof(uint64_t)));
     CU(ctx, cudaMemcpyAsync(d.flag_base.p, flag_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
@@ -1107,7 +1132,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         CU(ctx, d.win_bucket.reserve((n_keys + 1) * sizeof(uint32_t)));
         CU(ctx, d.win_items.reserve(max_items * sizeof(uint32_t)));
         CU(ctx, d.win_nitems.reserve(sizeof(uint32_t)));
-    } else {
+    } else if (!long_mode) {
         CU(ctx, d.flags.reserve(((chunk_seqs + 1) / 2) * task_stride * 4));
     }
     for (DevBuf *b : {&d.ref_start, &d.ref_end, &d.query_start, &d.query_end, &d.cig_count, &d.best, &d.score})
@@ -1116,7 +1141,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     CU(ctx, d.tier.reserve(pairs));
     CU(ctx, d.hazard.reserve(pairs));
     CU(ctx, d.hazard_list.reserve((size_t)chunk_seqs * n_prof * sizeof(uint32_t)));
-    CU(ctx, d.cig_scratch.reserve((size_t)chunk_seqs * n_prof * cig_cap * sizeof(uint32_t)));
+    CU(ctx, d.cig_scratch.reserve(long_mode ? 16 : (size_t)chunk_seqs * n_prof * cig_cap * sizeof(uint32_t)));
     CU(ctx, d.cig_off.reserve((pairs + 1) * sizeof(uint64_t)));
     CU(ctx, d.cig_out.reserve(std::max<uint64_t>(cigar_cap_words, 1) * sizeof(uint32_t)));
     CU(ctx, d.wide_ids.reserve((d.n_count + 1) * sizeof(uint32_t)));
@@ -1130,8 +1155,9 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     LaunchPlan plan, plan_b;
     // pass A comes in two instantiations: profiled symbol codes staged in shared memory, or (sets > 96 KB) read from
     // global memory; plan_launch tells which one fits
-    int rc = use_window ? plan_launch(ctx, *k, k->scan, &plan) : plan_launch(ctx, *k, k->fill, &plan);
+    int rc = long_mode ? 0 : (use_window ? plan_launch(ctx, *k, k->scan, &plan) : plan_launch(ctx, *k, k->fill, &plan));
     if (rc) return rc;
+    if (long_mode) plan.threads = k->G;  // no fill launch below; keeps the block arithmetic defined
     void (*scan_fn)(const WinParams) = k->scan;
     if (use_window && !plan.cols_in_smem) {
         scan_fn = k->scan_g;
@@ -1149,7 +1175,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         CU(ctx, cudaFuncSetAttribute(k->pin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_p.smem));
         CU(ctx, cudaFuncSetAttribute(scan_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
         CU(ctx, cudaFuncSetAttribute(k->winfill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_b.smem));
-    } else {
+    } else if (!long_mode) {
         CU(ctx, cudaFuncSetAttribute(k->fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     }
     dbg.lap("align: plan");
@@ -1189,7 +1215,7 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         uint32_t groups_per_block = plan.threads / k->G;
         uint32_t blocks = std::min<uint32_t>((uint32_t)(d.sm_count * plan.blocks_per_sm),
                                              (p.n_tasks + groups_per_block - 1) / groups_per_block);
-        if (!use_window) {
+        if (!use_window && !long_mode) {
             CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
             k->fill<<<blocks, plan.threads, plan.smem, d.stream>>>(ap);
             CU(ctx, cudaGetLastError());
@@ -1336,12 +1362,23 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                     default: break;
                 }
                 if (!fn) return fail(ctx, ZOE_CUDA_E_STATE, "internal error: no literal kernel for %d lanes", N);
+                // short lists with known end cells: one CTA per pair (latency), else one group of N threads per pair
+                void (*fn_cta)(const ExactFastParams) = N == 8 ? sw_exact_cta_kernel<8> : (N == 16 ? sw_exact_cta_kernel<16> : sw_exact_cta_kernel<32>);
+                const size_t cta_smem = exact_cta_smem_bytes(vcap, ctx->S, N);
+                const int cta_env = getenv("ZOE_CUDA_EXACT_CTA") ? atoi(getenv("ZOE_CUDA_EXACT_CTA")) : -1;  // 0 never, 1 always
+                const bool use_cta = !full && cta_smem <= 200 * 1024 &&
+                                     (cta_env == 1 || (cta_env != 0 && cnt[which] <= 4u * (uint32_t)d.sm_count));
+                if (use_cta) CU(ctx, cudaFuncSetAttribute(fn_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_smem));
                 CU(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 for (uint32_t r0 = 0; r0 < cnt[which]; r0 += round) {
                     x.list = d.ex_lists.as<uint32_t>() + (size_t)which * n_exact + r0;
                     x.list_count = std::min<uint32_t>(round, cnt[which] - r0);
-                    const uint32_t blocks = std::min<uint32_t>((uint32_t)d.sm_count, (x.list_count + groups - 1) / groups);
-                    fn<<<blocks, groups * N, smem, stream>>>(x);
+                    if (use_cta) {
+                        fn_cta<<<std::min<uint32_t>(x.list_count, 2u * (uint32_t)d.sm_count), N * 32, cta_smem, stream>>>(x);
+                    } else {
+                        const uint32_t blocks = std::min<uint32_t>((uint32_t)d.sm_count, (x.list_count + groups - 1) / groups);
+                        fn<<<blocks, groups * N, smem, stream>>>(x);
+                    }
                     CU(ctx, cudaGetLastError());
                     sw_exact_walk_kernel<<<(x.list_count + 127) / 128, 128, 0, stream>>>(x, full ? 1 : 0);
                     CU(ctx, cudaGetLastError());
@@ -1412,7 +1449,13 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             return 0;
         };
         const uint32_t cpairs = cn * n_prof;
-        if (!use_window) {
+        if (long_mode) {
+            collect_mapped_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(d.ends.as<AlignEnd>(), d.status.as<uint8_t>(),
+                                                                              (uint32_t)(c0 * n_prof), cpairs, t.best_arr, t.hazard,
+                                                                              t.cig_count, t.hazard_list, ctr);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+        } else if (!use_window) {
             sw_traceback_kernel<<<(cpairs + 127) / 128, 128, 0, d.stream>>>(t);
             CU(ctx, cudaGetLastError());
             ctx->last_launches++;
@@ -2736,6 +2779,92 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
                             uint64_t cigar_cap, uint8_t *hazard) {
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     if (!cigar_off || (!cigar && cigar_cap)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null CIGAR outputs");
+    // A batch that mixes long (> 1024 residues) and short sequences is split: the short ones take the fast pipelines,
+    // the long ones the long-row path (run_align_on_device, long_mode); results are merged in the caller's order.
+    if (n > 0 && offsets && streamed_concat && ctx->have_profiled) {
+        std::vector<uint64_t> idx[2];  // [0] short, [1] long
+        for (uint64_t i = 0; i < n; ++i) idx[offsets[i + 1] - offsets[i] > (uint64_t)kMaxRowsSinglePass ? 1 : 0].push_back(i);
+        if (!idx[0].empty() && !idx[1].empty()) {
+            const uint32_t np = ctx->n_prof;
+            struct Part {
+                std::vector<uint8_t> buf;
+                std::vector<uint64_t> off;
+                std::vector<uint32_t> score, rs, re, qs, qe, cig;
+                std::vector<uint8_t> status, tier, hz;
+                std::vector<uint64_t> coff;
+            } part[2];
+            zoe_cuda_stats total{};
+            float total_ms = 0.f, dp_ms = 0.f;
+            uint32_t launches = 0;
+            uint64_t need = 0;
+            int rc_cap = 0;
+            for (int w = 0; w < 2; ++w) {
+                Part &q = part[w];
+                q.off.push_back(0);
+                for (uint64_t i : idx[w]) {
+                    q.buf.insert(q.buf.end(), streamed_concat + offsets[i], streamed_concat + offsets[i + 1]);
+                    q.off.push_back(q.buf.size());
+                }
+                if (q.buf.empty()) q.buf.push_back(0);
+                const size_t pairs = idx[w].size() * np;
+                for (auto *v : {&q.score, &q.rs, &q.re, &q.qs, &q.qe}) v->assign(pairs, 0);
+                for (auto *v : {&q.status, &q.tier, &q.hz}) v->assign(pairs, 0);
+                q.coff.assign(pairs + 1, 0);
+                q.cig.assign(std::max<uint64_t>(cigar_cap, 1), 0);
+                int rc = zoe_cuda_sw_align_batch(ctx, q.buf.data(), q.off.data(), idx[w].size(), q.score.data(), q.status.data(),
+                                                 q.tier.data(), q.rs.data(), q.re.data(), q.qs.data(), q.qe.data(), q.cig.data(),
+                                                 q.coff.data(), cigar_cap, q.hz.data());
+                if (rc == ZOE_CUDA_E_CIGAR_CAP) {
+                    rc_cap = rc;
+                    need += q.coff[0];
+                    continue;
+                }
+                if (rc) return rc;
+                need += q.coff[pairs];
+                const zoe_cuda_stats &st = ctx->stats;
+                total.pairs += st.pairs; total.cells += st.cells; total.tier8 += st.tier8; total.tier16 += st.tier16;
+                total.tier32 += st.tier32; total.overflowed += st.overflowed; total.unmapped += st.unmapped;
+                total.rerun_wide += st.rerun_wide; total.hazard += st.hazard; total.window_fallback += st.window_fallback;
+                total.window_pinned += st.window_pinned;
+                total_ms += ctx->last_total_ms;
+                dp_ms += ctx->last_dp_ms;
+                launches += ctx->last_launches.load();
+            }
+            if (rc_cap || need > cigar_cap) {
+                cigar_off[0] = need;
+                return fail(ctx, ZOE_CUDA_E_CIGAR_CAP, "CIGAR buffer too small: need at least %llu words, have %llu",
+                            (unsigned long long)need, (unsigned long long)cigar_cap);
+            }
+            uint64_t pos = 0;
+            size_t cursor[2] = {0, 0};
+            for (uint64_t i = 0; i < n; ++i) {
+                const int w = offsets[i + 1] - offsets[i] > (uint64_t)kMaxRowsSinglePass ? 1 : 0;
+                const Part &q = part[w];
+                const size_t src = cursor[w]++ * np, dst = (size_t)i * np;
+                for (uint32_t j = 0; j < np; ++j) {
+                    if (score) score[dst + j] = q.score[src + j];
+                    if (status) status[dst + j] = q.status[src + j];
+                    if (tier) tier[dst + j] = q.tier[src + j];
+                    if (ref_start) ref_start[dst + j] = q.rs[src + j];
+                    if (ref_end) ref_end[dst + j] = q.re[src + j];
+                    if (query_start) query_start[dst + j] = q.qs[src + j];
+                    if (query_end) query_end[dst + j] = q.qe[src + j];
+                    if (hazard) hazard[dst + j] = q.hz[src + j];
+                    cigar_off[dst + j] = pos;
+                    const uint64_t a = q.coff[src + j], b = q.coff[src + j + 1];
+                    if (b > a) memcpy(cigar + pos, q.cig.data() + a, (b - a) * sizeof(uint32_t));
+                    pos += b - a;
+                }
+            }
+            cigar_off[(size_t)n * np] = pos;
+            ctx->stats = total;
+            ctx->last_total_ms = total_ms;
+            ctx->last_dp_ms = dp_ms;
+            ctx->last_launches = launches;
+            ctx->staged = false;
+            return 0;
+        }
+    }
     begin_call(ctx);
     DebugTimer dbg;
     int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
