@@ -730,6 +730,9 @@ struct ClassifyParams {
     int maxw, go, ge;              // largest weight and the (positive) gap penalties: bound the walk's column-only moves
     int all_exact;
     uint32_t *hist;
+    uint8_t *amb;                  // [chunk-local pair] 1 = the pair's end cell is ambiguous (written by pin stage 1)
+    int subset;                    // classification proper: 0 = every pair, 1 = unambiguous pairs only, 2 = ambiguous only
+                                   // (the pin sweep of the ambiguous ones overlaps the window fill of the others)
     int pin_stage;                 // 1: select the ambiguous pairs for the pin sweep; 2: every mapped pair (ranges);
                                    // 0: the classification proper
     int32_t *best_arr;
@@ -760,10 +763,13 @@ __global__ void win_classify_kernel(const ClassifyParams t) {
     const uint32_t seq_local = k / t.n_cseq, cj = k % t.n_cseq;
     const uint32_t seq = t.chunk_first + seq_local;
     const size_t gid = (size_t)seq * t.n_cseq + cj;
+    if (!t.pin_stage && t.subset && (t.amb[k] != 0) != (t.subset == 2)) return;  // the other pass's pair: not even read
     const AlignEnd e = t.ends[gid];
     const uint32_t n = (uint32_t)(t.roff[seq + 1] - t.roff[seq]);
     if (t.pin_stage) {  // ambiguous end cells only: bucket them by (profiled sequence, checkpoint block)
-        if (win_eligible(e, n, t.tp, t.all_exact) && (t.pin_stage == 2 || e.aux != e.c_end)) {
+        const bool sel = win_eligible(e, n, t.tp, t.all_exact) && (t.pin_stage == 2 || e.aux != e.c_end);
+        if (t.amb) t.amb[k] = sel ? 1 : 0;
+        if (sel) {
             atomicAdd(&t.hist[cj * t.nblk + (pin_start(e.c_end, t.coff[cj + 1] - t.coff[cj], t.cb_log2) >> t.cb_log2)], 1u);
             if (e.aux != e.c_end) atomicAdd(&t.counters[11], 1ULL);
         }
@@ -875,6 +881,7 @@ __global__ void win_scatter_kernel(const ClassifyParams t, const uint32_t *bucke
     if (k >= pairs) return;
     const uint32_t seq = t.chunk_first + k / t.n_cseq, cj = k % t.n_cseq;
     const size_t gid = (size_t)seq * t.n_cseq + cj;
+    if (!t.pin_stage && t.subset && (t.amb[k] != 0) != (t.subset == 2)) return;
     const AlignEnd e = t.ends[gid];
     uint32_t key;
     if (t.pin_stage) {

@@ -79,6 +79,8 @@ struct Device {
     int sm_count = 0;
     size_t free_at_create = 0;  // cudaMemGetInfo is slow (tens of ms on a 180 GB part): asked once
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;  // align: the pin sweep of the ambiguous pairs runs beside the main window fill
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     // scoring + profiled (replicated on every device)
     DevBuf ccodes, coff, wk, lut, corder;
@@ -89,7 +91,7 @@ struct Device {
     DevBuf pbytes, ends, flags, flag_base, ref_start, ref_end, query_start, query_end, hazard, hazard_list;
     DevBuf cig_scratch, cig_count, cig_off, cig_out, ex_hbuf, ex_fbuf, ex_cig, weights, ex_lists, ex_counts, ex_fast_fbuf;
     // windowed align path (sw_align_win.cuh)
-    DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems;
+    DevBuf ckpt, ckpt_base, win_hist, win_bucket, win_items, win_nitems, win_pitems, win_pnitems, win_amb;
     DevBuf starts;  // ranges: reverse-pass results
     DevBuf cig_bsum;  // CIGAR scan: per-block sums
     DevBuf sn_refs, sn_roff, sn_qry, sn_qoff, sn_out;  // SneakySnake filter batch (sneaky_snake.cuh)
@@ -1132,6 +1134,14 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
         CU(ctx, d.win_bucket.reserve((n_keys + 1) * sizeof(uint32_t)));
         CU(ctx, d.win_items.reserve(max_items * sizeof(uint32_t)));
         CU(ctx, d.win_nitems.reserve(sizeof(uint32_t)));
+        CU(ctx, d.win_pitems.reserve(max_items * sizeof(uint32_t)));
+        CU(ctx, d.win_pnitems.reserve(sizeof(uint32_t)));
+        CU(ctx, d.win_amb.reserve(chunk_seqs * n_prof + 16));
+        if (!d.aux_stream) {
+            CU(ctx, cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking));
+            CU(ctx, cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming));
+        }
     } else if (!long_mode) {
         CU(ctx, d.flags.reserve(((chunk_seqs + 1) / 2) * task_stride * 4));
     }
@@ -1516,47 +1526,22 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             cp.cig_count = t.cig_count;
             cp.counters = ctr;
             cp.hazard_list = t.hazard_list;
-            // counting sort of the selected pairs by (profiled sequence, checkpoint block) into wp.items
-            auto bucket = [&](int pin_stage) -> int {
+            // counting sort of the selected pairs by (profiled sequence, checkpoint block) into `items`
+            cp.amb = d.win_amb.as<uint8_t>();
+            auto bucket = [&](int pin_stage, int subset, uint32_t *items, uint32_t *n_items) -> int {
                 cp.pin_stage = pin_stage;
+                cp.subset = subset;
                 CU(ctx, cudaMemsetAsync(d.win_hist.p, 0, n_keys * sizeof(uint32_t), d.stream));
-                CU(ctx, cudaMemsetAsync(d.win_items.p, 0xff, max_items * sizeof(uint32_t), d.stream));
+                CU(ctx, cudaMemsetAsync(items, 0xff, max_items * sizeof(uint32_t), d.stream));
                 win_classify_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp);
                 CU(ctx, cudaGetLastError());
-                win_bucket_scan_kernel<<<1, 1024, 0, d.stream>>>(wp.hist, n_keys, wp.bucket_start, wp.n_items);
+                win_bucket_scan_kernel<<<1, 1024, 0, d.stream>>>(wp.hist, n_keys, wp.bucket_start, n_items);
                 CU(ctx, cudaGetLastError());
-                win_scatter_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp, wp.bucket_start, wp.items);
+                win_scatter_kernel<<<(cpairs + 255) / 256, 256, 0, d.stream>>>(cp, wp.bucket_start, items);
                 CU(ctx, cudaGetLastError());
                 ctx->last_launches += 3;
                 return 0;
             };
-            // ---- pin stage: pairs whose maximum recurs in the winning lane get their exact best cell ----
-            rc = bucket(1);
-            if (rc) return rc;
-            {
-                WinParams wq = wp;
-                wq.pin_mode = 1;
-                wq.s.cols_in_smem = plan_p.cols_in_smem;
-                const uint32_t gpb = plan_p.threads / k->G;
-                const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_p.blocks_per_sm),
-                                                       (uint32_t)((max_items / 2 + gpb - 1) / gpb));
-                k->pin<<<nb, plan_p.threads, plan_p.smem, d.stream>>>(wq);
-                CU(ctx, cudaGetLastError());
-            }
-            // ---- classification proper, window fill, walk ----
-            rc = bucket(0);
-            if (rc) return rc;
-            {
-                WinParams wb = wp;
-                wb.pin_mode = 0;
-                wb.s.cols_in_smem = plan_b.cols_in_smem;
-                const uint32_t gpb = plan_b.threads / k->G;
-                const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_b.blocks_per_sm),
-                                                       (uint32_t)((max_items / 2 + gpb - 1) / gpb));
-                k->winfill<<<nb, plan_b.threads, plan_b.smem, d.stream>>>(wb);
-                CU(ctx, cudaGetLastError());
-            }
-            CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
             TraceWinParams tw{};
             tw.t = t;
             tw.items = wp.items;
@@ -1565,9 +1550,60 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             tw.win_task_stride = win_task_stride;
             tw.cb_log2 = cb_log2;
             tw.slack = win_slack;
-            sw_traceback_win_kernel<<<(uint32_t)((max_items + 127) / 128), 128, 0, d.stream>>>(tw);
-            CU(ctx, cudaGetLastError());
-            ctx->last_launches += 4;
+            auto fill_and_walk = [&]() -> int {  // window fill + walk of the pairs in wp.items
+                WinParams wb = wp;
+                wb.pin_mode = 0;
+                wb.s.cols_in_smem = plan_b.cols_in_smem;
+                const uint32_t gpb = plan_b.threads / k->G;
+                const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_b.blocks_per_sm),
+                                                       (uint32_t)((max_items / 2 + gpb - 1) / gpb));
+                k->winfill<<<nb, plan_b.threads, plan_b.smem, d.stream>>>(wb);
+                CU(ctx, cudaGetLastError());
+                sw_traceback_win_kernel<<<(uint32_t)((max_items + 127) / 128), 128, 0, d.stream>>>(tw);
+                CU(ctx, cudaGetLastError());
+                ctx->last_launches += 2;
+                return 0;
+            };
+            // ---- pin stage: pairs whose maximum recurs in the winning lane get their exact best cell.  Few pairs, long
+            //      sweeps: latency bound (1.6 ms whatever the batch size), so it runs on a second stream beside the
+            //      window fill + walk of the unambiguous pairs; the pinned pairs follow in a second, short pass ----
+            rc = bucket(1, 0, d.win_pitems.as<uint32_t>(), d.win_pnitems.as<uint32_t>());
+            if (rc) return rc;
+            CU(ctx, cudaEventRecord(d.ev_fork, d.stream));
+            CU(ctx, cudaStreamWaitEvent(d.aux_stream, d.ev_fork, 0));
+            {
+                WinParams wq = wp;
+                wq.pin_mode = 1;
+                wq.items = d.win_pitems.as<uint32_t>();
+                wq.n_items = d.win_pnitems.as<uint32_t>();
+                wq.s.cols_in_smem = plan_p.cols_in_smem;
+                // small CTAs (two warps' worth of groups, ~20 KB of tables): they must fit beside the window-fill CTAs,
+                // which take most of an SM's shared memory, or the two streams would simply run one after the other
+                // (small chunks only: with a million pairs the pin sweep has enough tasks to want full-size CTAs, and
+                // then runs before / after the window fill as it always did -- measured 60.8 vs 66.0 ms on 1M reads)
+                const bool small_chunk = cpairs <= 400000u;
+                const int pin_threads = small_chunk ? std::max(k->G, 64) : plan_p.threads;
+                const size_t pin_smem = small_chunk ? score_smem_bytes(ctx, *k, pin_threads, plan_p.cols_in_smem, ctx->ccodes.size())
+                                                    : plan_p.smem;
+                const uint32_t gpb = pin_threads / k->G;
+                const uint32_t nb = std::min<uint32_t>(small_chunk ? (uint32_t)d.sm_count * 2u : (uint32_t)(d.sm_count * plan_p.blocks_per_sm),
+                                                       (uint32_t)((max_items / 2 + gpb - 1) / gpb));
+                k->pin<<<nb, pin_threads, pin_smem, d.aux_stream>>>(wq);
+                CU(ctx, cudaGetLastError());
+                ctx->last_launches++;
+            }
+            CU(ctx, cudaEventRecord(d.ev_join, d.aux_stream));
+            // ---- classification proper, window fill, walk: the unambiguous pairs, then the pinned ones ----
+            rc = bucket(0, 1, wp.items, wp.n_items);
+            if (rc) return rc;
+            rc = fill_and_walk();
+            if (rc) return rc;
+            CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_join, 0));
+            rc = bucket(0, 2, wp.items, wp.n_items);
+            if (rc) return rc;
+            rc = fill_and_walk();
+            if (rc) return rc;
+            CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
         }
 
         unsigned long long hc[5] = {0, 0, 0, 0, 0};  // ctr[4..8]
@@ -2462,12 +2498,15 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
                           &d.query_start, &d.query_end, &d.hazard, &d.hazard_list, &d.cig_scratch, &d.cig_count,
                           &d.cig_off, &d.cig_out, &d.ex_hbuf, &d.ex_fbuf, &d.ex_cig, &d.ex_lists, &d.ex_counts, &d.ex_fast_fbuf, &d.weights, &d.tp_pair, &d.tp_off, &d.tp_cap, &d.tp_slot,
                           &d.tp_blob, &d.tp_ctr, &d.tp_cigoff, &d.tp_bw, &d.tp_list, &d.tp_cig, &d.sn_refs, &d.sn_roff, &d.sn_qry, &d.sn_qoff, &d.sn_out, &d.long_ids, &d.long_bnd,
-                          &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.starts, &d.cig_bsum})
+                          &d.long_queue, &d.ckpt, &d.ckpt_base, &d.win_hist, &d.win_bucket, &d.win_items, &d.win_nitems, &d.win_pitems, &d.win_pnitems, &d.win_amb, &d.starts, &d.cig_bsum})
             b->release();
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
         if (d.ev_k0) cudaEventDestroy(d.ev_k0);
         if (d.ev_k1) cudaEventDestroy(d.ev_k1);
+        if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+        if (d.ev_join) cudaEventDestroy(d.ev_join);
+        if (d.aux_stream) cudaStreamDestroy(d.aux_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
