@@ -15,7 +15,8 @@ the per-rank result checksums are summed (off the clock) and must equal the N = 
 `legs`   = the other half of the metric and the other configurations, timed by the same code in the same run:
            "align" (cfg 3: zoe_cuda_sw_align_batch, device traceback + CIGARs; at N = 1 checked pair by pair against the
            vectorised CPU restatement of sw_simd_align on the WHOLE set), and at N = 1 also "cfg1", "cfg4" (a stated
-           slice), "cfg5".  `--legs none` skips them, `--config C` benches one configuration alone.
+           slice), "cfg4_3pass" (CIGARs for the long reads), "align_tieheavy" (a scoring that sends 6.7 % of the pairs
+           through the literal striped kernels), "cfg5".  `--legs none` skips them, `--config C` benches one alone.
 `--impl reference` times the CPU restatement of zoe's striped path (oracle/zoe_sw_cpu.cpp) on all host threads; zoe
 itself (Rust nightly) cannot be built in this image.
 """
@@ -301,12 +302,20 @@ def pinned(torch, arr: np.ndarray):
 
 
 def run_leg(ctx: Ctx, config: int, mode_override, n_override, steps: int, warmup: int, cpu: bool, cpu_seconds: float,
-            align_opts=None, sample_clocks: bool = False, full_parity: bool = True):
+            align_opts=None, sample_clocks: bool = False, full_parity: bool = True, scoring=None):
     """Times one configuration on this rank's shard; returns the record rank 0 prints (None on the other ranks)."""
     from zoe_b200 import CudaProfiles
 
     torch = ctx.torch
-    key, name, matrix, go, ge, targets, (buf_all, offs_all), mode = make_workload(config, n_override)
+    global SCORING
+    saved_scoring = SCORING
+    if scoring is not None:
+        SCORING = scoring
+    try:
+        key, name, matrix, go, ge, targets, (buf_all, offs_all), mode = make_workload(config, n_override)
+    finally:
+        SCORING = saved_scoring
+    tie_heavy = scoring is not None or SCORING is not None
     if mode_override:
         mode = mode_override
         name += f" [mode {mode}]"
@@ -347,7 +356,7 @@ def run_leg(ctx: Ctx, config: int, mode_override, n_override, steps: int, warmup
             outs[k] = a
     if mode in ("align", "3pass"):
         # CIGAR words: <= 5 per short read; cheap gaps fragment them; long noisy reads need ~1 word per 15 bases
-        cap = pairs * (64 if SCORING else 8) + int(offs[-1]) * n_prof // 6 + 1024
+        cap = pairs * (64 if tie_heavy else 8) + int(offs[-1]) * n_prof // 6 + 1024
         t, a = pinned(torch, np.zeros(pairs + 1, dtype=np.int64))
         keep.append(t)
         outs["cigar_off"] = a.view(np.uint64)
@@ -599,7 +608,7 @@ def main():
     ap.add_argument("--align-opts", default=None, help="mode,checkpoint_log2,slack for zoe_cuda_set_align_options (tuning)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--legs", default="auto", help="auto | none | comma list of align,cfg1,cfg4,cfg5,w512")
+    ap.add_argument("--legs", default="auto", help="auto | none | comma list of align,cfg1,cfg4,cfg4_3pass,align_tieheavy,cfg5,w512")
     ap.add_argument("--leg-steps", type=int, default=5)
     ap.add_argument("--parity", default="full", choices=["full", "sample"],
                     help="full: cfg 1 / 3 / 5 are checked on the whole set (SURVEY 8(d)); sample: a bounded prefix")
@@ -628,7 +637,7 @@ def main():
     want = []
     if args.legs == "auto":
         if not headline_alone and args.n is None:
-            want = ["align", "cfg5", "cfg4", "cfg1", "w512"] if ctx.n_gpus == 1 else ["align"]
+            want = (["align", "cfg5", "cfg4", "cfg4_3pass", "align_tieheavy", "cfg1", "w512"] if ctx.n_gpus == 1 else ["align"])
     elif args.legs != "none":
         want = [x for x in args.legs.split(",") if x]
     for leg in want:
@@ -642,6 +651,17 @@ def main():
             if r:
                 r["config"]["workload"] += " [the first 20000 reads of the 100k-read set]"
             legs["cfg4"] = compact(r)
+        elif leg == "cfg4_3pass":
+            # CIGARs for long reads through the memory-light 3-pass alignment (long-row ranges + banded pass 3)
+            r = run_leg(ctx, 4, "3pass", 20_000, 3, 2, cpu, 5.0, full_parity=full)
+            if r:
+                r["config"]["workload"] += " [the first 20000 reads of the 100k-read set]"
+            legs["cfg4_3pass"] = compact(r)
+        elif leg == "align_tieheavy":
+            # a scoring whose walks meet E == H == F ties (6.7 % of the pairs go through the literal striped
+            # kernels) -- the cost of zoe's lane-layout-dependent tie-breaks, checked on every pair against the CPU port
+            legs["align_tieheavy"] = compact(run_leg(ctx, 3, "align", 200_000, 3, 2, cpu, 6.0, full_parity=full,
+                                                     scoring=(2, -3, -4, -1)))
         elif leg == "cfg1":
             legs["cfg1"] = compact(run_leg(ctx, 1, None, None, max(ls, 20), lw, cpu, 2.0, full_parity=full))
         elif leg == "w512" and cpu and ctx.rank == 0 and ctx.n_gpus == 1:

@@ -85,3 +85,35 @@ def test_standalone_striped_profile_types(bits, signed, lanes, wm, go, ge):
     if bits == 8:
         assert n_over > 0  # near-identical reads score beyond the 8-bit types
     prof.close()
+
+
+@pytest.mark.parametrize("policy", [(8, 32), (16, 32), (32, 32)])
+def test_tiers_agree_across_entry_points_including_unmapped(policy):
+    # `tier` is the width of the type that produced the result -- for Unmapped too (decided in the FIRST tier of
+    # the chain), and the same from score, align, ranges and 3-pass
+    targets, seqs = _inputs(7, n=30)
+    seqs += [b"NNNNNNNNNNNN", b"N"]  # score 0 against anything: Unmapped
+    import numpy as _np
+    buf = _np.frombuffer(b"".join(seqs), dtype=_np.uint8)
+    offs = _np.zeros(len(seqs) + 1, dtype=_np.uint64)
+    offs[1:] = _np.cumsum([len(s) for s in seqs])
+    prof = CudaProfiles.new_with_w256(targets, W25, -10, -1)
+    prof.set_width_policy(policy[0], policy[1])
+    score, status, tier = prof.sw_score_arrays(buf, offs)
+    al = prof.align_arrays(buf, offs)
+    rg = prof.ranges_arrays(buf, offs)
+    tp = prof.align_arrays(buf, offs, three_pass=True)
+    prof.close()
+    n_pairs = len(seqs) * len(targets)
+    sc = osc(W25, -10, -1)
+    for name, got in (("align", al), ("ranges", rg), ("3pass", tp)):
+        assert _np.array_equal(got["status"][:n_pairs], status.ravel()), name
+        assert _np.array_equal(got["tier"][:n_pairs], tier.ravel()), name
+    assert (status.ravel() == 2).any()
+    assert (tier.ravel()[status.ravel() == 2] == policy[0]).all()
+    for i, s in enumerate(seqs):
+        for j, t in enumerate(targets):
+            rc, _, want_tier = O.sw_score_from(t, s, sc, first_bits=policy[0])
+            assert int(status[i, j]) == rc
+            if rc != 1:
+                assert int(tier[i, j]) == want_tier, (i, j, rc, tier[i, j], want_tier)

@@ -107,8 +107,11 @@ __device__ __forceinline__ uint32_t win_start(uint32_t r_end, uint32_t c_end, ui
 // share the profiled sequence and the end column; rows = each item's reversed prefix streamed[r_end], streamed[r_end-1],
 // ..., columns = profiled[c_end], profiled[c_end-1], ...; no checkpoints -- the reversed alignment starts in the
 // corner, so the exact best cell is pinned by re-sweeping the first columns from scratch inside the same kernel.
+#ifndef ZOE_SCAN_THREADS
+#define ZOE_SCAN_THREADS 640
+#endif
 template <int G, int K, bool CSM = true, bool REV = false>
-__global__ void __launch_bounds__(K > 24 ? 256 : 512) sw_align_scan_kernel(const WinParams wp) {
+__global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZOE_SCAN_THREADS : 512)) sw_align_scan_kernel(const WinParams wp) {
     using O = Ops<true>;
     const ScoreParams &p = wp.s;
     constexpr int K4 = (K + 3) / 4;

@@ -233,8 +233,11 @@ __device__ __forceinline__ void build_task_table(const TaskSmem &m, const ScoreP
 #ifndef ZOE_SCORE_PP
 #define ZOE_SCORE_PP 1
 #endif
+#ifndef ZOE_SCORE2_THREADS
+#define ZOE_SCORE2_THREADS 384
+#endif
 template <int G, int K, bool PACKED, int NS, bool PP = (ZOE_SCORE_PP && NS == 2 && K <= 19)>
-__global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? 384 : 512) sw_score_kernel(const ScoreParams p) {
+__global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? ZOE_SCORE2_THREADS : 512) sw_score_kernel(const ScoreParams p) {
     using O = Ops<PACKED>;
     constexpr int K4 = (K + 3) / 4;
     constexpr unsigned FULL = 0xffffffffu;

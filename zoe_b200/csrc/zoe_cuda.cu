@@ -446,7 +446,7 @@ int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan
     for (int cols_in_smem = 1; cols_in_smem >= 0; --cols_in_smem) {
         if (cols_in_smem && cc_bytes > kColsSmemLimit) continue;
         static const int env_max_threads = getenv("ZOE_CUDA_MAX_THREADS") ? atoi(getenv("ZOE_CUDA_MAX_THREADS")) : 1024;
-        for (int threads : {512, 448, 384, 352, 320, 288, 256, 224, 192, 160, 128, 96, 64, 32}) {
+        for (int threads : {640, 576, 512, 448, 384, 352, 320, 288, 256, 224, 192, 160, 128, 96, 64, 32}) {
             if (threads < k.G || threads % k.G || threads > fa.maxThreadsPerBlock || threads > env_max_threads) continue;
             size_t smem = score_smem_bytes(ctx, k, threads, cols_in_smem, cc_bytes, tabs_per_group);
             if (smem > 227 * 1024) continue;
