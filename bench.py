@@ -581,6 +581,67 @@ def run_leg(ctx: Ctx, config: int, mode_override, n_override, steps: int, warmup
     return rec
 
 
+def sneaky_leg(ctx: Ctx, cpu: bool, n: int = 1_000_000, threshold: float = 0.1):
+    """the SneakySnake pre-alignment filter on 1M (150-nt window, 150-nt read) pairs -- an HBM-light
+    byte-compare kernel, reported in pairs/s with the bytes it has to move against the measured HBM peak."""
+    from zoe_b200 import SneakySnake
+
+    torch = ctx.torch
+    rng = np.random.default_rng(9)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    refs = acgt[rng.integers(0, 4, (n, 150))]
+    qs = refs.copy()
+    nerr = rng.integers(0, 30, n)  # 0..29 substitutions per read: both outcomes occur at threshold 0.1 (15 edits)
+    pos = rng.integers(0, 150, (n, 30))
+    mask = np.arange(30)[None, :] < nerr[:, None]
+    rows = np.repeat(np.arange(n), 30).reshape(n, 30)[mask]
+    qs[rows, pos[mask]] = acgt[rng.integers(0, 4, int(mask.sum()))]
+    offs = (np.arange(n + 1, dtype=np.uint64) * np.uint64(150)).astype(np.uint64)
+    t_r, h_r = pinned(torch, np.ascontiguousarray(refs.reshape(-1)))
+    t_q, h_q = pinned(torch, np.ascontiguousarray(qs.reshape(-1)))
+    snake = SneakySnake()
+    for _ in range(2):
+        out = snake.filter_arrays(h_r, offs, h_q, offs, threshold)
+    tot, ker = [], []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        out = snake.filter_arrays(h_r, offs, h_q, offs, threshold)
+        wall = (time.perf_counter() - t0) * 1e3
+        a, b = snake.last_timing()
+        tot.append(max(a, wall))
+        ker.append(b)
+    snake.close()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_moved = float(h_r.nbytes + h_q.nbytes + 2 * offs.nbytes + n)
+    k_ms, e_ms = float(np.mean(ker)), float(np.mean(tot))
+    rec = {"workload": f"{n} pairs of (150-nt window, 150-nt read with 0-29 substitutions), threshold {threshold}",
+           "value": n / (k_ms * 1e-3) / 1e6, "unit": "Mpairs/s", "ms_per_step": k_ms,
+           "e2e": {"value": n / (e_ms * 1e-3) / 1e6, "unit": "Mpairs/s", "ms_per_step": e_ms,
+                   "h2d_bytes_per_step": int(h_r.nbytes + h_q.nbytes + 2 * offs.nbytes), "d2h_bytes_per_step": n},
+           "roofline": {"bound": "hbm", "achieved": bytes_moved / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bytes_moved / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                        "note": "algorithmic bytes = both sequences + offsets + 1 result byte per pair, each read once; the "
+                                "kernel is a chain of dependent byte compares per pair (latency, not bandwidth, bound)"},
+           "outcomes": {"some_true": int((out == 1).sum()), "some_false": int((out == 0).sum()), "none": int((out == 2).sum())}}
+    if cpu:
+        from oracle import oracle as O
+        m = 20000
+        t0 = time.perf_counter()
+        want = [O.sneaky_snake(bytes(refs[i]), bytes(qs[i]), threshold) for i in range(m)]
+        dt = time.perf_counter() - t0
+        code = {False: 0, True: 1, None: 2}
+        mism = int(sum(1 for i in range(m) if code[want[i]] != int(out[i])))
+        rec["parity"] = {"checked_pairs": m, "of_pairs": n, "mismatches": mism, "against": "oracle/zoe_sw_oracle.c zo_sneaky_snake"}
+        rec["cpu_baseline"] = {"value": m / dt / 1e6, "unit": "Mpairs/s", "cores": 1, "kind": "port",
+                               "sample": f"first {m} pairs, plain-C restatement called pair by pair through ctypes ({dt:.1f} s)"}
+    return rec
+
+
 def compact(rec):
     """An extra leg's record inside the headline line: the same keys, minus the long prose."""
     if rec is None:
@@ -637,7 +698,7 @@ def main():
     want = []
     if args.legs == "auto":
         if not headline_alone and args.n is None:
-            want = (["align", "cfg5", "cfg4", "cfg4_3pass", "align_tieheavy", "cfg1", "w512"] if ctx.n_gpus == 1 else ["align"])
+            want = (["align", "cfg5", "cfg4", "cfg4_3pass", "align_tieheavy", "cfg1", "sneaky", "w512"] if ctx.n_gpus == 1 else ["align"])
     elif args.legs != "none":
         want = [x for x in args.legs.split(",") if x]
     for leg in want:
@@ -662,6 +723,8 @@ def main():
             # kernels) -- the cost of zoe's lane-layout-dependent tie-breaks, checked on every pair against the CPU port
             legs["align_tieheavy"] = compact(run_leg(ctx, 3, "align", 200_000, 3, 2, cpu, 6.0, full_parity=full,
                                                      scoring=(2, -3, -4, -1)))
+        elif leg == "sneaky" and ctx.rank == 0 and ctx.n_gpus == 1:
+            legs["sneaky_snake"] = sneaky_leg(ctx, cpu)
         elif leg == "cfg1":
             legs["cfg1"] = compact(run_leg(ctx, 1, None, None, max(ls, 20), lw, cpu, 2.0, full_parity=full))
         elif leg == "w512" and cpu and ctx.rank == 0 and ctx.n_gpus == 1:

@@ -32,7 +32,7 @@ while time.time() < t_end:
     lanes = [(16, 8, 4), (32, 16, 8), (64, 32, 16)][int(rng.integers(0, 3))]
     pq = bool(rng.integers(0, 2))
     max_t = int(rng.choice([60, 300, 1500, 1500, 30000]))
-    max_r = int(rng.choice([40, 150, 400, 1024]))
+    max_r = int(rng.choice([40, 150, 400, 1024, 1024, 2600]))  # beyond 1024: the long-row ranges / 3-pass / align paths
     targets = [rand_seq(int(rng.integers(1, max_t + 1))) for _ in range(int(rng.integers(1, 7 if max_t < 30000 else 5)))]
     seqs = []
     for _ in range(int(rng.integers(20, 60))):

@@ -95,3 +95,34 @@ def test_gpu_read_sized_batch():
     assert got == [O.sneaky_snake(r, q, 0.1) for r, q in zip(refs, qs)]
     assert True in got and False in got
     snake.close()
+
+
+@pytest.mark.gpu
+def test_gpu_warp_and_thread_kernels_agree_on_long_and_ragged_pairs():
+    # pairs beyond the warp kernel's staging area take zoe's loops one thread per pair; both must give the oracle's answer
+    import os
+    from zoe_b200 import SneakySnake
+    rng = np.random.default_rng(12)
+    refs, qs = [], []
+    for L in list(rng.integers(1, 1400, 150)) + [1023, 1024, 1025]:
+        ref = rng.choice(list(b"ACGT"), int(L)).astype(np.uint8)
+        q = ref.copy()
+        for pos in rng.integers(0, int(L), int(rng.integers(0, max(2, int(L) // 8)))):
+            q[pos] = rng.choice(list(b"ACGT"))
+        if rng.random() < 0.3 and L > 4:
+            q = np.delete(q, int(rng.integers(0, len(q))))
+        refs.append(bytes(ref))
+        qs.append(bytes(q))
+    short = [i for i in range(len(refs)) if max(len(refs[i]), len(qs[i])) <= 1024]
+    snake = SneakySnake()
+    for thr in (0.02, 0.1, 0.3):
+        want = [O.sneaky_snake(r, q, thr) for r, q in zip(refs, qs)]
+        assert snake.sneaky_snake_batch(refs, qs, thr) == want                       # thread kernel (a pair > 1024)
+        sr, sq = [refs[i] for i in short], [qs[i] for i in short]
+        assert snake.sneaky_snake_batch(sr, sq, thr) == [want[i] for i in short]    # warp kernel
+        os.environ["ZOE_CUDA_SNAKE_THREAD"] = "1"
+        try:
+            assert snake.sneaky_snake_batch(sr, sq, thr) == [want[i] for i in short]
+        finally:
+            os.environ.pop("ZOE_CUDA_SNAKE_THREAD", None)
+    snake.close()

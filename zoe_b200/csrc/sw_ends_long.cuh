@@ -45,8 +45,11 @@ struct EndsLongParams {
     unsigned long long *counters;  // [7] scan and pin disagree (internal error)
 };
 
+#ifndef ZOE_ENDS_LONG_THREADS
+#define ZOE_ENDS_LONG_THREADS 384
+#endif
 template <int K, bool PACKED, bool REV>
-__global__ void __launch_bounds__(384) sw_ends_long_kernel(const EndsLongParams lp) {
+__global__ void __launch_bounds__(ZOE_ENDS_LONG_THREADS) sw_ends_long_kernel(const EndsLongParams lp) {
     using O = Ops<PACKED>;
     const ScoreParams &p = lp.s;
     constexpr int G = 32;

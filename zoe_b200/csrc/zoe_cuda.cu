@@ -1581,10 +1581,15 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                 // which take most of an SM's shared memory, or the two streams would simply run one after the other
                 // (small chunks only: with a million pairs the pin sweep has enough tasks to want full-size CTAs, and
                 // then runs before / after the window fill as it always did -- measured 60.8 vs 66.0 ms on 1M reads)
-                const bool small_chunk = cpairs <= 400000u;
-                const int pin_threads = small_chunk ? std::max(k->G, 64) : plan_p.threads;
-                const size_t pin_smem = small_chunk ? score_smem_bytes(ctx, *k, pin_threads, plan_p.cols_in_smem, ctx->ccodes.size())
-                                                    : plan_p.smem;
+                bool small_chunk = cpairs <= 400000u;
+                int pin_threads = small_chunk ? std::min(plan_p.threads, std::max(k->G, 64)) : plan_p.threads;
+                size_t pin_smem = small_chunk ? score_smem_bytes(ctx, *k, pin_threads, plan_p.cols_in_smem, ctx->ccodes.size())
+                                              : plan_p.smem;
+                if (pin_smem > plan_p.smem) {  // (large per-group tables: the planned launch is already the small one)
+                    small_chunk = false;
+                    pin_threads = plan_p.threads;
+                    pin_smem = plan_p.smem;
+                }
                 const uint32_t gpb = pin_threads / k->G;
                 const uint32_t nb = std::min<uint32_t>(small_chunk ? (uint32_t)d.sm_count * 2u : (uint32_t)(d.sm_count * plan_p.blocks_per_sm),
                                                        (uint32_t)((max_items / 2 + gpb - 1) / gpb));
@@ -1734,7 +1739,7 @@ int launch_ends_long(zoe_cuda_ctx *ctx, Device &d, EndsLongParams lp, uint32_t n
         CU(ctx, cudaFuncGetAttributes(&fa, fn));
         for (int cols_in_smem = 1; cols_in_smem >= 0 && best_warps == 0; --cols_in_smem) {
             if (cols_in_smem && ctx->ccodes.size() > kColsSmemLimit) continue;
-            for (int threads : {384, 320, 256, 192, 128, 64, 32}) {
+            for (int threads : {512, 448, 384, 320, 256, 192, 128, 64, 32}) {
                 if (threads > fa.maxThreadsPerBlock) continue;
                 const size_t smem = tab_per_warp * (threads / 32) + fixed + (cols_in_smem ? ((ctx->ccodes.size() + 15) & ~(size_t)15) : 0);
                 if (smem > 227 * 1024) continue;
@@ -3041,8 +3046,22 @@ int zoe_cuda_sneaky_snake_batch(zoe_cuda_ctx *ctx, const uint8_t *refs, const ui
         sp.n = cnt;
         sp.threshold = threshold;
         sp.out = d.sn_out.as<uint8_t>();
-        sneaky_snake_kernel<<<(uint32_t)((cnt + 127) / 128), 128, 0, d.stream>>>(sp);
+        CU(ctx, cudaEventRecord(d.ev_k0, d.stream));
+        // warp per pair when both sequences of every pair fit the staging area, else zoe's loops one thread per pair
+        uint64_t longest = 0;
+        for (uint64_t q = lo; q < hi; ++q)
+            longest = std::max<uint64_t>(longest, std::max(ref_offsets[q + 1] - ref_offsets[q], query_offsets[q + 1] - query_offsets[q]));
+        if (longest <= (uint64_t)kSnakeStage && !getenv("ZOE_CUDA_SNAKE_THREAD")) {
+            const int wpb = 8;
+            const size_t smem = (size_t)wpb * 2 * kSnakeStage;
+            const uint32_t nb = (uint32_t)std::min<uint64_t>((cnt + wpb - 1) / wpb, (uint64_t)d.sm_count * 32);
+            sneaky_snake_warp_kernel<<<nb, wpb * 32, smem, d.stream>>>(sp);
+        } else {
+            sneaky_snake_kernel<<<(uint32_t)((cnt + 127) / 128), 128, 0, d.stream>>>(sp);
+        }
         CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
+        d.timed_kernel = true;
         ctx->last_launches++;
         CU(ctx, cudaMemcpyAsync(out + lo, d.sn_out.p, cnt, cudaMemcpyDeviceToHost, d.stream));
     }

@@ -50,6 +50,12 @@ class SneakySnake:
         qb, qo = _pack(queries)
         return [_RESULT[int(v)] for v in self.filter_arrays(rb, ro, qb, qo, threshold)]
 
+    def last_timing(self):
+        """(total ms incl. copies, kernel ms) of the last call, from CUDA events on the library's stream."""
+        t, k, n = C.c_float(0), C.c_float(0), C.c_uint32(0)
+        self._lib.zoe_cuda_last_timing(self._h, C.byref(t), C.byref(k), C.byref(n))
+        return t.value, k.value
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.zoe_cuda_destroy(self._h)
