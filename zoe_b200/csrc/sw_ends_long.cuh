@@ -288,6 +288,14 @@ __global__ void __launch_bounds__(ZOE_ENDS_LONG_THREADS) sw_ends_long_kernel(con
                     column(parity, fullk, j, h_in, e_in, (uint32_t)scs[REV ? -j : j]);
                     h_up_prev = h_in;
                 };
+                auto block_step = [&](auto parity, const int step, const int k) {  // inside a 32-step block: no per-step tests
+                    const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1), e_sh = __shfl_up_sync(FULL, e_out, 1);
+                    const uint32_t h_top = __shfl_sync(FULL, cur.x, k), e_top = __shfl_sync(FULL, cur.y, k);
+                    const uint32_t h_in = h_sh * nz + h_top * top_on, e_in = e_sh * nz + e_top * top_on;
+                    const int j = step - lane;
+                    column(parity, std::true_type{}, j, h_in, e_in, (uint32_t)scs[REV ? -j : j]);
+                    h_up_prev = h_in;
+                };
 
                 const bool fast = !PIN && p.cols_in_smem != 0;
                 const bool fullk = k4_eff == K4;
@@ -298,6 +306,20 @@ __global__ void __launch_bounds__(ZOE_ENDS_LONG_THREADS) sw_ends_long_kernel(con
                     const int end = seg_end[seg];
                     if (seg == 1) {
                         if (fast && fullk) {
+                            // whole blocks of 32 steps: boundary-row prefetch and hand-over once per block (sw_score_long.cuh)
+                            for (; step + 32 <= end; step += 32) {
+                                if (has_top) {
+                                    const int idx = step + 32 + lane;
+                                    nxt = (idx < L) ? __ldcg(bnd_top + idx) : make_uint2(0, 0);
+                                }
+#pragma unroll 1
+                                for (int k = 0; k < 32; k += 2) {
+                                    block_step(P0{}, step + k, k);
+                                    block_step(P1{}, step + k + 1, k + 1);
+                                    bookkeeping((uint32_t)(step + k));
+                                }
+                                cur = nxt;
+                            }
                             for (; step < end; step += 2) {
                                 steady_step(P0{}, std::true_type{}, step);
                                 steady_step(P1{}, std::true_type{}, step + 1);

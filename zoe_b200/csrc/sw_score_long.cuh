@@ -201,6 +201,15 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
                     if (j >= 0 && j < L) column(parity, std::false_type{}, j, h_in, e_in, (uint32_t)cs[j]);
                     h_up_prev = h_in;
                 };
+                // a steady step inside a 32-step block: inputs without the per-step prefetch / hand-over tests
+                auto block_step = [&](auto parity, const int step, const int k) {
+                    const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1), e_sh = __shfl_up_sync(FULL, e_out, 1);
+                    const uint32_t h_top = __shfl_sync(FULL, cur.x, k), e_top = __shfl_sync(FULL, cur.y, k);
+                    const uint32_t h_in = h_sh * nz + h_top * top_on, e_in = e_sh * nz + e_top * top_on;
+                    const int j = step - kSkewLong * lane;
+                    column(parity, std::true_type{}, j, h_in, e_in, (uint32_t)scs[j]);
+                    h_up_prev = h_in;
+                };
                 auto steady_step = [&](auto parity, auto fullk, const int step) {
                     uint32_t h_in, e_in;
                     inputs(step, h_in, e_in);
@@ -219,6 +228,21 @@ __global__ void __launch_bounds__(512) sw_score_long_kernel(const LongParams lp)
                     const int end = seg_end[seg];
                     if (seg == 1) {
                         if (fast && fullk) {
+                            // whole blocks of 32 steps (the steady segment starts at step 32): the boundary-row prefetch
+                            // and the hand-over cur <- nxt happen once per block, outside the two-step body, instead of
+                            // being tested in every step (5.04 -> 4.9 ALU-pipe instructions per cell pair)
+                            for (; step + 32 <= end; step += 32) {
+                                if (has_top) {
+                                    const int idx = step + 32 + lane;
+                                    nxt = (idx < L) ? __ldcg(bnd + idx) : make_uint2(0, 0);
+                                }
+#pragma unroll 1
+                                for (int k = 0; k < 32; k += 2) {
+                                    block_step(P0{}, step + k, k);
+                                    block_step(P1{}, step + k + 1, k + 1);
+                                }
+                                cur = nxt;
+                            }
                             for (; step < end; step += 2) {
                                 steady_step(P0{}, std::true_type{}, step);
                                 steady_step(P1{}, std::true_type{}, step + 1);
