@@ -100,7 +100,22 @@ struct ScoreParams {
     int32_t *best;             // [n_rseq * n_cseq] exact score, or -1 = needs the wide kernel
     uint32_t best_stride;      // row stride of `best` (0 = n_cseq) and first column: a launch may cover a sub-range of the
     uint32_t best_col0;        // profiled set (panels larger than the shared-memory staging area are swept group by group)
+    // End-to-end calls: the batch is uploaded in chunks by the copy engine WHILE the first kernel runs; `progress` holds the
+    // number of bytes of rseq that have arrived (a 4-byte DMA write after every chunk, in stream order, chunk boundaries on
+    // 128-byte lines so no line is ever fetched half-arrived).  nullptr = the batch is resident.
+    const unsigned int *progress;
 };
+
+// Spin until the first `need` bytes of the streamed batch are on the device (see ScoreParams::progress).
+__device__ __forceinline__ void wait_for_bytes(const unsigned int *progress, unsigned long long need) {
+    if (progress == nullptr) return;
+    unsigned int have;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(progress) : "memory");
+        if ((unsigned long long)have >= need) break;
+        __nanosleep(256);
+    }
+}
 
 template <bool PACKED>
 struct Ops;
@@ -301,6 +316,7 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? ZOE_SCORE2_THREA
             len_hi = (int)(p.roff[id_hi + 1] - off_hi);
         }
 
+        wait_for_bytes(p.progress, max(off_lo + (uint64_t)len_lo, off_hi + (uint64_t)len_hi));
         build_task_table<G, K, PACKED>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
 
         // ---- sweep the column sequences, NS at a time ----

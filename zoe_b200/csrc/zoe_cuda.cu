@@ -79,6 +79,18 @@ struct Device {
     int sm_count = 0;
     size_t free_at_create = 0;  // cudaMemGetInfo is slow (tens of ms on a 180 GB part): asked once
     cudaStream_t stream = nullptr;
+    // per-profiled-sequence base offsets (flag_base / ckpt_base) are a function of the profiled set, the kernel's (G, K) and
+    // the checkpoint spacing: uploaded once and reused (a pageable-memory copy synchronises the stream: 0.4 ms per call)
+    uint64_t flb_epoch = 0, ckb_epoch = 0;
+    int flb_G = 0, flb_K = 0, ckb_G = 0, ckb_K = 0, ckb_cb = -1;
+    bool ckpt_base_cached(uint64_t epoch, int G, int K, int cb) const { return ckb_epoch == epoch && ckb_G == G && ckb_K == K && ckb_cb == cb; }
+    void ckpt_base_mark(uint64_t epoch, int G, int K, int cb) { ckb_epoch = epoch; ckb_G = G; ckb_K = K; ckb_cb = cb; }
+    // streamed upload (end-to-end calls): chunks + a bytes-arrived word on `copy_stream`, polled by the first kernel
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_first = nullptr, ev_copied = nullptr;
+    DevBuf progress;
+    unsigned int *prog_host = nullptr;  // pinned: the values the copy engine writes into `progress`
+    bool copy_pending = false;
     cudaStream_t aux_stream = nullptr;  // align: the pin sweep of the ambiguous pairs runs beside the main window fill
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -177,6 +189,7 @@ struct PlanKey {
 struct zoe_cuda_ctx {
     std::vector<Device> devs;
     std::map<PlanKey, LaunchPlan> plans;  // launch configurations, valid for the current scoring + profiled set
+    uint64_t profiled_epoch = 1;          // bumped by set_profiled: invalidates what the devices cached about the set
     // One extra stream + buffer set per GPU: zoe_cuda_sw_score_batch alternates sub-batches between devs[k] and alt[k]
     // so that the H2D copy of sub-batch i+1 and the D2H copy of sub-batch i-1 overlap the kernels of sub-batch i.
     std::vector<Device> alt;
@@ -586,16 +599,60 @@ int prepare_batch(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offs
 }
 
 // Uploads the sequences [d.n_first, d.n_first + d.n_count) of the batch to `d` (async on d.stream).
-int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint64_t *offsets, bool record_begin = true) {
+constexpr int kUploadChunks = 8;
+
+// The first kernel of a call that was staged with `streamed` polls d.progress; everything else needs the whole batch.
+int ensure_resident(zoe_cuda_ctx *ctx, Device &d) {
+    if (!d.copy_pending) return 0;
+    CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_copied, 0));
+    d.copy_pending = false;
+    return 0;
+}
+
+// streamed: upload the bytes in chunks on the copy stream, a "bytes arrived" word after each, and let d.stream go on after
+// the first chunk -- sw_score_kernel / sw_align_scan_kernel poll the word before they touch a sequence (ScoreParams::progress),
+// so the copy engine runs beside the first kernel instead of in front of it (config 3: 3.3 ms of a 70 ms call).
+int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint64_t *offsets, bool record_begin = true,
+                 bool streamed = false) {
     CU(ctx, cudaSetDevice(d.id));
     if (record_begin) CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
+    d.copy_pending = false;
     if (d.n_count == 0) return 0;
     uint64_t b0 = offsets[d.n_first], b1 = offsets[d.n_first + d.n_count];
     d.rseq_bytes = b1 - b0;
     CU(ctx, d.rseq.reserve(d.rseq_bytes + 16));
     CU(ctx, d.roff.reserve((d.n_count + 1) * sizeof(uint64_t)));
-    if (d.rseq_bytes)
+    streamed = streamed && d.rseq_bytes >= ((uint64_t)8 << 20) && d.rseq_bytes < 0xfff00000ull && !getenv("ZOE_CUDA_NO_STREAMED_UPLOAD");
+    if (streamed) {
+        if (!d.copy_stream) {
+            CU(ctx, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+            CU(ctx, cudaEventCreateWithFlags(&d.ev_first, cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&d.ev_copied, cudaEventDisableTiming));
+            CU(ctx, cudaHostAlloc((void **)&d.prog_host, (kUploadChunks + 2) * sizeof(unsigned int), cudaHostAllocDefault));
+            CU(ctx, d.progress.reserve(sizeof(unsigned int)));
+        }
+        CU(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_begin, 0));
+        d.prog_host[0] = 0;
+        CU(ctx, cudaMemcpyAsync(d.progress.p, &d.prog_host[0], sizeof(unsigned int), cudaMemcpyHostToDevice, d.copy_stream));
+        uint64_t lo = 0;
+        for (int c = 0; c < kUploadChunks; ++c) {
+            // a small first chunk (1/16) so the kernel starts early; boundaries on 128-byte lines of the device buffer
+            uint64_t hi = c + 1 == kUploadChunks ? d.rseq_bytes
+                                                 : ((d.rseq_bytes / 16 + (d.rseq_bytes - d.rseq_bytes / 16) * c / (kUploadChunks - 1)) + 127) & ~127ull;
+            hi = std::min<uint64_t>(std::max(hi, lo), d.rseq_bytes);
+            if (hi > lo)
+                CU(ctx, cudaMemcpyAsync((uint8_t *)d.rseq.p + lo, concat + b0 + lo, hi - lo, cudaMemcpyHostToDevice, d.copy_stream));
+            d.prog_host[c + 1] = (unsigned int)hi;
+            CU(ctx, cudaMemcpyAsync(d.progress.p, &d.prog_host[c + 1], sizeof(unsigned int), cudaMemcpyHostToDevice, d.copy_stream));
+            if (c == 0) CU(ctx, cudaEventRecord(d.ev_first, d.copy_stream));
+            lo = hi;
+        }
+        CU(ctx, cudaEventRecord(d.ev_copied, d.copy_stream));
+        CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_first, 0));
+        d.copy_pending = true;
+    } else if (d.rseq_bytes) {
         CU(ctx, cudaMemcpyAsync(d.rseq.p, concat + b0, d.rseq_bytes, cudaMemcpyHostToDevice, d.stream));
+    }
     // the shard's offsets go up as the caller holds them (one copy straight from the caller's buffer, which
     // outlives the call) and are rebased to the shard's first byte on the device
     CU(ctx, cudaMemcpyAsync(d.roff.p, offsets + d.n_first, (d.n_count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
@@ -615,13 +672,38 @@ int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint
     return 0;
 }
 
-int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n) {
-    int rc = prepare_batch(ctx, concat, offsets, n);
-    if (rc) return rc;
-    for (Device &d : ctx->devs) {
-        rc = stage_device(ctx, d, concat, offsets);
-        if (rc) return rc;
+int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n, bool streamed = false) {
+    // The upload only needs the shard boundaries, so it is queued first (after the cheap checks) and the pass over all
+    // offsets -- validation, longest / shortest sequence, cells: 0.9 ms of host time for 1M reads -- runs while the copy
+    // engine works.  A batch that fails validation is reported after the copies have drained.
+    if (!ctx->have_profiled) return fail(ctx, ZOE_CUDA_E_STATE, "set_profiled must be called before a batch");
+    if (n > 0 && (!concat || !offsets)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null batch pointers");
+    if (n >= 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "batch too large");
+    bool early = n > 0;
+    if (early) {
+        shard(ctx, n);
+        for (Device &d : ctx->devs)  // shard boundaries must be ordered or nothing is queued early
+            if (d.n_count && offsets[d.n_first + d.n_count] < offsets[d.n_first]) early = false;
     }
+    int rc = 0;
+    if (early)
+        for (Device &d : ctx->devs) {
+            rc = stage_device(ctx, d, concat, offsets, true, streamed);
+            if (rc) return rc;
+        }
+    rc = prepare_batch(ctx, concat, offsets, n);
+    if (rc) {
+        for (Device &d : ctx->devs) {
+            cudaSetDevice(d.id);
+            cudaStreamSynchronize(d.stream);
+        }
+        return rc;
+    }
+    if (!early)
+        for (Device &d : ctx->devs) {
+            rc = stage_device(ctx, d, concat, offsets, true, streamed);
+            if (rc) return rc;
+        }
     ctx->staged = true;
     return 0;
 }
@@ -644,7 +726,11 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
     p.ovf_thresh = kPackedLimit - std::max(ctx->max_weight, 0) - 1;
     p.best = d.best.as<int32_t>();
     p.best_stride = ctx->n_prof;
-    if (p.n_tasks == 0) return 0;
+    if (p.n_tasks == 0) return ensure_resident(ctx, d);
+    if (task_ids) {  // a re-run of listed sequences: no streamed upload can still be pending, but make sure
+        int rc0 = ensure_resident(ctx, d);
+        if (rc0) return rc0;
+    }
 
     // one launch over the whole profiled set, or (panels beyond the staging area) one launch per group of profiled
     // sequences whose codes fit shared memory: the steady-state loops read the column codes from shared memory
@@ -681,9 +767,12 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
         uint32_t max_blocks = (uint32_t)(d.sm_count * plan.blocks_per_sm);
         uint32_t need_blocks = (p.n_tasks + groups_per_block - 1) / groups_per_block;
         uint32_t blocks = std::min(max_blocks, need_blocks);
+        p.progress = d.copy_pending ? d.progress.as<unsigned int>() : nullptr;  // the first launch runs beside the upload
         fn<<<blocks, plan.threads, plan.smem, d.stream>>>(p);
         CU(ctx, cudaGetLastError());
         ctx->last_launches++;
+        rc = ensure_resident(ctx, d);
+        if (rc) return rc;
     }
     return 0;
 }
@@ -716,6 +805,7 @@ bool rows_path_applies(const zoe_cuda_ctx *ctx) {
 }
 
 int launch_score_rows(zoe_cuda_ctx *ctx, Device &d) {
+    if (int rc0 = ensure_resident(ctx, d)) return rc0;
     const RowsEntry *k = nullptr;
     const bool stream = ctx->staged_min_len >= 64 && !getenv("ZOE_CUDA_NO_ROWS_STREAM");
     for (const RowsEntry &e : (stream ? kRowsStreamKernels : kRowsKernels))
@@ -855,6 +945,7 @@ int launch_score_long(zoe_cuda_ctx *ctx, Device &d, const uint32_t *d_ids, uint3
 }
 
 int run_score_long_on_device(zoe_cuda_ctx *ctx, Device &d) {
+    if (int rc0 = ensure_resident(ctx, d)) return rc0;
     // longest-first order, so that (a) the two halves of a packed task have similar lengths and (b) the
     // atomic queue hands out the big tasks first
     std::vector<uint32_t> order(d.n_count);
@@ -1083,6 +1174,8 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     bool use_window = window_ok && (uint64_t)ctx->max_prof_len >= 2ull * wmax;
     if (ctx->align_mode == 1) use_window = false;
     if (long_mode) use_window = false;
+    if (!use_window)
+        if (int rc0 = ensure_resident(ctx, d)) return rc0;
     if (ctx->align_mode == 2) use_window = window_ok;
     if (const char *e = getenv("ZOE_CUDA_ALIGN_MODE")) {
         if (!strcmp(e, "full")) use_window = false;
@@ -1118,18 +1211,25 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
     uint64_t chunk_seqs = std::min<uint64_t>(d.n_count, tasks_cap * 2);
     if (chunk_seqs > 1) chunk_seqs &= ~1ULL;
 
-    CU(ctx, d.flag_base.reserve(n_prof * sizeof(uint64_t)));
-    CU(ctx, cudaMemcpyAsync(d.flag_base.p, flag_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
-    CU(ctx, cudaStreamSynchronize(d.stream));
+    const bool flb_cached = d.flb_epoch == ctx->profiled_epoch && d.flb_G == k->G && d.flb_K == k->K;
+    const bool ckb_cached = d.ckpt_base_cached(ctx->profiled_epoch, k->G, k->K, cb_log2);
+    if (!flb_cached || !ckb_cached) {
+        CU(ctx, d.flag_base.reserve(n_prof * sizeof(uint64_t)));
+        CU(ctx, d.ckpt_base.reserve(n_prof * sizeof(uint64_t)));
+        CU(ctx, cudaMemcpyAsync(d.flag_base.p, flag_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaMemcpyAsync(d.ckpt_base.p, ckpt_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        d.flb_epoch = ctx->profiled_epoch;
+        d.flb_G = k->G;
+        d.flb_K = k->K;
+        d.ckpt_base_mark(ctx->profiled_epoch, k->G, k->K, cb_log2);
+    }
     dbg0.lap("align: flag_base upload");
     CU(ctx, d.ends.reserve(pairs * sizeof(AlignEnd)));
     if (use_window) {
         const uint64_t max_items = chunk_seqs * n_prof + n_keys + 2;  // every bucket rounds up to even
         CU(ctx, d.flags.reserve((max_items / 2 + 1) * win_task_stride * 4));
         CU(ctx, d.ckpt.reserve(std::max<uint64_t>(((chunk_seqs + 1) / 2) * ckpt_task_stride * 4, 16)));
-        CU(ctx, d.ckpt_base.reserve(n_prof * sizeof(uint64_t)));
-        CU(ctx, cudaMemcpyAsync(d.ckpt_base.p, ckpt_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
-        CU(ctx, cudaStreamSynchronize(d.stream));
         CU(ctx, d.win_hist.reserve(n_keys * sizeof(uint32_t)));
         CU(ctx, d.win_bucket.reserve((n_keys + 1) * sizeof(uint32_t)));
         CU(ctx, d.win_items.reserve(max_items * sizeof(uint32_t)));
@@ -1494,9 +1594,14 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             {
                 const uint32_t gpa = plan.threads / k->G, units = (p.n_tasks + scan_tpg - 1) / scan_tpg;
                 const uint32_t nba = std::min<uint32_t>((uint32_t)(d.sm_count * plan.blocks_per_sm), (units + gpa - 1) / gpa);
-                scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wp);
+                WinParams wa = wp;
+                wa.s.progress = (d.copy_pending && scan_tpg == 1) ? d.progress.as<unsigned int>() : nullptr;
+                if (!wa.s.progress)
+                    if (int rc0 = ensure_resident(ctx, d)) return rc0;
+                scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wa);
             }
             CU(ctx, cudaGetLastError());
+            if (int rc0 = ensure_resident(ctx, d)) return rc0;  // everything after pass A needs the whole batch
             ClassifyParams cp{};
             cp.ends = ap.ends;
             cp.roff = p.roff;
@@ -1791,6 +1896,7 @@ int launch_ends_long(zoe_cuda_ctx *ctx, Device &d, EndsLongParams lp, uint32_t n
 }
 
 int run_ranges_long_on_device(zoe_cuda_ctx *ctx, Device &d) {
+    if (int rc0 = ensure_resident(ctx, d)) return rc0;
     const uint32_t n_prof = ctx->n_prof;
     const size_t pairs = (size_t)d.n_count * n_prof;
     if (pairs >= 0x7fffffffULL) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "too many pairs for one ranges call");
@@ -1918,6 +2024,7 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
         ctx->max_prof_len > kEndsMaxCols || getenv("ZOE_CUDA_RANGES_LONG"))
         return run_ranges_long_on_device(ctx, d);
     const bool scan_ok = ctx->max_prof_len <= kScanMaxCols && !getenv("ZOE_CUDA_RANGES_SLOW");
+    // (the forward scan below polls the streamed upload; every other first kernel needs the batch resident)
     const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
     if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
     const uint32_t n_prof = ctx->n_prof;
@@ -2013,9 +2120,12 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
         CU(ctx, cudaFuncSetAttribute(scan_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_a.smem));
         CU(ctx, cudaFuncSetAttribute(k->pin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_p.smem));
         CU(ctx, d.ckpt.reserve(std::max<uint64_t>(((chunk_seqs + 1) / 2) * ckpt_task_stride * 4, 16)));
-        CU(ctx, d.ckpt_base.reserve(n_prof * sizeof(uint64_t)));
-        CU(ctx, cudaMemcpyAsync(d.ckpt_base.p, ckpt_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
-        CU(ctx, cudaStreamSynchronize(d.stream));
+        if (!d.ckpt_base_cached(ctx->profiled_epoch, k->G, k->K, cb_log2)) {
+            CU(ctx, d.ckpt_base.reserve(n_prof * sizeof(uint64_t)));
+            CU(ctx, cudaMemcpyAsync(d.ckpt_base.p, ckpt_base.data(), n_prof * sizeof(uint64_t), cudaMemcpyHostToDevice, d.stream));
+            CU(ctx, cudaStreamSynchronize(d.stream));
+            d.ckpt_base_mark(ctx->profiled_epoch, k->G, k->K, cb_log2);
+        }
         // (win_hist / win_bucket / win_items are sized for the larger key space of the reverse pass below)
         for (uint64_t c0 = 0; c0 < d.n_count; c0 += chunk_seqs) {
             const uint32_t cn = (uint32_t)std::min<uint64_t>(chunk_seqs, d.n_count - c0);
@@ -2040,9 +2150,16 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
             wp.n_items = d.win_nitems.as<uint32_t>();
             wp.counters = ctr;
             const uint32_t gpa = plan_a.threads / k->G, units = (wp.s.n_tasks + scan_tpg - 1) / scan_tpg;
-            scan_fn<<<std::min<uint32_t>((uint32_t)(d.sm_count * plan_a.blocks_per_sm), (units + gpa - 1) / gpa),
-                      plan_a.threads, plan_a.smem, d.stream>>>(wp);
+            {
+                WinParams wa = wp;
+                wa.s.progress = (d.copy_pending && scan_tpg == 1) ? d.progress.as<unsigned int>() : nullptr;
+                if (!wa.s.progress)
+                    if (int rc0 = ensure_resident(ctx, d)) return rc0;
+                scan_fn<<<std::min<uint32_t>((uint32_t)(d.sm_count * plan_a.blocks_per_sm), (units + gpa - 1) / gpa),
+                          plan_a.threads, plan_a.smem, d.stream>>>(wa);
+            }
             CU(ctx, cudaGetLastError());
+            if (int rc0 = ensure_resident(ctx, d)) return rc0;
             ClassifyParams cp{};
             cp.ends = d.ends.as<AlignEnd>();
             cp.roff = p.roff;
@@ -2082,6 +2199,7 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
         CU(ctx, cudaMemsetAsync(d.win_hist.p, 0, n_keys * sizeof(uint32_t), d.stream));
         CU(ctx, cudaMemsetAsync(d.win_items.p, 0xff, max_items * sizeof(uint32_t), d.stream));
     } else {
+        if (int rc0 = ensure_resident(ctx, d)) return rc0;
         fn<<<std::min<uint32_t>(max_blocks, (p.n_tasks + gpb - 1) / gpb), plan.threads, plan.smem, d.stream>>>(ep);
         CU(ctx, cudaGetLastError());
     }
@@ -2512,6 +2630,11 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
         if (d.ev_fork) cudaEventDestroy(d.ev_fork);
         if (d.ev_join) cudaEventDestroy(d.ev_join);
         if (d.aux_stream) cudaStreamDestroy(d.aux_stream);
+        if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+        if (d.ev_first) cudaEventDestroy(d.ev_first);
+        if (d.ev_copied) cudaEventDestroy(d.ev_copied);
+        if (d.prog_host) cudaFreeHost(d.prog_host);
+        d.progress.release();
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
@@ -2597,6 +2720,7 @@ int zoe_cuda_set_profiled(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64
         max_len = std::max<uint32_t>(max_len, (uint32_t)len);
     }
     ctx->plans.clear();
+    ctx->profiled_epoch++;
     ctx->n_prof = n;
     ctx->max_prof_len = max_len;
     ctx->prof_bytes.assign(concat + offsets[0], concat + offsets[n]);
@@ -2767,7 +2891,7 @@ int zoe_cuda_sw_score_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
                           (copy_s > 0.1 * kernel_s || getenv("ZOE_CUDA_PIPELINE")) && !getenv("ZOE_CUDA_NO_PIPELINE");
     if (!pipeline) {
         for (Device &d : ctx->devs) {
-            rc = stage_device(ctx, d, streamed_concat, offsets);
+            rc = stage_device(ctx, d, streamed_concat, offsets, true, /*streamed=*/true);
             if (rc) return rc;
         }
         for (Device &d : ctx->devs) {
@@ -2911,7 +3035,7 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
     }
     begin_call(ctx);
     DebugTimer dbg;
-    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*streamed=*/true);
     if (rc) return rc;
     dbg.lap("align: stage");
     rc = for_each_device(ctx, [&](Device &d) { return run_align_on_device(ctx, d, cigar_cap); });
@@ -2932,7 +3056,7 @@ int zoe_cuda_sw_score_ranges_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_co
                                    uint32_t *query_start, uint32_t *query_end) {
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     begin_call(ctx);
-    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*streamed=*/true);
     if (rc) return rc;
     rc = for_each_device(ctx, [&](Device &d) { return run_ranges_on_device(ctx, d); });
     if (rc) return rc;
@@ -2979,7 +3103,7 @@ int zoe_cuda_sw_align_3pass_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_con
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     if (!cigar_off || (!cigar && cigar_cap)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null CIGAR outputs");
     begin_call(ctx);
-    int rc = stage_on_devices(ctx, streamed_concat, offsets, n);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*streamed=*/true);
     if (rc) return rc;
     rc = for_each_device(ctx, [&](Device &d) { return run_3pass_on_device(ctx, d, cigar_cap); });
     if (rc) return rc;
