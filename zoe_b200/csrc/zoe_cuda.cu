@@ -1655,14 +1655,21 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             tw.win_task_stride = win_task_stride;
             tw.cb_log2 = cb_log2;
             tw.slack = win_slack;
-            auto fill_and_walk = [&]() -> int {  // window fill + walk of the pairs in wp.items
+            // Small chunks: the pin sweep (second stream) must fit on an SM beside a window-fill CTA -- shared memory AND
+            // registers (a 512-thread fill CTA holds 61k of the 64k registers) -- so the fill runs with 384 threads and the
+            // pin with 128, one CTA each per SM.
+            const bool small_chunk = cpairs <= 400000u && plan_b.threads >= 384 && 384 % k->G == 0 && plan_p.threads >= 128 &&
+                                     128 % k->G == 0 && !getenv("ZOE_CUDA_NO_PIN_OVERLAP");
+            auto fill_and_walk = [&](bool beside_pin) -> int {  // window fill + walk of the pairs in wp.items
                 WinParams wb = wp;
                 wb.pin_mode = 0;
                 wb.s.cols_in_smem = plan_b.cols_in_smem;
-                const uint32_t gpb = plan_b.threads / k->G;
-                const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * plan_b.blocks_per_sm),
+                const int fthreads = beside_pin ? 384 : plan_b.threads;
+                const size_t fsmem = beside_pin ? score_smem_bytes(ctx, *k, fthreads, plan_b.cols_in_smem, ctx->ccodes.size()) : plan_b.smem;
+                const uint32_t gpb = fthreads / k->G;
+                const uint32_t nb = std::min<uint32_t>((uint32_t)(d.sm_count * (beside_pin ? 1 : plan_b.blocks_per_sm)),
                                                        (uint32_t)((max_items / 2 + gpb - 1) / gpb));
-                k->winfill<<<nb, plan_b.threads, plan_b.smem, d.stream>>>(wb);
+                k->winfill<<<nb, fthreads, fsmem, d.stream>>>(wb);
                 CU(ctx, cudaGetLastError());
                 sw_traceback_win_kernel<<<(uint32_t)((max_items + 127) / 128), 128, 0, d.stream>>>(tw);
                 CU(ctx, cudaGetLastError());
@@ -1682,21 +1689,11 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                 wq.items = d.win_pitems.as<uint32_t>();
                 wq.n_items = d.win_pnitems.as<uint32_t>();
                 wq.s.cols_in_smem = plan_p.cols_in_smem;
-                // small CTAs (two warps' worth of groups, ~20 KB of tables): they must fit beside the window-fill CTAs,
-                // which take most of an SM's shared memory, or the two streams would simply run one after the other
-                // (small chunks only: with a million pairs the pin sweep has enough tasks to want full-size CTAs, and
-                // then runs before / after the window fill as it always did -- measured 60.8 vs 66.0 ms on 1M reads)
-                bool small_chunk = cpairs <= 400000u;
-                int pin_threads = small_chunk ? std::min(plan_p.threads, std::max(k->G, 64)) : plan_p.threads;
-                size_t pin_smem = small_chunk ? score_smem_bytes(ctx, *k, pin_threads, plan_p.cols_in_smem, ctx->ccodes.size())
-                                              : plan_p.smem;
-                if (pin_smem > plan_p.smem) {  // (large per-group tables: the planned launch is already the small one)
-                    small_chunk = false;
-                    pin_threads = plan_p.threads;
-                    pin_smem = plan_p.smem;
-                }
+                const int pin_threads = small_chunk ? 128 : plan_p.threads;
+                const size_t pin_smem = small_chunk ? score_smem_bytes(ctx, *k, pin_threads, plan_p.cols_in_smem, ctx->ccodes.size())
+                                                    : plan_p.smem;
                 const uint32_t gpb = pin_threads / k->G;
-                const uint32_t nb = std::min<uint32_t>(small_chunk ? (uint32_t)d.sm_count * 2u : (uint32_t)(d.sm_count * plan_p.blocks_per_sm),
+                const uint32_t nb = std::min<uint32_t>(small_chunk ? (uint32_t)d.sm_count : (uint32_t)(d.sm_count * plan_p.blocks_per_sm),
                                                        (uint32_t)((max_items / 2 + gpb - 1) / gpb));
                 k->pin<<<nb, pin_threads, pin_smem, d.aux_stream>>>(wq);
                 CU(ctx, cudaGetLastError());
@@ -1706,12 +1703,12 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             // ---- classification proper, window fill, walk: the unambiguous pairs, then the pinned ones ----
             rc = bucket(0, 1, wp.items, wp.n_items);
             if (rc) return rc;
-            rc = fill_and_walk();
+            rc = fill_and_walk(small_chunk);
             if (rc) return rc;
             CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_join, 0));
             rc = bucket(0, 2, wp.items, wp.n_items);
             if (rc) return rc;
-            rc = fill_and_walk();
+            rc = fill_and_walk(false);
             if (rc) return rc;
             CU(ctx, cudaEventRecord(d.ev_k1, d.stream));
         }
