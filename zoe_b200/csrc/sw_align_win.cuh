@@ -205,7 +205,6 @@ __global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZO
             }
         }
 
-        if (!REV) wait_for_bytes(p.progress, max(off_lo + (uint64_t)len_lo, off_hi + (uint64_t)len_hi));
         build_task_table<G, K, true>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi, REV ? -1 : 1);
 
         uint32_t *ck_task = REV ? nullptr : wp.ckpt + (size_t)task * wp.ckpt_task_stride;

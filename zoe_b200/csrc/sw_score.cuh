@@ -100,22 +100,9 @@ struct ScoreParams {
     int32_t *best;             // [n_rseq * n_cseq] exact score, or -1 = needs the wide kernel
     uint32_t best_stride;      // row stride of `best` (0 = n_cseq) and first column: a launch may cover a sub-range of the
     uint32_t best_col0;        // profiled set (panels larger than the shared-memory staging area are swept group by group)
-    // End-to-end calls: the batch is uploaded in chunks by the copy engine WHILE the first kernel runs; `progress` holds the
-    // number of bytes of rseq that have arrived (a 4-byte DMA write after every chunk, in stream order, chunk boundaries on
-    // 128-byte lines so no line is ever fetched half-arrived).  nullptr = the batch is resident.
-    const unsigned int *progress;
+    uint32_t task_first;       // first task of this launch (a call may cover its tasks in two launches, the first one running
+                               // while the second part of the batch is still being uploaded); n_tasks stays the END task
 };
-
-// Spin until the first `need` bytes of the streamed batch are on the device (see ScoreParams::progress).
-__device__ __forceinline__ void wait_for_bytes(const unsigned int *progress, unsigned long long need) {
-    if (progress == nullptr) return;
-    unsigned int have;
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(progress) : "memory");
-        if ((unsigned long long)have >= need) break;
-        __nanosleep(256);
-    }
-}
 
 template <bool PACKED>
 struct Ops;
@@ -191,10 +178,18 @@ __device__ __forceinline__ TaskSmem carve_and_stage(uint8_t *smem, const ScorePa
 // Builds a task's score table: lane `lig` fills its own K rows for every column symbol.  Row r of the low / high
 // half reads rseq[base + dir * r] for r < len (dir = -1: a reversed prefix), else the padding weight.
 // tab[(s * K4 + i4) * G + lig] = the four packed weights of rows lig*K + 4*i4 .. +3 against column symbol s.
+// -DZOE_TABLE_STAGED_LOADS: the sequence bytes come in with coalesced 128-bit loads -- the group stages the 16-byte words
+// covering its two sequences in the (not yet written) table area, every lane then picks its K residues out of shared
+// memory, maps them to symbol indices (four per register) and only then writes the table over the staging area.
 template <int G, int K, bool PACKED>
 __device__ __forceinline__ void build_task_table(const TaskSmem &m, const ScoreParams &p, int lig, int64_t base_lo, int len_lo,
                                                  int64_t base_hi, int len_hi, int dir = 1) {
     constexpr int K4 = (K + 3) / 4;
+#ifndef ZOE_TABLE_STAGED_LOADS
+    // Every lane fetches its own K residues with byte loads at immediate offsets (one 128-byte line or two per sequence,
+    // L1 hits after the first touch).  The 128-bit staged variant below (-DZOE_TABLE_STAGED_LOADS) was measured slower
+    // on a B200: cfg 1 0.629 -> 0.673 ms, cfg 3 61.4 -> 63.2 ms, cfg 4 324 -> 341 ms, cfg 2 unchanged (two more warp
+    // barriers and a shared-memory round trip per task against loads that already hit L1); DESIGN.md 4.1.
     __syncwarp();
     for (int i4 = 0; i4 < K4; ++i4) {
         int sym_lo[4], sym_hi[4];
@@ -217,6 +212,63 @@ __device__ __forceinline__ void build_task_table(const TaskSmem &m, const ScoreP
         }
     }
     __syncwarp();
+#else
+    constexpr int RA = (G * K + 32 + 15) & ~15;  // staging bytes per sequence; 2 * RA <= one symbol's table slice (G*K >= 32)
+    static_assert(2 * RA <= K4 * G * 16, "the staging area must fit the table of one column symbol");
+    uint8_t *stg = reinterpret_cast<uint8_t *>(m.tab);
+    __syncwarp();
+    int sh_lo = 0, sh_hi = 0;
+    {
+        const int64_t a0 = dir > 0 ? base_lo : base_lo - (len_lo - 1);
+        const int64_t a0a = a0 & ~(int64_t)15;
+        sh_lo = (int)(a0 - a0a);
+        const int nq = len_lo > 0 ? (sh_lo + len_lo + 15) >> 4 : 0;
+        for (int q = lig; q < nq; q += G)
+            reinterpret_cast<uint4 *>(stg)[q] = __ldg(reinterpret_cast<const uint4 *>(p.rseq + a0a) + q);
+    }
+    if (PACKED) {
+        const int64_t a0 = dir > 0 ? base_hi : base_hi - (len_hi - 1);
+        const int64_t a0a = a0 & ~(int64_t)15;
+        sh_hi = (int)(a0 - a0a);
+        const int nq = len_hi > 0 ? (sh_hi + len_hi + 15) >> 4 : 0;
+        for (int q = lig; q < nq; q += G)
+            reinterpret_cast<uint4 *>(stg + RA)[q] = __ldg(reinterpret_cast<const uint4 *>(p.rseq + a0a) + q);
+    }
+    __syncwarp();
+    uint32_t symw_lo[K4], symw_hi[K4];  // four symbol indices per register, 0xff = padding row
+#pragma unroll
+    for (int i4 = 0; i4 < K4; ++i4) {
+        uint32_t wl = 0, wh = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i4 * 4 + q, r = lig * K + i;
+            uint32_t sl = 0xffu, sh = 0xffu;
+            if (i < K && r < len_lo) sl = m.s_lut[stg[sh_lo + (dir > 0 ? r : len_lo - 1 - r)]];
+            if (PACKED && i < K && r < len_hi) sh = m.s_lut[stg[RA + sh_hi + (dir > 0 ? r : len_hi - 1 - r)]];
+            wl |= sl << (8 * q);
+            wh |= sh << (8 * q);
+        }
+        symw_lo[i4] = wl;
+        symw_hi[i4] = wh;
+    }
+    __syncwarp();  // every lane has read the staging area: the table may overwrite it
+#pragma unroll
+    for (int i4 = 0; i4 < K4; ++i4) {
+        for (int s = 0; s < p.n_csym; ++s) {
+            const int8_t *wrow = m.s_wk + s * p.S;
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t sl = (symw_lo[i4] >> (8 * q)) & 0xffu, sh = (symw_hi[i4] >> (8 * q)) & 0xffu;
+                const int wl = sl != 0xffu ? (int)wrow[sl] : kPadWeight;
+                const int wh = sh != 0xffu ? (int)wrow[sh] : kPadWeight;
+                w[q] = PACKED ? ((uint32_t)(wl & 0xffff) | ((uint32_t)(wh & 0xffff) << 16)) : (uint32_t)wl;
+            }
+            m.tab[(s * K4 + i4) * G + lig] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncwarp();
+#endif
 }
 
 // One column step of one systolic stream: K rows, fully unrolled.  `tp` points at this lane's uint4 of the
@@ -282,8 +334,8 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? ZOE_SCORE2_THREA
     // Static round-robin task assignment: every group of a warp makes the same number of trips,
     // so the warp never diverges on the task loop (invalid trips run on empty sequences).
     const uint32_t total_groups = gridDim.x * groups_per_block;
-    const uint32_t trips = (p.n_tasks + total_groups - 1) / total_groups;
-    const uint32_t first = blockIdx.x * groups_per_block + group_in_block;
+    const uint32_t trips = (p.n_tasks - p.task_first + total_groups - 1) / total_groups;
+    const uint32_t first = p.task_first + blockIdx.x * groups_per_block + group_in_block;
 
     for (uint32_t trip = 0; trip < trips; ++trip) {
         const uint32_t task = first + trip * total_groups;
@@ -316,7 +368,6 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? ZOE_SCORE2_THREA
             len_hi = (int)(p.roff[id_hi + 1] - off_hi);
         }
 
-        wait_for_bytes(p.progress, max(off_lo + (uint64_t)len_lo, off_hi + (uint64_t)len_hi));
         build_task_table<G, K, PACKED>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
 
         // ---- sweep the column sequences, NS at a time ----

@@ -85,12 +85,12 @@ struct Device {
     int flb_G = 0, flb_K = 0, ckb_G = 0, ckb_K = 0, ckb_cb = -1;
     bool ckpt_base_cached(uint64_t epoch, int G, int K, int cb) const { return ckb_epoch == epoch && ckb_G == G && ckb_K == K && ckb_cb == cb; }
     void ckpt_base_mark(uint64_t epoch, int G, int K, int cb) { ckb_epoch = epoch; ckb_G = G; ckb_K = K; ckb_cb = cb; }
-    // streamed upload (end-to-end calls): chunks + a bytes-arrived word on `copy_stream`, polled by the first kernel
+    // split upload (end-to-end calls): the first 1/8 of the sequences, then the rest, on `copy_stream`; the first kernel of
+    // the call runs on the first part while the second is still arriving
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_first = nullptr, ev_copied = nullptr;
-    DevBuf progress;
-    unsigned int *prog_host = nullptr;  // pinned: the values the copy engine writes into `progress`
     bool copy_pending = false;
+    uint64_t seq_split = 0;  // sequences [0, seq_split) of the shard are in the first part (even)
     cudaStream_t aux_stream = nullptr;  // align: the pin sweep of the ambiguous pairs runs beside the main window fill
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
@@ -599,9 +599,7 @@ int prepare_batch(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offs
 }
 
 // Uploads the sequences [d.n_first, d.n_first + d.n_count) of the batch to `d` (async on d.stream).
-constexpr int kUploadChunks = 8;
-
-// The first kernel of a call that was staged with `streamed` polls d.progress; everything else needs the whole batch.
+// Everything but the first launch of a call's first kernel needs the whole batch.
 int ensure_resident(zoe_cuda_ctx *ctx, Device &d) {
     if (!d.copy_pending) return 0;
     CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_copied, 0));
@@ -609,11 +607,23 @@ int ensure_resident(zoe_cuda_ctx *ctx, Device &d) {
     return 0;
 }
 
-// streamed: upload the bytes in chunks on the copy stream, a "bytes arrived" word after each, and let d.stream go on after
-// the first chunk -- sw_score_kernel / sw_align_scan_kernel poll the word before they touch a sequence (ScoreParams::progress),
-// so the copy engine runs beside the first kernel instead of in front of it (config 3: 3.3 ms of a 70 ms call).
+// Tasks (pairs of sequences) the first launch of a split call covers: whole trips of the persistent grid, so the extra
+// launch adds no partial wave; 0 = do not split.
+uint32_t first_part_tasks(const Device &d, uint32_t n_tasks, uint32_t total_groups) {
+    if (!d.copy_pending || total_groups == 0) return 0;
+    uint32_t t = (uint32_t)(d.seq_split / 2);
+    if (t >= total_groups) t -= t % total_groups;
+    return (t == 0 || t >= n_tasks) ? 0 : t;
+}
+
+// split: upload the first 1/8 of the sequences, let d.stream go on, upload the rest behind it on the copy stream.  The first
+// kernel of the call (sw_score_kernel or pass A: persistent grids that take tasks in index order) is launched twice -- on
+// the tasks of the first part at once, on the others once everything has arrived -- so the copy engine works beside the
+// kernel instead of in front of it (config 3: 3.3 ms of a 70 ms call).  [An earlier version polled a "bytes arrived" word
+// inside the kernels: the extra control flow cost the two-stream score kernel 67 register moves per 76 cell pairs in its
+// steady loop, 292 -> 318 ms on config 2; measured and dropped.]
 int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint64_t *offsets, bool record_begin = true,
-                 bool streamed = false) {
+                 bool split = false) {
     CU(ctx, cudaSetDevice(d.id));
     if (record_begin) CU(ctx, cudaEventRecord(d.ev_begin, d.stream));
     d.copy_pending = false;
@@ -622,37 +632,7 @@ int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint
     d.rseq_bytes = b1 - b0;
     CU(ctx, d.rseq.reserve(d.rseq_bytes + 16));
     CU(ctx, d.roff.reserve((d.n_count + 1) * sizeof(uint64_t)));
-    streamed = streamed && d.rseq_bytes >= ((uint64_t)8 << 20) && d.rseq_bytes < 0xfff00000ull && !getenv("ZOE_CUDA_NO_STREAMED_UPLOAD");
-    if (streamed) {
-        if (!d.copy_stream) {
-            CU(ctx, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
-            CU(ctx, cudaEventCreateWithFlags(&d.ev_first, cudaEventDisableTiming));
-            CU(ctx, cudaEventCreateWithFlags(&d.ev_copied, cudaEventDisableTiming));
-            CU(ctx, cudaHostAlloc((void **)&d.prog_host, (kUploadChunks + 2) * sizeof(unsigned int), cudaHostAllocDefault));
-            CU(ctx, d.progress.reserve(sizeof(unsigned int)));
-        }
-        CU(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_begin, 0));
-        d.prog_host[0] = 0;
-        CU(ctx, cudaMemcpyAsync(d.progress.p, &d.prog_host[0], sizeof(unsigned int), cudaMemcpyHostToDevice, d.copy_stream));
-        uint64_t lo = 0;
-        for (int c = 0; c < kUploadChunks; ++c) {
-            // a small first chunk (1/16) so the kernel starts early; boundaries on 128-byte lines of the device buffer
-            uint64_t hi = c + 1 == kUploadChunks ? d.rseq_bytes
-                                                 : ((d.rseq_bytes / 16 + (d.rseq_bytes - d.rseq_bytes / 16) * c / (kUploadChunks - 1)) + 127) & ~127ull;
-            hi = std::min<uint64_t>(std::max(hi, lo), d.rseq_bytes);
-            if (hi > lo)
-                CU(ctx, cudaMemcpyAsync((uint8_t *)d.rseq.p + lo, concat + b0 + lo, hi - lo, cudaMemcpyHostToDevice, d.copy_stream));
-            d.prog_host[c + 1] = (unsigned int)hi;
-            CU(ctx, cudaMemcpyAsync(d.progress.p, &d.prog_host[c + 1], sizeof(unsigned int), cudaMemcpyHostToDevice, d.copy_stream));
-            if (c == 0) CU(ctx, cudaEventRecord(d.ev_first, d.copy_stream));
-            lo = hi;
-        }
-        CU(ctx, cudaEventRecord(d.ev_copied, d.copy_stream));
-        CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_first, 0));
-        d.copy_pending = true;
-    } else if (d.rseq_bytes) {
-        CU(ctx, cudaMemcpyAsync(d.rseq.p, concat + b0, d.rseq_bytes, cudaMemcpyHostToDevice, d.stream));
-    }
+    // (queued before the sequences: copies drain in issue order, and the first launch needs the offsets)
     // the shard's offsets go up as the caller holds them (one copy straight from the caller's buffer, which
     // outlives the call) and are rebased to the shard's first byte on the device
     CU(ctx, cudaMemcpyAsync(d.roff.p, offsets + d.n_first, (d.n_count + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice,
@@ -661,6 +641,29 @@ int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint
         rebase_offsets_kernel<<<(uint32_t)((d.n_count + 256) / 256), 256, 0, d.stream>>>(d.roff.as<uint64_t>(),
                                                                                          d.n_count + 1, b0);
         CU(ctx, cudaGetLastError());
+    }
+    split = split && d.rseq_bytes >= ((uint64_t)8 << 20) && d.n_count >= 4096 && !getenv("ZOE_CUDA_NO_SPLIT_UPLOAD");
+    if (split) {
+        if (!d.copy_stream) {
+            CU(ctx, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+            CU(ctx, cudaEventCreateWithFlags(&d.ev_first, cudaEventDisableTiming));
+            CU(ctx, cudaEventCreateWithFlags(&d.ev_copied, cudaEventDisableTiming));
+        }
+        // 1/8 of the shard, but at least one trip of the widest persistent grid (96 groups per SM, two sequences per
+        // group): a first launch that fills only part of the grid costs more than the copy it hides
+        d.seq_split = std::min<uint64_t>(std::max<uint64_t>(d.n_count / 8, (uint64_t)d.sm_count * 96 * 2), d.n_count / 2) & ~1ull;
+        const uint64_t bs = offsets[d.n_first + d.seq_split];
+        if (bs < b0 || bs > b1) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "offsets must be non-decreasing");
+        CU(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_begin, 0));
+        if (bs > b0) CU(ctx, cudaMemcpyAsync(d.rseq.p, concat + b0, bs - b0, cudaMemcpyHostToDevice, d.copy_stream));
+        CU(ctx, cudaEventRecord(d.ev_first, d.copy_stream));
+        if (b1 > bs)
+            CU(ctx, cudaMemcpyAsync((uint8_t *)d.rseq.p + (bs - b0), concat + bs, b1 - bs, cudaMemcpyHostToDevice, d.copy_stream));
+        CU(ctx, cudaEventRecord(d.ev_copied, d.copy_stream));
+        CU(ctx, cudaStreamWaitEvent(d.stream, d.ev_first, 0));
+        d.copy_pending = true;
+    } else if (d.rseq_bytes) {
+        CU(ctx, cudaMemcpyAsync(d.rseq.p, concat + b0, d.rseq_bytes, cudaMemcpyHostToDevice, d.stream));
     }
     size_t pairs = (size_t)d.n_count * ctx->n_prof;
     CU(ctx, d.best.reserve(pairs * sizeof(int32_t)));
@@ -672,7 +675,7 @@ int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint
     return 0;
 }
 
-int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n, bool streamed = false) {
+int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *offsets, uint64_t n, bool split = false) {
     // The upload only needs the shard boundaries, so it is queued first (after the cheap checks) and the pass over all
     // offsets -- validation, longest / shortest sequence, cells: 0.9 ms of host time for 1M reads -- runs while the copy
     // engine works.  A batch that fails validation is reported after the copies have drained.
@@ -688,7 +691,7 @@ int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *o
     int rc = 0;
     if (early)
         for (Device &d : ctx->devs) {
-            rc = stage_device(ctx, d, concat, offsets, true, streamed);
+            rc = stage_device(ctx, d, concat, offsets, true, split);
             if (rc) return rc;
         }
     rc = prepare_batch(ctx, concat, offsets, n);
@@ -701,7 +704,7 @@ int stage_on_devices(zoe_cuda_ctx *ctx, const uint8_t *concat, const uint64_t *o
     }
     if (!early)
         for (Device &d : ctx->devs) {
-            rc = stage_device(ctx, d, concat, offsets, true, streamed);
+            rc = stage_device(ctx, d, concat, offsets, true, split);
             if (rc) return rc;
         }
     ctx->staged = true;
@@ -767,12 +770,23 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
         uint32_t max_blocks = (uint32_t)(d.sm_count * plan.blocks_per_sm);
         uint32_t need_blocks = (p.n_tasks + groups_per_block - 1) / groups_per_block;
         uint32_t blocks = std::min(max_blocks, need_blocks);
-        p.progress = d.copy_pending ? d.progress.as<unsigned int>() : nullptr;  // the first launch runs beside the upload
+        // a call whose upload is still running covers the tasks of the first part now, the others once all has arrived
+        const uint32_t t_end = p.n_tasks, t_a = first_part_tasks(d, p.n_tasks, blocks * groups_per_block);
+        p.task_first = 0;
+        if (t_a) {
+            p.n_tasks = t_a;
+            fn<<<blocks, plan.threads, plan.smem, d.stream>>>(p);
+            CU(ctx, cudaGetLastError());
+            ctx->last_launches++;
+            p.task_first = t_a;
+            p.n_tasks = t_end;
+        }
+        rc = ensure_resident(ctx, d);
+        if (rc) return rc;
         fn<<<blocks, plan.threads, plan.smem, d.stream>>>(p);
         CU(ctx, cudaGetLastError());
         ctx->last_launches++;
-        rc = ensure_resident(ctx, d);
-        if (rc) return rc;
+        p.task_first = 0;
     }
     return 0;
 }
@@ -1594,14 +1608,28 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
             {
                 const uint32_t gpa = plan.threads / k->G, units = (p.n_tasks + scan_tpg - 1) / scan_tpg;
                 const uint32_t nba = std::min<uint32_t>((uint32_t)(d.sm_count * plan.blocks_per_sm), (units + gpa - 1) / gpa);
-                WinParams wa = wp;
-                wa.s.progress = (d.copy_pending && scan_tpg == 1) ? d.progress.as<unsigned int>() : nullptr;
-                if (!wa.s.progress)
+                // split upload: pass A on the sequences of the first part now, on the others once all has arrived (the
+                // second launch continues the chunk: checkpoints are indexed by chunk-relative task)
+                const uint32_t t_a = (c0 == 0 && scan_tpg == 1) ? first_part_tasks(d, p.n_tasks, nba * gpa) : 0;
+                if (t_a) {
+                    WinParams wa = wp;
+                    wa.s.n_rseq = 2 * t_a;
+                    wa.s.n_tasks = t_a;
+                    scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wa);
+                    CU(ctx, cudaGetLastError());
+                    ctx->last_launches++;
                     if (int rc0 = ensure_resident(ctx, d)) return rc0;
-                scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wa);
+                    wa.chunk_first = wp.chunk_first + 2 * t_a;
+                    wa.s.n_rseq = cn - 2 * t_a;
+                    wa.s.n_tasks = (wa.s.n_rseq + 1) / 2;
+                    wa.ckpt = wp.ckpt + (size_t)t_a * ckpt_task_stride;
+                    scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wa);
+                } else {
+                    if (int rc0 = ensure_resident(ctx, d)) return rc0;
+                    scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wp);
+                }
             }
             CU(ctx, cudaGetLastError());
-            if (int rc0 = ensure_resident(ctx, d)) return rc0;  // everything after pass A needs the whole batch
             ClassifyParams cp{};
             cp.ends = ap.ends;
             cp.roff = p.roff;
@@ -2021,7 +2049,6 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
         ctx->max_prof_len > kEndsMaxCols || getenv("ZOE_CUDA_RANGES_LONG"))
         return run_ranges_long_on_device(ctx, d);
     const bool scan_ok = ctx->max_prof_len <= kScanMaxCols && !getenv("ZOE_CUDA_RANGES_SLOW");
-    // (the forward scan below polls the streamed upload; every other first kernel needs the batch resident)
     const KernelEntry *k = pick_score_kernel(std::max<uint32_t>(ctx->staged_max_len, 1), ctx->n_csym);
     if (!k) return fail(ctx, ZOE_CUDA_E_UNSUPPORTED, "no kernel for length %u", ctx->staged_max_len);
     const uint32_t n_prof = ctx->n_prof;
@@ -2148,15 +2175,27 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
             wp.counters = ctr;
             const uint32_t gpa = plan_a.threads / k->G, units = (wp.s.n_tasks + scan_tpg - 1) / scan_tpg;
             {
-                WinParams wa = wp;
-                wa.s.progress = (d.copy_pending && scan_tpg == 1) ? d.progress.as<unsigned int>() : nullptr;
-                if (!wa.s.progress)
+                const uint32_t nba = std::min<uint32_t>((uint32_t)(d.sm_count * plan_a.blocks_per_sm), (units + gpa - 1) / gpa);
+                const uint32_t t_a = (c0 == 0 && scan_tpg == 1) ? first_part_tasks(d, wp.s.n_tasks, nba * gpa) : 0;
+                if (t_a) {  // split upload: see run_align_on_device
+                    WinParams wa = wp;
+                    wa.s.n_rseq = 2 * t_a;
+                    wa.s.n_tasks = t_a;
+                    scan_fn<<<nba, plan_a.threads, plan_a.smem, d.stream>>>(wa);
+                    CU(ctx, cudaGetLastError());
+                    ctx->last_launches++;
                     if (int rc0 = ensure_resident(ctx, d)) return rc0;
-                scan_fn<<<std::min<uint32_t>((uint32_t)(d.sm_count * plan_a.blocks_per_sm), (units + gpa - 1) / gpa),
-                          plan_a.threads, plan_a.smem, d.stream>>>(wa);
+                    wa.chunk_first = wp.chunk_first + 2 * t_a;
+                    wa.s.n_rseq = cn - 2 * t_a;
+                    wa.s.n_tasks = (wa.s.n_rseq + 1) / 2;
+                    wa.ckpt = wp.ckpt + (size_t)t_a * ckpt_task_stride;
+                    scan_fn<<<nba, plan_a.threads, plan_a.smem, d.stream>>>(wa);
+                } else {
+                    if (int rc0 = ensure_resident(ctx, d)) return rc0;
+                    scan_fn<<<nba, plan_a.threads, plan_a.smem, d.stream>>>(wp);
+                }
             }
             CU(ctx, cudaGetLastError());
-            if (int rc0 = ensure_resident(ctx, d)) return rc0;
             ClassifyParams cp{};
             cp.ends = d.ends.as<AlignEnd>();
             cp.roff = p.roff;
@@ -2630,8 +2669,6 @@ void zoe_cuda_destroy(zoe_cuda_ctx *ctx) {
         if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
         if (d.ev_first) cudaEventDestroy(d.ev_first);
         if (d.ev_copied) cudaEventDestroy(d.ev_copied);
-        if (d.prog_host) cudaFreeHost(d.prog_host);
-        d.progress.release();
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete ctx;
@@ -2888,7 +2925,7 @@ int zoe_cuda_sw_score_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
                           (copy_s > 0.1 * kernel_s || getenv("ZOE_CUDA_PIPELINE")) && !getenv("ZOE_CUDA_NO_PIPELINE");
     if (!pipeline) {
         for (Device &d : ctx->devs) {
-            rc = stage_device(ctx, d, streamed_concat, offsets, true, /*streamed=*/true);
+            rc = stage_device(ctx, d, streamed_concat, offsets, true, /*split=*/true);
             if (rc) return rc;
         }
         for (Device &d : ctx->devs) {
@@ -3032,7 +3069,7 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
     }
     begin_call(ctx);
     DebugTimer dbg;
-    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*streamed=*/true);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*split=*/true);
     if (rc) return rc;
     dbg.lap("align: stage");
     rc = for_each_device(ctx, [&](Device &d) { return run_align_on_device(ctx, d, cigar_cap); });
@@ -3053,7 +3090,7 @@ int zoe_cuda_sw_score_ranges_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_co
                                    uint32_t *query_start, uint32_t *query_end) {
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     begin_call(ctx);
-    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*streamed=*/true);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*split=*/true);
     if (rc) return rc;
     rc = for_each_device(ctx, [&](Device &d) { return run_ranges_on_device(ctx, d); });
     if (rc) return rc;
@@ -3100,7 +3137,7 @@ int zoe_cuda_sw_align_3pass_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_con
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     if (!cigar_off || (!cigar && cigar_cap)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null CIGAR outputs");
     begin_call(ctx);
-    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*streamed=*/true);
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*split=*/true);
     if (rc) return rc;
     rc = for_each_device(ctx, [&](Device &d) { return run_3pass_on_device(ctx, d, cigar_cap); });
     if (rc) return rc;
