@@ -496,6 +496,41 @@ int plan_launch(zoe_cuda_ctx *ctx, const KernelEntry &k, Fn fn, LaunchPlan *plan
     return 0;
 }
 
+// The shape of a persistent launch over `units` tasks.  Warps are bound to one of the SM's four schedulers, so the time
+// of a grid trip goes with ceil(warps per SM / 4), not with the warps: 18 warps (576 threads) run exactly as long as 20
+// (measured: config 3, 62 500 tasks, 9.43 ms either way), and only a multiple of four warps fewer helps.  A small batch
+// whose last trip is mostly empty (62 500 tasks on 148 x 80 groups: 5.3, hence 6 trips of 5 warps per scheduler = 30) may
+// be cheaper with fewer, narrower trips (7 trips of 4 = 28).  More warps hide more latency than this model knows (1M
+// reads: 640 threads beat 512 although 43 x 5 > 53 x 4), so the shape changes only for a predicted gain of 5 % or more.
+// [Also measured: spreading config 1's 5 000 tasks over 250 CTAs of 160 threads instead of 114 of 352 -- same warps per
+// scheduler, more CTAs staging the columns: 0.672 against 0.632 ms.  Not done.]
+struct GridShape {
+    uint32_t blocks, threads;
+};
+GridShape balance_grid(const Device &d, const LaunchPlan &plan, int G, uint32_t units) {
+    const uint32_t gpb = (uint32_t)plan.threads / (uint32_t)G, bps = (uint32_t)std::max(plan.blocks_per_sm, 1);
+    GridShape g{std::min<uint32_t>((uint32_t)d.sm_count * bps, (units + gpb - 1) / gpb), (uint32_t)plan.threads};
+    static const bool off = getenv("ZOE_CUDA_NO_BALANCE") != nullptr, dbg = getenv("ZOE_CUDA_DEBUG_GRID") != nullptr;
+    if (!off && units != 0 && bps == 1 && (128 % G) == 0) {
+        const uint32_t sms = (uint32_t)d.sm_count;
+        auto cost = [&](uint32_t threads) {
+            const uint32_t per_trip = sms * (threads / (uint32_t)G);
+            return (uint64_t)((units + per_trip - 1) / per_trip) * ((threads / 32 + 3) / 4);
+        };
+        uint64_t best = cost((uint32_t)plan.threads) * 100;
+        for (uint32_t t = ((uint32_t)plan.threads - 1) / 128 * 128; t >= 512; t -= 128)  // >= 16 warps: latency hiding
+            if (cost(t) * 105 <= best) {
+                best = cost(t) * 105;
+                g.threads = t;
+            }
+        const uint32_t gpb2 = g.threads / (uint32_t)G;
+        g.blocks = std::min<uint32_t>(sms, (units + gpb2 - 1) / gpb2);
+    }
+    if (dbg) fprintf(stderr, "[zoe_cuda] grid: %u units, plan %d x %d per SM -> %u CTAs of %u threads\n", units, plan.threads,
+                     plan.blocks_per_sm, g.blocks, g.threads);
+    return g;
+}
+
 // Pass A of the windowed pipelines with two tasks per group (two dependency chains per thread).  MEASURED AND REJECTED on
 // cfg 3 (1M reads): 67.7 ms against 64.8 ms with the one-task kernel -- two score tables per group leave 11 warps per SM
 // instead of 16 (22 chains against 16), and the 168-register build spills.  Kept behind ZOE_CUDA_SCAN2 as a record.
@@ -783,7 +818,8 @@ int launch_score(zoe_cuda_ctx *ctx, Device &d, const KernelEntry &k, bool packed
         }
         rc = ensure_resident(ctx, d);
         if (rc) return rc;
-        fn<<<blocks, plan.threads, plan.smem, d.stream>>>(p);
+        const GridShape gs = balance_grid(d, plan, k.G, p.n_tasks - p.task_first);
+        fn<<<gs.blocks, gs.threads, plan.smem, d.stream>>>(p);
         CU(ctx, cudaGetLastError());
         ctx->last_launches++;
         p.task_first = 0;
@@ -1623,10 +1659,12 @@ int run_align_on_device(zoe_cuda_ctx *ctx, Device &d, uint64_t cigar_cap_words) 
                     wa.s.n_rseq = cn - 2 * t_a;
                     wa.s.n_tasks = (wa.s.n_rseq + 1) / 2;
                     wa.ckpt = wp.ckpt + (size_t)t_a * ckpt_task_stride;
-                    scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wa);
+                    const GridShape gs = balance_grid(d, plan, k->G, wa.s.n_tasks);
+                    scan_fn<<<gs.blocks, gs.threads, plan.smem, d.stream>>>(wa);
                 } else {
                     if (int rc0 = ensure_resident(ctx, d)) return rc0;
-                    scan_fn<<<nba, plan.threads, plan.smem, d.stream>>>(wp);
+                    const GridShape gs = scan_tpg == 1 ? balance_grid(d, plan, k->G, units) : GridShape{nba, (uint32_t)plan.threads};
+                    scan_fn<<<gs.blocks, gs.threads, plan.smem, d.stream>>>(wp);
                 }
             }
             CU(ctx, cudaGetLastError());
@@ -2189,10 +2227,12 @@ int run_ranges_on_device(zoe_cuda_ctx *ctx, Device &d) {
                     wa.s.n_rseq = cn - 2 * t_a;
                     wa.s.n_tasks = (wa.s.n_rseq + 1) / 2;
                     wa.ckpt = wp.ckpt + (size_t)t_a * ckpt_task_stride;
-                    scan_fn<<<nba, plan_a.threads, plan_a.smem, d.stream>>>(wa);
+                    const GridShape gs = balance_grid(d, plan_a, k->G, wa.s.n_tasks);
+                    scan_fn<<<gs.blocks, gs.threads, plan_a.smem, d.stream>>>(wa);
                 } else {
                     if (int rc0 = ensure_resident(ctx, d)) return rc0;
-                    scan_fn<<<nba, plan_a.threads, plan_a.smem, d.stream>>>(wp);
+                    const GridShape gs = scan_tpg == 1 ? balance_grid(d, plan_a, k->G, units) : GridShape{nba, (uint32_t)plan_a.threads};
+                    scan_fn<<<gs.blocks, gs.threads, plan_a.smem, d.stream>>>(wp);
                 }
             }
             CU(ctx, cudaGetLastError());
