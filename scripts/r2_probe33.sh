@@ -1,0 +1,21 @@
+#!/bin/bash
+O=gpurun_out/r2p33; mkdir -p $O
+timeout 1200 python -m pytest tests -x -q -m gpu > $O/pytest_all.log 2>&1; tail -2 $O/pytest_all.log
+timeout 300 python bench.py --config 2 --steps 4 --warmup 3 --legs none --no-cpu-baseline > $O/cfg2.json 2> $O/cfg2.err
+timeout 300 python bench.py --config 3 --steps 8 --warmup 3 > $O/cfg3.json 2> $O/cfg3.err
+timeout 300 python bench.py --config 3 --mode ranges --steps 6 --warmup 3 --no-cpu-baseline > $O/cfg3r.json 2> $O/cfg3r.err
+timeout 300 python bench.py --config 1 --steps 30 --warmup 5 --no-cpu-baseline > $O/cfg1.json 2> $O/cfg1.err
+timeout 300 python bench.py --config 3 --n 125000 --steps 20 --warmup 5 --no-cpu-baseline > $O/cfg3_125k.json 2> $O/cfg3_125k.err
+timeout 200 python scripts/soak.py 100 909 > $O/soak_seed909.txt 2>&1; tail -1 $O/soak_seed909.txt
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2p33/*.json')):
+    try:
+        j=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split('/')[-1], round(j['value'],1), round(j['ms_per_step'],4), 'e2e', round(j['e2e']['value'],1), j['e2e'].get('checksum_matches_n1'), 'peak', round(j['roofline']['peak'],1), (j.get('parity') or {}).get('mismatches'))
+    except Exception as e: print(f, 'ERR', e)
+PY
+timeout 300 python bench.py --config 3 --n 250000 --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_plain.json 2> $O/ncu_plain.err && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sw_align_winfill_kernel -s 3 -c 3 -o $O/winfill_cfg3 -f \
+   python bench.py --config 3 --n 250000 --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_winfill.log 2>&1; echo "ncu rc=$?"
+ls -la $O/*.ncu-rep

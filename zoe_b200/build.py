@@ -13,8 +13,13 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
     "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-cudart", "shared",
-    "-split-compile", str(min(os.cpu_count() or 1, 16)),  # one translation unit, many kernels: optimise them in parallel
 ]
+# Development only: ZOE_CUDA_SPLIT_COMPILE=N optimises the kernels of the one translation unit in parallel (build 165 s ->
+# 75 s) -- NOT for a build that is measured: with -split-compile ptxas emitted 17 % more instructions over the 236
+# kernels (outside the hot loops) and every configuration ran 1-5 % slower (cfg 2 295.5 vs 292.1 ms, cfg 4 341 vs 324 ms,
+# same box, same sources); which kernels are hit depends on how the functions fall into the partitions.
+if os.environ.get("ZOE_CUDA_SPLIT_COMPILE"):
+    FLAGS += ["-split-compile", os.environ["ZOE_CUDA_SPLIT_COMPILE"]]
 
 
 def sources():

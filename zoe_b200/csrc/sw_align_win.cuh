@@ -215,6 +215,14 @@ __global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZO
             // REV: the groups of a warp sweep different numbers of columns (sorted by end column, so nearly equal)
             const int L = REV ? min(rev_cend + 1, rev_cols) : (int)(p.coff[cj + 1] - c0);
             const uint8_t *cs = cc + c0 + (REV ? max(rev_cend, 0) : 0);  // column j reads cs[j] (REV: cs[-j])
+            // the lane's column of step s is s - lig: fold the lane into the pointer once per sweep (the compiler would
+            // otherwise re-derive lig from %tid.x inside the steady loop, in front of the column-code load)
+            const uint8_t *cs_lane = REV ? cs + lig : cs - lig;
+            uint32_t cs_idx = CSM ? (uint32_t)(cs_lane - smem) : 0u;  // staged columns: an index into the shared array (LDS)
+            if (CSM)
+                asm volatile("" : "+r"(cs_idx));
+            else
+                asm volatile("" : "+l"(cs_lane));
             uint32_t *ck = REV ? nullptr : ck_task + wp.ckpt_base[cj] + lig;
 
             uint32_t H[2][K], F[K];
@@ -236,11 +244,13 @@ __global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZO
             // STEADY (the two-step steady loop only): with an odd K the column's last row is not folded into the column
             // maximum by an extra VIMNMX; it stays pending in `hp_pend` and pairs up with row 0 of the next (odd) step,
             // so two steps fold their 2K values with exactly K VIMNMX3.
-            auto column = [&](auto parity, auto steady, const int j, const uint32_t h_in, const uint32_t e_in) {
+            // `st` is the STEP (the lane is folded into cs_lane / cs_idx)
+            auto column = [&](auto parity, auto steady, const int st, const uint32_t h_in, const uint32_t e_in) {
                 constexpr int PO = decltype(parity)::value, PN = 1 - PO;
                 constexpr bool STEADY = decltype(steady)::value;
                 constexpr int PH = (STEADY && (K & 1)) ? PO : 0;  // pairing phase of this column
-                const uint4 *tp = reinterpret_cast<const uint4 *>(smem + tab_lane_off + (uint32_t)cs[REV ? -j : j] * (uint32_t)(K4 * G * 16));
+                const uint32_t code = CSM ? smem[cs_idx + (uint32_t)(REV ? -st : st)] : cs_lane[REV ? -st : st];
+                const uint4 *tp = reinterpret_cast<const uint4 *>(smem + tab_lane_off + code * (uint32_t)(K4 * G * 16));
                 uint32_t diag = h_up_prev, E = e_in, hp = hp_pend;
 #pragma unroll
                 for (int i4 = 0; i4 < K4; ++i4) {
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZO
                 const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
                 const int j = s - lig;
                 if (j >= 0 && j < L) {
-                    column(parity, GenericT{}, j, h_in, e_in);
+                    column(parity, GenericT{}, s, h_in, e_in);
                     bookkeeping((uint32_t)s & ~1u);
                 }
                 h_up_prev = h_in;
@@ -318,21 +328,26 @@ __global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZO
                 else
                     generic_step(I0{}, s);
             }
-            for (; s + 1 < L_steady; s += 2) {  // steps s and s+1: every lane has a column
+            while (s + 1 < L_steady) {  // steps s and s+1: every lane has a column
                 if (!REV && (((uint32_t)s) & cb_mask) == 0 && valid) checkpoint(s);
-                {   // lane 0 receives zeros from "above": a multiply on the FMA pipe, not a SEL on the ALU pipe
-                    const uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G) * nz_lane;
-                    const uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G) * nz_lane;
-                    column(I0{}, SteadyT{}, s - lig, h_in, e_in);
-                    h_up_prev = h_in;
+                // the inner loop runs to the next checkpoint boundary without a branch in its body (CB >= G >= 4, even)
+                const int s_end = REV ? L_steady : min(L_steady, (int)(((uint32_t)s | cb_mask) + 1u));
+                for (; s + 1 < s_end; s += 2) {
+                    {   // lane 0 receives zeros from "above": a multiply on the FMA pipe, not a SEL on the ALU pipe
+                        const uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G) * nz_lane;
+                        const uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G) * nz_lane;
+                        column(I0{}, SteadyT{}, s, h_in, e_in);
+                        h_up_prev = h_in;
+                    }
+                    {
+                        const uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G) * nz_lane;
+                        const uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G) * nz_lane;
+                        column(I1{}, SteadyT{}, s + 1, h_in, e_in);
+                        h_up_prev = h_in;
+                    }
+                    bookkeeping((uint32_t)s);
                 }
-                {
-                    const uint32_t h_in = __shfl_up_sync(FULL, h_last, 1, G) * nz_lane;
-                    const uint32_t e_in = __shfl_up_sync(FULL, e_out, 1, G) * nz_lane;
-                    column(I1{}, SteadyT{}, s + 1 - lig, h_in, e_in);
-                    h_up_prev = h_in;
-                }
-                bookkeeping((uint32_t)s);
+                if (s_end >= L_steady) break;
             }
             for (; s < nsteps; ++s) {
                 if (!REV && (((uint32_t)s) & cb_mask) == 0 && s >= G && s < L && valid) checkpoint(s);
@@ -375,7 +390,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZO
                     const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
                     const int j = st - lig;
                     if (j >= 0 && j < L) {
-                        column(parity, GenericT{}, j, h_in, e_in);
+                        column(parity, GenericT{}, st, h_in, e_in);
                         if (lig == wl_lo && st >= fs_lo && st <= se_lo) {
                             int irow = K;
 #pragma unroll

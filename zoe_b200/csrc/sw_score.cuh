@@ -178,18 +178,19 @@ __device__ __forceinline__ TaskSmem carve_and_stage(uint8_t *smem, const ScorePa
 // Builds a task's score table: lane `lig` fills its own K rows for every column symbol.  Row r of the low / high
 // half reads rseq[base + dir * r] for r < len (dir = -1: a reversed prefix), else the padding weight.
 // tab[(s * K4 + i4) * G + lig] = the four packed weights of rows lig*K + 4*i4 .. +3 against column symbol s.
-// -DZOE_TABLE_STAGED_LOADS: the sequence bytes come in with coalesced 128-bit loads -- the group stages the 16-byte words
-// covering its two sequences in the (not yet written) table area, every lane then picks its K residues out of shared
-// memory, maps them to symbol indices (four per register) and only then writes the table over the staging area.
-template <int G, int K, bool PACKED>
+// STAGED (the score kernel): the sequence bytes come in with coalesced 128-bit loads (north_star (2)) -- the group stages
+// the 16-byte words covering its two sequences in the (not yet written) table area, every lane then picks its K residues
+// out of shared memory, maps them to symbol indices (four per register) and only then writes the table over the staging
+// area.  !STAGED (pass A, pass B, the ends kernels): every lane fetches its own residues with byte loads at immediate
+// offsets.  Measured on one B200, same box, builds without -split-compile, byte loads / 128-bit staged:
+//   sw_score_kernel      cfg 1 0.656 / 0.604 ms per call, cfg 2 292.1 / 288.2 ms
+//   sw_align_scan_kernel cfg 3 align 59.6 / 60.7 ms, ranges 56.9 / 58.6 ms (one table per 1704-column sweep: the two extra
+//                        warp barriers and the larger code cost more than the loads they replace)
+template <int G, int K, bool PACKED, bool STAGED = false>
 __device__ __forceinline__ void build_task_table(const TaskSmem &m, const ScoreParams &p, int lig, int64_t base_lo, int len_lo,
                                                  int64_t base_hi, int len_hi, int dir = 1) {
     constexpr int K4 = (K + 3) / 4;
-#ifndef ZOE_TABLE_STAGED_LOADS
-    // Every lane fetches its own K residues with byte loads at immediate offsets (one 128-byte line or two per sequence,
-    // L1 hits after the first touch).  The 128-bit staged variant below (-DZOE_TABLE_STAGED_LOADS) was measured slower
-    // on a B200: cfg 1 0.629 -> 0.673 ms, cfg 3 61.4 -> 63.2 ms, cfg 4 324 -> 341 ms, cfg 2 unchanged (two more warp
-    // barriers and a shared-memory round trip per task against loads that already hit L1); DESIGN.md 4.1.
+  if constexpr (!STAGED) {
     __syncwarp();
     for (int i4 = 0; i4 < K4; ++i4) {
         int sym_lo[4], sym_hi[4];
@@ -212,7 +213,7 @@ __device__ __forceinline__ void build_task_table(const TaskSmem &m, const ScoreP
         }
     }
     __syncwarp();
-#else
+  } else {
     constexpr int RA = (G * K + 32 + 15) & ~15;  // staging bytes per sequence; 2 * RA <= one symbol's table slice (G*K >= 32)
     static_assert(2 * RA <= K4 * G * 16, "the staging area must fit the table of one column symbol");
     uint8_t *stg = reinterpret_cast<uint8_t *>(m.tab);
@@ -268,7 +269,7 @@ __device__ __forceinline__ void build_task_table(const TaskSmem &m, const ScoreP
         }
     }
     __syncwarp();
-#endif
+  }
 }
 
 // One column step of one systolic stream: K rows, fully unrolled.  `tp` points at this lane's uint4 of the
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__((NS == 2 && (PP || K > 20)) ? ZOE_SCORE2_THREA
             len_hi = (int)(p.roff[id_hi + 1] - off_hi);
         }
 
-        build_task_table<G, K, PACKED>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
+        build_task_table<G, K, PACKED, true>(sm, p, lig, (int64_t)off_lo, len_lo, (int64_t)off_hi, len_hi);
 
         // ---- sweep the column sequences, NS at a time ----
         for (uint32_t ci = 0; ci < p.n_cseq; ci += NS) {
