@@ -389,9 +389,13 @@ __global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZO
                     const uint32_t h_sh = __shfl_up_sync(FULL, h_last, 1, G), h_in = lane0 ? 0u : h_sh;
                     const uint32_t e_sh = __shfl_up_sync(FULL, e_out, 1, G), e_in = lane0 ? 0u : e_sh;
                     const int j = st - lig;
-                    if (j >= 0 && j < L) {
-                        column(parity, GenericT{}, st, h_in, e_in);
-                        if (lig == wl_lo && st >= fs_lo && st <= se_lo) {
+                    const bool in_cols = j >= 0 && j < L;
+                    if (in_cols) column(parity, GenericT{}, st, h_in, e_in);
+                    // the search for the best cell sits behind a warp-uniform branch (see sw_align_winfill_kernel)
+                    const bool hit_lo = in_cols && lig == wl_lo && st >= fs_lo && st <= se_lo;
+                    const bool hit_hi = in_cols && lig == wl_hi && st >= fs_hi && st <= se_hi;
+                    if (__any_sync(FULL, hit_lo || hit_hi)) {
+                        if (hit_lo) {
                             int irow = K;
 #pragma unroll
                             for (int i = K - 1; i >= 0; --i)
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(K > 24 ? 256 : (K > 16 && K <= 20 && !REV ? ZO
                                 bj_lo = j;
                             }
                         }
-                        if (lig == wl_hi && st >= fs_hi && st <= se_hi) {
+                        if (hit_hi) {
                             int irow = K;
 #pragma unroll
                             for (int i = K - 1; i >= 0; --i)
@@ -1107,33 +1111,43 @@ __global__ void __launch_bounds__(512) sw_align_winfill_kernel(const WinParams w
                 }
                 h_last = Hrow[K - 1];
                 e_out = E;
-                // ---- pin the best cell down: smallest row, then smallest column (striped.rs:555-583) ----
-                const uint32_t s_abs = ws + (uint32_t)step;
-                if ((uint32_t)lig == ls_lo && s_abs >= fs_lo && s_abs <= se_lo) {
-                    int irow = K;
-#pragma unroll
-                    for (int i = K - 1; i >= 0; --i)
-                        if ((int)(int16_t)(Hrow[i] & 0xffffu) == best_lo) irow = i;
-                    if (irow < bi_lo) {
-                        bi_lo = irow;
-                        bj_lo = j;
-                    }
-                }
-                if ((uint32_t)lig == ls_hi && s_abs >= fs_hi && s_abs <= se_hi) {
-                    int irow = K;
-#pragma unroll
-                    for (int i = K - 1; i >= 0; --i)
-                        if ((int)(int16_t)(Hrow[i] >> 16) == best_hi) irow = i;
-                    if (irow < bi_hi) {
-                        bi_hi = irow;
-                        bj_hi = j;
-                    }
-                }
                 if (FLAGS && valid) {
 #pragma unroll
                     for (int w = 0; w < NW; w += 4)
                         *reinterpret_cast<uint4 *>(fl + (size_t)jw * (G * NW) + w) =
                             make_uint4(words[w], words[w + 1], words[w + 2], words[w + 3]);
+                }
+            }
+            // ---- pin the best cell down: smallest row, then smallest column (striped.rs:555-583).  One lane of a group
+            //      looks, in the two steps of its column pair (pin mode: between the first and last occurrence), so the
+            //      search sits behind a warp-uniform branch: as straight-line predicated code it was 114 of the ~290
+            //      ALU instructions of EVERY step (ncu: 15 ALU instructions per cell pair instead of 9.5) ----
+            {
+                const uint32_t s_abs = ws + (uint32_t)step;
+                const bool in_win = j >= 0 && j <= we;
+                const bool hit_lo = in_win && (uint32_t)lig == ls_lo && s_abs >= fs_lo && s_abs <= se_lo;
+                const bool hit_hi = in_win && (uint32_t)lig == ls_hi && s_abs >= fs_hi && s_abs <= se_hi;
+                if (__any_sync(FULL, hit_lo || hit_hi)) {
+                    if (hit_lo) {
+                        int irow = K;
+#pragma unroll
+                        for (int i = K - 1; i >= 0; --i)
+                            if ((int)(int16_t)(Hrow[i] & 0xffffu) == best_lo) irow = i;
+                        if (irow < bi_lo) {
+                            bi_lo = irow;
+                            bj_lo = j;
+                        }
+                    }
+                    if (hit_hi) {
+                        int irow = K;
+#pragma unroll
+                        for (int i = K - 1; i >= 0; --i)
+                            if ((int)(int16_t)(Hrow[i] >> 16) == best_hi) irow = i;
+                        if (irow < bi_hi) {
+                            bi_hi = irow;
+                            bj_hi = j;
+                        }
+                    }
                 }
             }
             h_up_prev = h_in;

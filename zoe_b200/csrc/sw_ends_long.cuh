@@ -251,12 +251,20 @@ __global__ void __launch_bounds__(ZOE_ENDS_LONG_THREADS) sw_ends_long_kernel(con
                 using P1 = std::integral_constant<int, 1>;
                 // PIN: the winning lane of sequence h looks for the best value among its rows (smallest row, then
                 // smallest column: steps ascend, a later step only wins with a strictly smaller row)
-                auto pin_search = [&](auto parity, const int step, const int j) {
+                // (behind a warp-uniform branch: as predicated straight-line code the search ran in every step)
+                auto pin_search = [&](auto parity, const int step, const int j, const bool in_cols) {
                     constexpr int PN = 1 - decltype(parity)::value;
+                    bool hit[NH], any = false;
 #pragma unroll
                     for (int h = 0; h < NH; ++h) {
-                        if (g_best[h] > 0 && g_chunk[h] == ch && lane == g_lane[h] && (uint32_t)step >= 2u * g_first[h] &&
-                            (uint32_t)step <= 2u * g_last[h] + 1u) {
+                        hit[h] = in_cols && g_best[h] > 0 && g_chunk[h] == ch && lane == g_lane[h] &&
+                                 (uint32_t)step >= 2u * g_first[h] && (uint32_t)step <= 2u * g_last[h] + 1u;
+                        any = any || hit[h];
+                    }
+                    if (!__any_sync(FULL, any)) return;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) {
+                        if (hit[h]) {
                             int irow = K;
 #pragma unroll
                             for (int i = K - 1; i >= 0; --i)
@@ -272,13 +280,12 @@ __global__ void __launch_bounds__(ZOE_ENDS_LONG_THREADS) sw_ends_long_kernel(con
                     uint32_t h_in, e_in;
                     inputs(step, h_in, e_in);
                     const int j = step - lane;
-                    if (j >= 0 && j < L) {
+                    const bool in_cols = j >= 0 && j < L;
+                    if (in_cols) {
                         column(parity, std::false_type{}, j, h_in, e_in, (uint32_t)cs[REV ? -j : j]);
-                        if (PIN)
-                            pin_search(parity, step, j);
-                        else
-                            bookkeeping((uint32_t)step & ~1u);
+                        if (!PIN) bookkeeping((uint32_t)step & ~1u);
                     }
+                    if (PIN) pin_search(parity, step, j, in_cols);
                     h_up_prev = h_in;
                 };
                 auto steady_step = [&](auto parity, auto fullk, const int step) {
