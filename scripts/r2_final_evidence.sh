@@ -8,6 +8,9 @@ timeout 1200 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; tail -2 
 timeout 300 python bench.py --steps 2 --warmup 1 --legs none --no-cpu-baseline > $O/headline_plain.json 2> $O/headline_plain.err && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_headline.csv \
    python bench.py --steps 2 --warmup 1 --legs none --no-cpu-baseline > $O/ncu_headline.log 2>&1; echo "ncu rc=$?"
+timeout 300 python bench.py --config 3 --steps 2 --warmup 1 --no-cpu-baseline > $O/cfg3_plain.json 2> $O/cfg3_plain.err && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_cfg3.csv \
+   python bench.py --config 3 --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_cfg3.log 2>&1; echo "ncu cfg3 rc=$?"
 timeout 300 python scripts/soak.py 150 707 > $O/soak_seed707.txt 2>&1; tail -1 $O/soak_seed707.txt
 timeout 300 python scripts/soak_long.py 8 > $O/soak_long_seed8.txt 2>&1; tail -1 $O/soak_long_seed8.txt
 python - <<'PY'

@@ -3021,9 +3021,23 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
                             uint64_t cigar_cap, uint8_t *hazard) {
     if (!ctx) return ZOE_CUDA_E_BAD_ARG;
     if (!cigar_off || (!cigar && cigar_cap)) return fail(ctx, ZOE_CUDA_E_BAD_ARG, "null CIGAR outputs");
+    begin_call(ctx);
+    DebugTimer dbg;
+    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*split=*/true);
+    if (rc) return rc;
+    dbg.lap("align: stage");
     // A batch that mixes long (> 1024 residues) and short sequences is split: the short ones take the fast pipelines,
     // the long ones the long-row path (run_align_on_device, long_mode); results are merged in the caller's order.
-    if (n > 0 && offsets && streamed_concat && ctx->have_profiled) {
+    // Detected from the lengths the staging pass collects anyway (a separate pass that lists the indices of 1M reads
+    // cost 3-4 ms of host time in front of every call); the upload already queued for the whole batch is drained and dropped.
+    if (n > 0 && ctx->staged_max_len > (uint32_t)kMaxRowsSinglePass && ctx->staged_min_len <= (uint32_t)kMaxRowsSinglePass) {
+        for (Device &d : ctx->devs) {
+            cudaSetDevice(d.id);
+            if (d.copy_stream) cudaStreamSynchronize(d.copy_stream);
+            cudaStreamSynchronize(d.stream);
+            d.copy_pending = false;
+        }
+        ctx->staged = false;
         std::vector<uint64_t> idx[2];  // [0] short, [1] long
         for (uint64_t i = 0; i < n; ++i) idx[offsets[i + 1] - offsets[i] > (uint64_t)kMaxRowsSinglePass ? 1 : 0].push_back(i);
         if (!idx[0].empty() && !idx[1].empty()) {
@@ -3107,11 +3121,6 @@ int zoe_cuda_sw_align_batch(zoe_cuda_ctx *ctx, const uint8_t *streamed_concat, c
             return 0;
         }
     }
-    begin_call(ctx);
-    DebugTimer dbg;
-    int rc = stage_on_devices(ctx, streamed_concat, offsets, n, /*split=*/true);
-    if (rc) return rc;
-    dbg.lap("align: stage");
     rc = for_each_device(ctx, [&](Device &d) { return run_align_on_device(ctx, d, cigar_cap); });
     if (rc) return rc;
     dbg.lap("align: run_align_on_device");
