@@ -133,7 +133,11 @@ struct KernelEntry {
     void (*scan2_g)(const WinParams);    // ... codes from global memory
 };
 
-// the two-task pass A exists for K <= 20 (two H / F register sets per thread)
+// the two-task pass A exists for K <= 20 (two H / F register sets per thread); a rejected experiment (see pick_scan2):
+// compiled only with -DZOE_CUDA_WITH_SCAN2 (28 large instantiations, a fifth of the build time)
+#ifndef ZOE_CUDA_WITH_SCAN2
+#define ZOE_CUDA_WITH_SCAN2 0
+#endif
 template <int G, int K, bool ON>
 struct Scan2 {
     static constexpr void (*smem())(const WinParams) { return sw_align_scan2_kernel<G, K, true>; }
@@ -151,7 +155,8 @@ struct Scan2<G, K, false> {
             sw_score_kernel<G, K, true, 2>, sw_align_scan_kernel<G, K>, sw_align_winfill_kernel<G, K>,     \
             sw_ends_kernel<G, K, true>, sw_ends_kernel<G, K, false>, sw_align_scan_kernel<G, K, false>,     \
             sw_align_winfill_kernel<G, K, false>, sw_align_scan_kernel<G, K, true, true>,                   \
-            Scan2<G, K, (K <= 20)>::smem(), Scan2<G, K, (K <= 20)>::gmem()                                  \
+            Scan2<G, K, (ZOE_CUDA_WITH_SCAN2 != 0) && (K <= 20)>::smem(),                                  \
+            Scan2<G, K, (ZOE_CUDA_WITH_SCAN2 != 0) && (K <= 20)>::gmem()                                   \
     }
 
 // Row capacity G*K of each instantiation; the host picks the tightest fit for the longest
