@@ -76,3 +76,32 @@ def test_split_upload_matches_single_upload_and_oracle():
                                                          wa.query_range[1]), (i, j)
     finally:
         prof.close()
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_n_gpus() < 2")
+def test_split_upload_two_devices_in_one_process():
+    """Each device's shard is large enough to be split: the per-device copy streams, events and second launches must
+    not depend on one another (zoe_cuda_create(n_devices = 2), one host thread per device)."""
+    targets, seqs, buf, offs = _batch(n=170_000, seed=12)
+    res = []
+    for nd in (1, 2):
+        prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], W, -10, -1, profiled_is_query=False, n_devices=nd)
+        try:
+            res.append((prof.sw_score_arrays(buf, offs), prof.align_arrays(buf, offs), prof.ranges_arrays(buf, offs)))
+        finally:
+            prof.close()
+    (s1, a1, r1), (s2, a2, r2) = res
+    for x, y in zip(s1, s2):
+        assert np.array_equal(x, y)
+    nw = int(a1["cigar_off"][-1])
+    assert nw == int(a2["cigar_off"][-1]) and np.array_equal(a1["cigar"][:nw], a2["cigar"][:nw])
+    for k in a1:
+        if k != "cigar":
+            assert np.array_equal(a1[k], a2[k]), k
+    for k in r1:
+        assert np.array_equal(r1[k], r2[k]), k
