@@ -1,7 +1,8 @@
 """GPU: the split upload of the end-to-end calls (first part of the batch, first launch of the call's first kernel on it
 while the rest arrives, second launch on the remaining tasks; zoe_cuda.cu stage_device / first_part_tasks) must give the
-results of the single upload, entry point by entry point, and the oracle's on a sample.  The batch is large enough to be
-split (>= 8 MB and >= 4096 sequences) and ragged, so the split point falls inside the task pairing."""
+results of the single upload, entry point by entry point, and the oracle's on a sample.  The library splits shards of
+64 MB and more; the tests lower that to 4 MB (ZOE_CUDA_SPLIT_UPLOAD_MIN_MB) so a 10-MB ragged batch is split, with the
+split point inside the task pairing."""
 import os
 
 import numpy as np
@@ -12,6 +13,17 @@ from zoe_b200 import CudaProfiles, WeightMatrix, synth
 
 pytestmark = pytest.mark.gpu
 W = WeightMatrix.new_dna_matrix(2, -5, b"N")
+
+
+@pytest.fixture(autouse=True)
+def _small_split_threshold():
+    old = os.environ.get("ZOE_CUDA_SPLIT_UPLOAD_MIN_MB")
+    os.environ["ZOE_CUDA_SPLIT_UPLOAD_MIN_MB"] = "4"
+    yield
+    if old is None:
+        os.environ.pop("ZOE_CUDA_SPLIT_UPLOAD_MIN_MB", None)
+    else:
+        os.environ["ZOE_CUDA_SPLIT_UPLOAD_MIN_MB"] = old
 
 
 def _batch(n=80_000, seed=11):
@@ -39,7 +51,7 @@ def _with_env(flag, fn):
 
 def test_split_upload_matches_single_upload_and_oracle():
     targets, seqs, buf, offs = _batch()
-    assert buf.nbytes >= (8 << 20) and len(seqs) >= 4096
+    assert buf.nbytes >= (4 << 20) and len(seqs) >= 4096
     prof = CudaProfiles.new_with_w256([bytes(t) for t in targets], W, -10, -1, profiled_is_query=False)
     try:
         runs = {}

@@ -682,7 +682,12 @@ int stage_device(zoe_cuda_ctx *ctx, Device &d, const uint8_t *concat, const uint
                                                                                          d.n_count + 1, b0);
         CU(ctx, cudaGetLastError());
     }
-    split = split && d.rseq_bytes >= ((uint64_t)8 << 20) && d.n_count >= 4096 && !getenv("ZOE_CUDA_NO_SPLIT_UPLOAD");
+    // Only for shards of 64 MB and more: a 19-MB shard (125 k reads, one of eight) is uploaded in 0.4 ms, and splitting its
+    // first kernel into a full-width trip plus a second launch costs more than that (end to end 9.70 ms split, 9.36 ms
+    // single upload with one trip-balanced launch); at 150 MB the split gains 1.4 ms.  ZOE_CUDA_SPLIT_UPLOAD_MIN_MB: tests.
+    uint64_t split_min_mb = 64;
+    if (const char *e = getenv("ZOE_CUDA_SPLIT_UPLOAD_MIN_MB")) split_min_mb = (uint64_t)std::max(atoi(e), 1);
+    split = split && d.rseq_bytes >= (split_min_mb << 20) && d.n_count >= 4096 && !getenv("ZOE_CUDA_NO_SPLIT_UPLOAD");
     if (split) {
         if (!d.copy_stream) {
             CU(ctx, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
